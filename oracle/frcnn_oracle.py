@@ -1,0 +1,418 @@
+"""CPU oracle for the Faster R-CNN forward detection path of mitmul/chainer-faster-rcnn.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+module; the product path (``chainer-faster-rcnn_b200/``) never does.
+
+Every function restates one reference function and cites it (paths relative to
+/root/reference).  Integer / index / box arithmetic is restated exactly (float32,
+same operation order); dense contractions use torch CPU fp32 as the stand-in for
+the UN-VENDORED Chainer functions (L.Convolution2D, L.Linear, F.MaxPooling2D,
+F.softmax, F.roi_pooling_2d -- Chainer "1.22.0+", README.md:13, absent here).
+
+Parity status
+-------------
+* PINNED against the reference itself (tests/golden, made by
+  tests/golden/make_golden.py which imports the reference's own modules and its
+  compiled cpu_nms.pyx): generate_anchors, _generate_all_bbox,
+  bbox_transform_inv, clip_boxes, filter_boxes, cpu_nms, ProposalLayer.__call__.
+* UNPINNED ("parity unpinned", no reference test or golden vector exists and
+  Chainer cannot be installed): conv / linear / max-pool / softmax / roi-pool.
+  Those follow the published Chainer-v1 / Caffe semantics and are cross-checked
+  against torch / torchvision CPU implementations only.
+
+Two deliberate, documented deviations from "whatever NumPy happens to do":
+* exp: `orc_expf` (oracle_c.c) -- a fixed IEEE-754 operation sequence, < 2 ulp
+  from numpy's float32 exp, so that device and oracle agree bit-for-bit on any host.
+* sort ties: score descending, then LOWER original index first.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+_LIB = None
+
+f32 = np.float32
+
+
+def build_c(force=False):
+    """Compile oracle_c.c -> oracle/_build/liboracle_c.so (gcc, no FMA contraction)."""
+    os.makedirs(_BUILD, exist_ok=True)
+    src = os.path.join(_HERE, "oracle_c.c")
+    out = os.path.join(_BUILD, "liboracle_c.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                               src, "-o", out, "-lm"])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build_c())
+        fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int)
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.orc_expf_array.argtypes = [fp, fp, ctypes.c_long]
+        L.orc_expf_array.restype = None
+        L.orc_argsort_desc.argtypes = [fp, ctypes.c_int, ip]
+        L.orc_argsort_desc.restype = None
+        L.orc_nms.argtypes = [fp, ctypes.c_int, ctypes.c_double, ip]
+        L.orc_nms.restype = ctypes.c_int
+        L.orc_roi_pool.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_float, fp]
+        L.orc_roi_pool.restype = None
+        L.orc_bbox_overlaps.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, dp]
+        L.orc_bbox_overlaps.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+# --------------------------------------------------------------------------- exp / sort
+def expf(x):
+    """Deterministic float32 exp (oracle_c.c orc_expf); stands in for xp.exp at
+    models/bbox_transform.py:62-63 and inside F.softmax."""
+    x = np.ascontiguousarray(x, dtype=f32)
+    y = np.empty_like(x)
+    _lib().orc_expf_array(_fp(x), _fp(y), x.size)
+    return y
+
+
+def argsort_desc(scores):
+    """`scores.argsort()[::-1]` (models/proposal_layer.py:158-165, models/cpu_nms.pyx:26)
+    with the build's tie rule: equal scores -> lower index first."""
+    s = np.ascontiguousarray(scores, dtype=f32).ravel()
+    order = np.empty(s.size, dtype=np.int32)
+    _lib().orc_argsort_desc(_fp(s), s.size, _ip(order))
+    return order.astype(np.int64)
+
+
+# --------------------------------------------------------------------------- anchors
+def generate_anchors(base_size=15, ratios=(0.5, 1, 2), scales=(4, 8, 16, 32)):
+    """models/generate_anchors.py:47-93 restated (float64).  For every ratio: a box of
+    the same area as the (0,0,base,base) window with rint-rounded sides
+    (:76-84); then for every scale the sides are multiplied (:87-93); boxes are
+    centred on the window centre (:58-73).  Known answer: SURVEY.md Q9."""
+    w = h = base_size + 1.0                      # _whctrs on [0,0,base,base]   (:58-64)
+    cx = cy = 0.5 * (w - 1.0)
+    out = []
+    for r in np.asarray(ratios, dtype=np.float64):
+        ws = np.rint(np.sqrt(w * h / r))         # _ratio_enum                  (:76-84)
+        hs = np.rint(ws * r)
+        for s in np.asarray(scales, dtype=np.float64):
+            W, H = ws * s, hs * s                # _scale_enum                  (:87-93)
+            out.append([cx - 0.5 * (W - 1), cy - 0.5 * (H - 1),
+                        cx + 0.5 * (W - 1), cy + 0.5 * (H - 1)])   # _mkanchors (:67-73)
+    return np.asarray(out, dtype=np.float64)
+
+
+def all_anchor_boxes(feat_h, feat_w, feat_stride, anchors):
+    """ProposalLayer._generate_all_bbox (models/proposal_layer.py:207-221) + the float32
+    cast at :200-205.  Row (h*W + w)*A + a = anchors[a] + (w*s, h*s, w*s, h*s)."""
+    A = len(anchors)
+    sx = np.arange(feat_w, dtype=np.int64) * feat_stride
+    sy = np.arange(feat_h, dtype=np.int64) * feat_stride
+    gx, gy = np.meshgrid(sx, sy)
+    shifts = np.stack([gx.ravel(), gy.ravel(), gx.ravel(), gy.ravel()], axis=1)
+    boxes = anchors.reshape(1, A, 4) + shifts.reshape(-1, 1, 4)
+    return boxes.reshape(-1, 4).astype(f32)
+
+
+# --------------------------------------------------------------------------- box algebra
+def bbox_transform_inv(boxes, trans):
+    """models/bbox_transform.py:41-76, float32, one rounding per operation."""
+    boxes = np.asarray(boxes, dtype=f32)
+    trans = np.asarray(trans, dtype=f32)
+    if boxes.shape[0] == 0:                                   # :48-49
+        return np.zeros((0, trans.shape[1]), dtype=trans.dtype)
+    one, half = f32(1.0), f32(0.5)
+    w = boxes[:, 2] - boxes[:, 0] + one                       # :51
+    h = boxes[:, 3] - boxes[:, 1] + one                       # :52
+    cx = boxes[:, 0] + half * w                               # :53
+    cy = boxes[:, 1] + half * h                               # :54
+    dx, dy, dw, dh = trans[:, 0::4], trans[:, 1::4], trans[:, 2::4], trans[:, 3::4]  # :56-59
+    pcx = dx * w[:, None] + cx[:, None]                       # :61
+    pcy = dy * h[:, None] + cy[:, None]                       # :62
+    pw = expf(dw) * w[:, None]                                # :63
+    ph = expf(dh) * h[:, None]                                # :64
+    out = np.zeros(trans.shape, dtype=f32)                    # :66
+    out[:, 0::4] = pcx - half * pw                            # :68
+    out[:, 1::4] = pcy - half * ph                            # :70
+    out[:, 2::4] = pcx + half * pw                            # :72
+    out[:, 3::4] = pcy + half * ph                            # :74
+    return out
+
+
+def clip_boxes(boxes, im_shape):
+    """models/bbox_transform.py:79-99.  im_shape = (height, width) integers; in place."""
+    wmax = f32(int(im_shape[1] - 1))
+    hmax = f32(int(im_shape[0] - 1))
+    zero = f32(0)
+    boxes[:, 0::4] = np.maximum(np.minimum(boxes[:, 0::4], wmax), zero)
+    boxes[:, 1::4] = np.maximum(np.minimum(boxes[:, 1::4], hmax), zero)
+    boxes[:, 2::4] = np.maximum(np.minimum(boxes[:, 2::4], wmax), zero)
+    boxes[:, 3::4] = np.maximum(np.minimum(boxes[:, 3::4], hmax), zero)
+    return boxes
+
+
+def filter_boxes(boxes, min_size):
+    """models/bbox_transform.py:102-109."""
+    ws = boxes[:, 2] - boxes[:, 0] + f32(1)
+    hs = boxes[:, 3] - boxes[:, 1] + f32(1)
+    return np.where((ws >= min_size) & (hs >= min_size))[0]
+
+
+def keep_inside(anchors, img_info):
+    """models/bbox_transform.py:112-130 (train-only, "next")."""
+    idx = np.where((anchors[:, 0] >= 0) & (anchors[:, 1] >= 0) &
+                   (anchors[:, 2] < img_info[1]) & (anchors[:, 3] < img_info[0]))[0]
+    return idx, anchors[idx]
+
+
+# --------------------------------------------------------------------------- NMS
+def cpu_nms(dets, thresh):
+    """models/cpu_nms.pyx:18-69 (oracle_c.c orc_nms).  dets f32[N,5]; returns list[int]."""
+    d = np.ascontiguousarray(dets, dtype=f32)
+    n = d.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int32)
+    k = _lib().orc_nms(_fp(d), n, float(thresh), _ip(keep))
+    return [int(v) for v in keep[:k]]
+
+
+def bbox_overlaps(boxes, query):
+    """models/bbox.pyx:16-56 (float64)."""
+    b = np.ascontiguousarray(boxes, dtype=np.float64)
+    q = np.ascontiguousarray(query, dtype=np.float64)
+    out = np.zeros((b.shape[0], q.shape[0]), dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    _lib().orc_bbox_overlaps(b.ctypes.data_as(dp), b.shape[0], q.ctypes.data_as(dp), q.shape[0],
+                             out.ctypes.data_as(dp))
+    return out
+
+
+# --------------------------------------------------------------------------- ProposalLayer
+RPN_NMS_THRESH = 0.7                 # models/proposal_layer.py:51
+TRAIN_PRE, TRAIN_POST = 12000, 2000  # :52-53
+TEST_PRE, TEST_POST = 6000, 300      # :54-55
+RPN_MIN_SIZE = 16                    # :56
+
+
+def proposal_layer(rpn_cls_prob, rpn_bbox_pred, img_info, anchors=None, feat_stride=16,
+                   pre_nms_top_n=TEST_PRE, post_nms_top_n=TEST_POST,
+                   nms_thresh=RPN_NMS_THRESH, min_size=RPN_MIN_SIZE, debug=None):
+    """ProposalLayer.__call__ (models/proposal_layer.py:102-198).
+
+    rpn_cls_prob (1,2A,H,W) f32, rpn_bbox_pred (1,4A,H,W) f32, img_info (1,2) or (2,) ints
+    (height, width).  Returns proposals (R,4) f32, fg_probs (R,1) f32, R <= post_nms_top_n,
+    in descending-score order.  `debug` (dict) receives the pre-NMS sorted dets.
+    """
+    if anchors is None:
+        anchors = generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))  # :60-65
+    A = len(anchors)
+    prob = np.asarray(rpn_cls_prob, dtype=f32)[0]           # :129
+    pred = np.asarray(rpn_bbox_pred, dtype=f32)[0]          # :130
+    info = np.asarray(img_info).reshape(-1)[:2]             # :131
+    _, H, W = pred.shape
+    all_bbox = all_anchor_boxes(H, W, feat_stride, anchors)             # :135
+    trans = pred.transpose(1, 2, 0).reshape(-1, 4)                      # :138
+    props = bbox_transform_inv(all_bbox, trans)                         # :141
+    props = clip_boxes(props, info)                                     # :144
+    keep = filter_boxes(props, min_size)                                # :147
+    props = props[keep]                                                 # :148
+    fg = prob[A:].transpose(1, 2, 0).reshape(-1, 1)[keep]               # :152-154
+    order = argsort_desc(fg.ravel())                                    # :158-165
+    if pre_nms_top_n > 0:
+        order = order[:pre_nms_top_n]                                   # :167-168
+    props, fg = props[order], fg[order]                                 # :169-170
+    dets = np.hstack((props, fg)).astype(f32)                           # :178
+    if debug is not None:
+        debug["dets"] = dets.copy()
+        debug["anchor_index"] = keep[order]
+    k = cpu_nms(dets, nms_thresh)                                       # :178
+    if post_nms_top_n > 0:
+        k = k[:post_nms_top_n]                                          # :189-190
+    if debug is not None:
+        debug["keep"] = np.asarray(k, dtype=np.int64)
+    return props[k].reshape(-1, 4), fg[k].reshape(-1, 1)                # :192-198
+
+
+# --------------------------------------------------------------------------- dense ops (torch CPU fp32)
+def _t(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=f32))
+
+
+def conv2d(x, w, b, pad):
+    """L.Convolution2D(in, out, k, 1, pad) forward, fp32 (stand-in: torch CPU)."""
+    import torch
+    with torch.no_grad():
+        return torch.nn.functional.conv2d(_t(x), _t(w), None if b is None else _t(b),
+                                          stride=1, padding=pad).numpy()
+
+
+def linear(x, w, b):
+    import torch
+    with torch.no_grad():
+        return torch.nn.functional.linear(_t(x), _t(w), None if b is None else _t(b)).numpy()
+
+
+def relu(x):
+    return np.maximum(x, f32(0))
+
+
+def max_pool_2x2_ceil(x):
+    """F.MaxPooling2D(2, 2) -- Chainer default cover_all=True == ceil mode."""
+    import torch
+    with torch.no_grad():
+        return torch.nn.functional.max_pool2d(_t(x), 2, 2, ceil_mode=True).numpy()
+
+
+def softmax_axis1(x):
+    """F.softmax (axis=1), Chainer CPU algorithm: y = x - max; exp; / sum, float32.
+    exp is orc_expf; the sum runs over channels in ascending order."""
+    x = np.asarray(x, dtype=f32)
+    y = x - x.max(axis=1, keepdims=True)
+    e = expf(y).reshape(y.shape)
+    s = np.zeros(e.shape[:1] + (1,) + e.shape[2:], dtype=f32)
+    for c in range(e.shape[1]):
+        s[:, 0] = s[:, 0] + e[:, c]
+    return e / s
+
+
+VGG16_LAYERS = [  # models/vgg16.py:38-69
+    ("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool",
+    ("conv2_1", 64, 128), ("conv2_2", 128, 128), "pool",
+    ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), "pool",
+    ("conv4_1", 256, 512), ("conv4_2", 512, 512), ("conv4_3", 512, 512), "pool",
+    ("conv5_1", 512, 512), ("conv5_2", 512, 512), ("conv5_3", 512, 512),
+]
+
+
+def vgg16_forward(x, params, quant=None, stop_after=None):
+    """VGG16Prev.__call__ (models/vgg16.py:74-82): 13x [conv3x3 s1 p1 + bias, ReLU], ceil-mode
+    2x2 pools after conv1_2/2_2/3_3/4_3, returns post-ReLU conv5_3.  `quant`, if given, is
+    applied to every layer input and weight (used to build "identical inputs" for a
+    reduced-precision kernel mode)."""
+    q = (lambda a: a) if quant is None else quant
+    h = np.asarray(x, dtype=f32)
+    for item in VGG16_LAYERS:
+        if item == "pool":
+            h = max_pool_2x2_ceil(h)
+            continue
+        name = item[0]
+        h = relu(conv2d(q(h), q(params["trunk/%s/W" % name]), params["trunk/%s/b" % name], 1))
+        if stop_after == name:
+            break
+    return h
+
+
+def rpn_forward(feat, params, img_info, quant=None, **pl_kwargs):
+    """RegionProposalNetwork.__call__ inference part (models/region_proposal_network.py:117-124)."""
+    q = (lambda a: a) if quant is None else quant
+    h = relu(conv2d(q(feat), q(params["RPN/rpn_conv_3x3/W"]), params["RPN/rpn_conv_3x3/b"], 1))   # :117
+    score = conv2d(q(h), q(params["RPN/rpn_cls_score/W"]), params["RPN/rpn_cls_score/b"], 0)       # :118
+    prob = softmax_axis1(score)                                                                 # :119 (18-way, Q1)
+    pred = conv2d(q(h), q(params["RPN/rpn_bbox_pred/W"]), params["RPN/rpn_bbox_pred/b"], 0)        # :120
+    props, fg = proposal_layer(prob, pred, img_info, **pl_kwargs)                                # :123
+    return props, fg, prob, pred
+
+
+def roi_pool(feat, rois, outh=7, outw=7, scale=1.0 / 16):
+    """F.roi_pooling_2d(feature_map, brois, 7, 7, 1/16) (models/faster_rcnn.py:125-126);
+    oracle_c.c orc_roi_pool.  feat (1,C,H,W), rois (R,5) -> (R,C,outh,outw)."""
+    f = np.ascontiguousarray(feat, dtype=f32)[0]
+    r = np.ascontiguousarray(rois, dtype=f32)
+    C, H, W = f.shape
+    out = np.empty((r.shape[0], C, outh, outw), dtype=f32)
+    _lib().orc_roi_pool(_fp(f), C, H, W, _fp(r), r.shape[0], outh, outw, scale, _fp(out))
+    return out
+
+
+def head_forward(feat, proposals, params, img_info, quant=None):
+    """FasterRCNN.__call__ inference tail (models/faster_rcnn.py:122-134,175-178)."""
+    q = (lambda a: a) if quant is None else quant
+    R = len(proposals)
+    brois = np.concatenate((np.zeros((R, 1), dtype=f32), proposals.astype(f32)), axis=1)   # :123-124
+    pool5 = roi_pool(feat, brois, 7, 7, 1.0 / 16)                                           # :125-126
+    fc6 = relu(linear(q(pool5.reshape(R, -1)), q(params["fc6/W"]), params["fc6/b"]))        # :127
+    fc7 = relu(linear(q(fc6), q(params["fc7/W"]), params["fc7/b"]))                         # :128
+    cls_score = linear(q(fc7), q(params["cls_score/W"]), params["cls_score/b"])             # :131
+    bbox_pred = linear(q(fc7), q(params["bbox_pred/W"]), params["bbox_pred/b"])             # :134
+    info = np.asarray(img_info).reshape(-1)[:2]
+    pred_boxes = clip_boxes(bbox_transform_inv(proposals, bbox_pred), info)                 # :175-176
+    return softmax_axis1(cls_score), pred_boxes, dict(pool5=pool5, fc6=fc6, fc7=fc7,
+                                                      cls_score=cls_score, bbox_pred=bbox_pred)
+
+
+def faster_rcnn_forward(x, params, img_info, quant=None, **pl_kwargs):
+    """FasterRCNN.__call__ inference branch (models/faster_rcnn.py:92-134,175-178)."""
+    feat = vgg16_forward(x, params, quant)                                                   # :112
+    props, fg, prob, pred = rpn_forward(feat, params, img_info, quant, **pl_kwargs)          # :118
+    cls_prob, pred_boxes, aux = head_forward(feat, props, params, img_info, quant)
+    aux.update(feature_map=feat, proposals=props, fg_probs=fg, rpn_cls_prob=prob, rpn_bbox_pred=pred)
+    return cls_prob, pred_boxes, aux
+
+
+def detect(cls_prob, pred_boxes, nms_thresh=0.3, conf=0.8):
+    """draw_result's numeric part (forward.py:48-57): for every foreground class, greedy NMS
+    (cpu_nms, 0.3) over (R,5) dets, then `score >= conf`.  Returns a list of
+    (cls_id, keep_indices_after_conf, dets_after_conf)."""
+    out = []
+    for c in range(1, cls_prob.shape[1]):
+        dets = np.hstack((pred_boxes[:, 4 * c:4 * c + 4], cls_prob[:, c:c + 1])).astype(f32)
+        keep = np.asarray(cpu_nms(dets, nms_thresh), dtype=np.int64)
+        d = dets[keep]
+        sel = np.where(d[:, -1] >= conf)[0]
+        out.append((c, keep[sel], d[sel]))
+    return out
+
+
+# --------------------------------------------------------------------------- synthetic weights / inputs
+def make_params(seed=1234, num_classes=21, mid_ch=512, n_anchors=9, trunk_std="he"):
+    """Random-init parameters with the reference's names (SURVEY.md 5 checkpoint format).
+    Heads N(0, 0.01), zero bias (models/faster_rcnn.py:27,33-36; region_proposal_network.py:50-57).
+    Trunk: He-normal std=sqrt(2/(9*C_in)), zero bias (SURVEY.md 8d -- Chainer's own default
+    init is un-vendored; N(0,0.01) in the trunk would collapse activations into ties)."""
+    rng = np.random.default_rng(seed)
+    p = {}
+    for item in VGG16_LAYERS:
+        if item == "pool":
+            continue
+        name, cin, cout = item
+        std = np.sqrt(2.0 / (9 * cin)) if trunk_std == "he" else float(trunk_std)
+        p["trunk/%s/W" % name] = (rng.standard_normal((cout, cin, 3, 3)) * std).astype(f32)
+        p["trunk/%s/b" % name] = np.zeros(cout, dtype=f32)
+
+    def head(name, shape):
+        p[name + "/W"] = (rng.standard_normal(shape) * 0.01).astype(f32)
+        p[name + "/b"] = np.zeros(shape[0], dtype=f32)
+    head("RPN/rpn_conv_3x3", (mid_ch, 512, 3, 3))
+    head("RPN/rpn_cls_score", (2 * n_anchors, mid_ch, 1, 1))
+    head("RPN/rpn_bbox_pred", (4 * n_anchors, mid_ch, 1, 1))
+    head("fc6", (4096, 512 * 7 * 7))
+    head("fc7", (4096, 4096))
+    head("cls_score", (num_classes, 4096))
+    head("bbox_pred", (4 * num_classes, 4096))
+    return p
+
+
+PIXEL_MEANS = np.array([102.9801, 115.9465, 122.7717], dtype=np.float64)   # forward.py:22 (BGR)
+
+
+def make_image(h=600, w=1000, seed=0):
+    """Synthetic preprocessed image: uniform(0,255) - BGR means, (1,3,h,w) f32."""
+    rng = np.random.default_rng(seed)
+    img = rng.uniform(0, 255, size=(h, w, 3)) - PIXEL_MEANS
+    return img.transpose(2, 0, 1)[None].astype(f32)
