@@ -1,0 +1,444 @@
+// conv_gemm_sm100.cu -- implicit-GEMM 3x3 / 1x1 convolution (and plain GEMM) on 5th-gen tensor
+// cores: TMA -> 128B-swizzled shared memory -> tcgen05.mma (kind::f16, bf16 operands, fp32
+// accumulators in TMEM) -> tcgen05.ld epilogue with fused bias + ReLU (+ bf16 hi/lo split).
+//
+// Replaces, for the forward path: L.Convolution2D at /root/reference models/vgg16.py:39-67 and
+// models/region_proposal_network.py:53-57, and L.Linear at models/faster_rcnn.py:33-36.
+//
+// Mapping (NHWC activations, tap-major K-major weights):
+//   M = output pixels, tiled as TH x TW patches of 128 pixels;  N = output channels (BN per tile);
+//   K = taps x Cin, walked as (tap, 64-channel block) "k-blocks".
+//   The A operand of k-block (tap=(r,s), cb) is ONE 3-D TMA box {BK ch, TW, TH} of the input at
+//   spatial offset (r-1, s-1): out-of-bounds rows/columns are zero-filled by the TMA unit, which
+//   is exactly the conv's zero padding -- no im2col buffer, no halo handling in the kernel.
+//   The box lands in smem as 128 rows x 128 B, i.e. the canonical K-major SWIZZLE_128B UMMA tile.
+//
+// Kernel structure: persistent, one CTA per SM, 6 warps:
+//   warp 0    : TMA producer (one elected lane)         smem ring, full/empty mbarriers
+//   warp 1    : TMEM allocator + MMA issuer (one lane)  double-buffered accumulators in TMEM
+//   warps 2-5 : epilogue (TMEM lane group = warp % 4)   overlaps the next tile's main loop
+//
+// "bf16x3" mode (lo planes present): per k-block the stage holds A_hi, A_lo, B_hi, B_lo and the
+// issuer runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the same accumulator (fp32-class accuracy,
+// 3x the tensor work, 1.33x the smem bytes of the single-pass mode).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace frcnn {
+
+struct ConvParams {
+    int H, W, Cout;
+    int taps, ksize, cin_blocks;
+    int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
+    int num_stages, x3, relu;
+    int ld_f32, n_cover;
+    __nv_bfloat16* y_hi;
+    __nv_bfloat16* y_lo;
+    float* y_f32;
+    const float* bias;
+    const int* m_valid;
+};
+
+constexpr int kNumThreads = 192;
+constexpr int kTileM = 128;
+
+template <int BN, int BK>
+struct Cfg {
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_BYTES = kTileM * ROW_BYTES;
+    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const ConvParams p) {
+    using C = Cfg<BN, BK>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-B alignment required by SWIZZLE_128B tiles.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
+    const int S = p.num_stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full_bar = bars;            // [S]
+    uint64_t* empty_bar = bars + S;       // [S]
+    uint64_t* tfull_bar = bars + 2 * S;   // [2]
+    uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a_hi);
+        ptx::prefetch_tensormap(&tm_b_hi);
+        if (p.x3) {
+            ptx::prefetch_tensormap(&tm_a_lo);
+            ptx::prefetch_tensormap(&tm_b_lo);
+        }
+        for (int i = 0; i < S; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_kb = p.taps * p.cin_blocks;
+    const int pad = (p.ksize - 1) / 2;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int mt = tile / p.n_tiles;
+                const int h0 = (mt / p.tiles_w) * p.TH;
+                const int w0 = (mt % p.tiles_w) * p.TW;
+                const int n0 = nt * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / p.cin_blocks;
+                    const int cb = kb - tap * p.cin_blocks;
+                    const int r = tap / p.ksize, s = tap - r * p.ksize;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * stage_bytes;
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    ptx::tma_load_3d(st, &tm_a_hi, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
+                    ptx::tma_load_3d(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
+                    if (p.x3) {
+                        uint8_t* st2 = st + C::A_BYTES + C::B_BYTES;
+                        ptx::tma_load_3d(st2, &tm_a_lo, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
+                        ptx::tma_load_3d(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, /*bf16*/ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t st = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t a_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
+                    const uint64_t b_hi = ptx::make_smem_desc(st + C::A_BYTES, C::ROW_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the swizzle span: +2 in (addr>>4)
+                        ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (p.x3) {
+                        const uint64_t a_lo = ptx::make_smem_desc(st + C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
+                        const uint64_t b_lo = ptx::make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+                    if (kb == num_kb - 1) ptx::mma_commit(&tfull_bar[acc]);   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int lg = warp & 3;                 // TMEM lane group this warp may access
+        const int row = lg * 32 + lane;          // accumulator row == pixel within the tile
+        const int m_valid = p.m_valid ? *p.m_valid : 0x7fffffff;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int mt = tile / p.n_tiles;
+            const int h = (mt / p.tiles_w) * p.TH + row / p.TW;
+            const int w = (mt % p.tiles_w) * p.TW + row % p.TW;
+            const int n0 = nt * BN;
+            const bool in_img = (h < p.H) && (w < p.W);
+            const long pix = (long)h * p.W + w;
+            const bool live = in_img && pix < m_valid;
+
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.n_cover) break;   // warp-uniform: nothing is stored past the covered columns
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                ptx::tmem_ld_wait();
+                const int n = n0 + c0;
+                float v[32];
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(b4 + j);
+                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                }
+                if (!live) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+                }
+                if (in_img) {
+                    if (p.y_f32 != nullptr && n < p.ld_f32) {
+                        float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.ld_f32 + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (p.y_hi != nullptr && n < p.Cout) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(v[2 * j], h0, l0);
+                            split_bf16(v[2 * j + 1], h1, l1);
+                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.Cout + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (p.y_lo != nullptr) {
+                            uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.Cout + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    // Resolved through the runtime so the library has no link-time dependency on libcuda.so
+    // (it must dlopen on a CPU-only box for the symbol/ABI tests).
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 3-D bf16 tensor map: dims (innermost first) {d0,d1,d2}, row pitch d0 elements, box {b0,b1,b2}.
+static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                        uint32_t b1, uint32_t b2) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return FRCNN_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapSwizzle sw = (b0 * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                                            : (b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims {%llu,%llu,%llu} box {%u,%u,%u} base %p", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2, base);
+        return FRCNN_ERR_CUDA;
+    }
+    return FRCNN_OK;
+}
+
+static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0;
+
+static int device_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int BN, int BK>
+static int launch_conv(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                       const CUtensorMap& tb_lo, ConvParams p, cudaStream_t stream) {
+    using C = Cfg<BN, BK>;
+    const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+    int stages = budget / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) {
+        set_error("conv tile BN=%d BK=%d does not fit 2 pipeline stages", BN, BK);
+        return FRCNN_ERR_ARG;
+    }
+    p.num_stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    auto kern = conv_gemm_kernel<BN, BK>;
+    FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    kern<<<grid, kNumThreads, smem, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
+    g_force_bn = block_n;
+    g_force_th = tile_h;
+    g_force_tw = tile_w;
+}
+
+extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
+                            const void* w_lo, const float* bias, int Cout, int ksize, int relu, void* y_hi,
+                            void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    FRCNN_REQUIRE(x_hi && w_hi && bias, "frcnn_conv2d: x_hi, w_hi and bias are required");
+    FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
+    FRCNN_REQUIRE(ksize == 1 || ksize == 3, "frcnn_conv2d: ksize must be 1 or 3 (got %d)", ksize);
+    FRCNN_REQUIRE(H > 0 && W > 0 && Cin > 0 && Cout > 0, "frcnn_conv2d: bad shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
+    FRCNN_REQUIRE(Cin % 8 == 0, "frcnn_conv2d: Cin must be a multiple of 8 (16-byte TMA rows), got %d", Cin);
+    FRCNN_REQUIRE(y_hi || y_f32, "frcnn_conv2d: no output requested");
+    FRCNN_REQUIRE(!y_hi || Cout % 32 == 0, "frcnn_conv2d: bf16 output needs Cout %% 32 == 0 (got %d)", Cout);
+    FRCNN_REQUIRE(!y_f32 || (ld_f32 % 32 == 0 && ld_f32 >= Cout), "frcnn_conv2d: ld_f32 must be a multiple of 32 and >= Cout");
+    FRCNN_REQUIRE(!y_lo || y_hi, "frcnn_conv2d: y_lo without y_hi");
+
+    const int BK = (Cin >= 64) ? 64 : (Cin >= 32 ? 32 : 16);
+    FRCNN_REQUIRE(BK != 32, "frcnn_conv2d: Cin in [32,64) is not supported (use 16 or >= 64)");
+
+    // ---- pixel tile: minimise padded pixels
+    static const int shapes[6][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
+    int TH = 8, TW = 16;
+    if (g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM) {
+        TH = g_force_th;
+        TW = g_force_tw;
+    } else {
+        long best = -1;
+        for (auto& s : shapes) {
+            long t = (long)cdiv(H, s[0]) * cdiv(W, s[1]);
+            if (best < 0 || t < best) { best = t; TH = s[0]; TW = s[1]; }
+        }
+    }
+    const int tiles_h = cdiv(H, TH), tiles_w = cdiv(W, TW);
+    const long m_tiles = (long)tiles_h * tiles_w;
+
+    // ---- N tile: minimise waves x per-k-step cost (N=64 is smem-bandwidth bound: 48 vs 32 cycles)
+    const int cout_cover = y_f32 ? (ld_f32 > Cout ? ld_f32 : Cout) : Cout;
+    int BN = 0;
+    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) {
+        BN = g_force_bn;
+    } else {
+        const int sms = device_sm_count();
+        double best = 0;
+        const int cand[3] = {256, 128, 64};
+        const double cost[3] = {128, 64, 48};
+        for (int i = 0; i < 3; ++i) {
+            if (cand[i] > 64 && cand[i] > cout_cover && cand[i] / 2 >= cout_cover) continue;  // too wide
+            long tiles = m_tiles * cdiv(cout_cover, cand[i]);
+            double t = (double)cdiv((int)tiles, sms) * cost[i];
+            if (BN == 0 || t < best) { best = t; BN = cand[i]; }
+        }
+    }
+
+    ConvParams p;
+    p.H = H; p.W = W; p.Cout = Cout;
+    p.ksize = ksize; p.taps = ksize * ksize; p.cin_blocks = cdiv(Cin, BK);
+    p.TH = TH; p.TW = TW; p.tiles_h = tiles_h; p.tiles_w = tiles_w;
+    p.n_tiles = cdiv(cout_cover, BN);
+    FRCNN_REQUIRE(m_tiles * p.n_tiles < (1l << 30), "frcnn_conv2d: too many tiles");
+    p.num_tiles = (int)(m_tiles * p.n_tiles);
+    p.num_stages = 0;
+    p.x3 = x_lo != nullptr;
+    p.relu = relu;
+    p.ld_f32 = ld_f32;
+    p.n_cover = cdiv(cout_cover, 32) * 32;
+    p.y_hi = static_cast<__nv_bfloat16*>(y_hi);
+    p.y_lo = static_cast<__nv_bfloat16*>(y_lo);
+    p.y_f32 = y_f32;
+    p.bias = bias;
+    p.m_valid = m_valid;
+
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int rc;
+    if ((rc = make_tmap_3d(&ta_hi, x_hi, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+    if ((rc = make_tmap_3d(&tb_hi, w_hi, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+    if (p.x3) {
+        if ((rc = make_tmap_3d(&ta_lo, x_lo, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tb_lo, w_lo, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+    } else {
+        ta_lo = ta_hi;
+        tb_lo = tb_hi;
+    }
+
+#define FRCNN_DISPATCH(BN_, BK_) \
+    if (BN == BN_ && BK == BK_) return launch_conv<BN_, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, p, stream);
+    FRCNN_DISPATCH(256, 64)
+    FRCNN_DISPATCH(128, 64)
+    FRCNN_DISPATCH(64, 64)
+    FRCNN_DISPATCH(256, 16)
+    FRCNN_DISPATCH(128, 16)
+    FRCNN_DISPATCH(64, 16)
+#undef FRCNN_DISPATCH
+    set_error("frcnn_conv2d: no kernel for BN=%d BK=%d", BN, BK);
+    return FRCNN_ERR_ARG;
+}

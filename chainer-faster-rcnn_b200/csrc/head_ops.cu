@@ -1,0 +1,391 @@
+// head_ops.cu -- the memory-bound kernels around the dense contractions:
+//   frcnn_pack_image / frcnn_pack_conv_weights / frcnn_unpack_nhwc : layout + bf16 hi/lo conversion
+//   frcnn_maxpool2x2_ceil : F.MaxPooling2D(2,2) ceil mode        (/root/reference models/vgg16.py:43,48,55,62)
+//   frcnn_roi_pool        : F.roi_pooling_2d(.., 7, 7, 1/16)     (models/faster_rcnn.py:123-126)
+//   frcnn_head_decode     : softmax + per-class decode + clip    (models/faster_rcnn.py:175-178)
+//   frcnn_detect          : per-class NMS + confidence filter    (forward.py:48-57)
+// All are HBM/L2-bound: 16-byte vector accesses along the channel axis (NHWC), grids sized to
+// cover the tensor with >= 2 waves of 148 SMs where the tensor is large enough.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace frcnn {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// 8 consecutive channels as bf16 hi (+lo) <-> 8 floats
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long off) {
+    F8 r;
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        r.v[2 * j] = __uint_as_float(hw[j] << 16);
+        r.v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u);
+    }
+    if (lo) {
+        const uint4 l = *reinterpret_cast<const uint4*>(lo + off);
+        const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            r.v[2 * j] += __uint_as_float(lw[j] << 16);          // exact: hi+lo has <= 24 significant bits
+            r.v[2 * j + 1] += __uint_as_float(lw[j] & 0xFFFF0000u);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, long off, const F8& r) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(r.v[2 * j], h0, l0);
+        split_bf16(r.v[2 * j + 1], h1, l1);
+        hw[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// ------------------------------------------------------------------------------------------ pack / unpack
+__global__ void pack_image_kernel(const float* x, int C, int H, int W, int Cp, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long total = (long)H * W * Cp;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp);
+        const long p = i / Cp;
+        const float v = c < C ? x[(long)c * H * W + p] : 0.0f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+__global__ void pack_weights_kernel(const float* w, int Cout, int Cin, int taps, int Cp, __nv_bfloat16* hi,
+                                    __nv_bfloat16* lo, int perm, int pc, int ph, int pw) {
+    // dst [tap][o][c'] ; src OIHW: w[(o*Cin + c)*taps + tap]
+    const long total = (long)taps * Cout * Cp;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int cdst = (int)(i % Cp);
+        const long t = i / Cp;
+        const int o = (int)(t % Cout);
+        const int tap = (int)(t / Cout);
+        float v = 0.0f;
+        if (cdst < Cin) {
+            int csrc = cdst;
+            if (perm) {     // dst K order (h,w,c)  <-  src K order (c,h,w)
+                const int c = cdst % pc, hw = cdst / pc;
+                csrc = c * (ph * pw) + hw;
+            }
+            v = w[((long)o * Cin + csrc) * taps + tap];
+        }
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+__global__ void unpack_nhwc_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int H, int W, int C, float* y) {
+    const long total = (long)H * W * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long p = i / C;
+        float v = __bfloat162float(hi[i]);
+        if (lo) v += __bfloat162float(lo[i]);
+        y[(long)c * H * W + p] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ max-pool 2x2/2 ceil
+__global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int H, int W, int C,
+                               __nv_bfloat16* yh, __nv_bfloat16* yl) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C8 = C / 8;
+    const long total = (long)Ho * Wo * C8;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const long p = i / C8;
+        const int wo = (int)(p % Wo), ho = (int)(p / Wo);
+        F8 m;
+        bool first = true;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int h = 2 * ho + dy, w = 2 * wo + dx;
+                if (h < H && w < W) {       // ceil mode: partial windows use the valid elements only
+                    const F8 v = load8(xh, xl, ((long)h * W + w) * C + 8 * c8);
+                    if (first) { m = v; first = false; }
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) m.v[j] = fmaxf(m.v[j], v.v[j]);
+                    }
+                }
+            }
+        store8(yh, yl, ((long)ho * Wo + wo) * C + 8 * c8, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ RoI max pooling
+// One thread per (roi, bin, 8 channels).  Caffe / Chainer-v1 GPU semantics (see the oracle's
+// orc_roi_pool): round() half away from zero, float32 bin sizes, empty bin -> 0.
+__global__ void roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl, int H, int W, int C,
+                                const float* rois, const int* count, int R_cap, int PH, int PW, float scale,
+                                __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32) {
+    const int C8 = C / 8;
+    const long total = (long)R_cap * PH * PW * C8;
+    const int R = count ? min(*count, R_cap) : R_cap;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long t = i / C8;
+        const int pw = (int)(t % PW); t /= PW;
+        const int ph = (int)(t % PH);
+        const int r = (int)(t / PH);
+        F8 m;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m.v[j] = 0.0f;
+        if (r < R) {
+            const float4 roi = reinterpret_cast<const float4*>(rois)[r];
+            const int sw = (int)roundf(__fmul_rn(roi.x, scale)), sh = (int)roundf(__fmul_rn(roi.y, scale));
+            const int ew = (int)roundf(__fmul_rn(roi.z, scale)), eh = (int)roundf(__fmul_rn(roi.w, scale));
+            const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+            const float bh = __fdiv_rn((float)rh, (float)PH), bw = __fdiv_rn((float)rw, (float)PW);
+            int hs = (int)floorf(__fmul_rn((float)ph, bh)) + sh, he = (int)ceilf(__fmul_rn((float)(ph + 1), bh)) + sh;
+            int ws = (int)floorf(__fmul_rn((float)pw, bw)) + sw, we = (int)ceilf(__fmul_rn((float)(pw + 1), bw)) + sw;
+            hs = min(max(hs, 0), H); he = min(max(he, 0), H);
+            ws = min(max(ws, 0), W); we = min(max(we, 0), W);
+            if (he > hs && we > ws) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m.v[j] = -1e37f;
+                for (int y = hs; y < he; ++y)
+                    for (int x = ws; x < we; ++x) {
+                        const F8 v = load8(fh, fl, ((long)y * W + x) * C + 8 * c8);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) m.v[j] = v.v[j] > m.v[j] ? v.v[j] : m.v[j];
+                    }
+            }
+        }
+        const long off = (((long)r * PH + ph) * PW + pw) * C + 8 * c8;
+        if (oh) store8(oh, ol, off, m);
+        if (of32) {
+            float4* d = reinterpret_cast<float4*>(of32 + off);
+            d[0] = make_float4(m.v[0], m.v[1], m.v[2], m.v[3]);
+            d[1] = make_float4(m.v[4], m.v[5], m.v[6], m.v[7]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ head decode
+// One thread per (roi, class): softmax over classes (every thread recomputes max/sum of its row --
+// 21 values, L1-resident) and bbox_transform_inv + clip_boxes for its class's 4 deltas.
+__global__ void head_decode_kernel(const float* scores, const float* deltas, int ld, const float* rois,
+                                   const int* count, int R_cap, int NC, int im_h, int im_w, float* prob,
+                                   float* boxes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R_cap * NC) return;
+    const int r = i / NC, c = i - r * NC;
+    const int R = count ? min(*count, R_cap) : R_cap;
+    float p = 0.0f;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R) {
+        const float* s = scores + (long)r * ld;
+        float m = s[0];
+        for (int k = 1; k < NC; ++k) m = fmaxf(m, s[k]);
+        float sum = 0.0f, mine = 0.0f;
+        for (int k = 0; k < NC; ++k) {
+            const float e = det_expf(__fsub_rn(s[k], m));
+            sum = __fadd_rn(sum, e);
+            if (k == c) mine = e;
+        }
+        p = __fdiv_rn(mine, sum);
+        const float4 a = reinterpret_cast<const float4*>(rois)[r];
+        const float* d = deltas + (long)r * ld + 4 * c;
+        const float bw = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), bh = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+        const float cx = __fadd_rn(a.x, __fmul_rn(0.5f, bw)), cy = __fadd_rn(a.y, __fmul_rn(0.5f, bh));
+        const float pcx = __fadd_rn(__fmul_rn(d[0], bw), cx), pcy = __fadd_rn(__fmul_rn(d[1], bh), cy);
+        const float pw = __fmul_rn(det_expf(d[2]), bw), ph = __fmul_rn(det_expf(d[3]), bh);
+        const float wmax = (float)(im_w - 1), hmax = (float)(im_h - 1);
+        box.x = fmaxf(fminf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), wmax), 0.0f);
+        box.y = fmaxf(fminf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), hmax), 0.0f);
+        box.z = fmaxf(fminf(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), wmax), 0.0f);
+        box.w = fmaxf(fminf(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), hmax), 0.0f);
+    }
+    prob[i] = p;
+    reinterpret_cast<float4*>(boxes)[i] = box;
+}
+
+// ------------------------------------------------------------------------------------------ per-class detection
+// One CTA per foreground class.  R <= 2048 rows.  Rank-by-counting sort (score desc, index asc),
+// then greedy suppression with a survivor list in shared memory: a candidate is tested against the
+// survivors only (<= R*R/2 IoUs worst case, R = 300: 45k -- trivial), exact cpu_nms semantics.
+constexpr int kDetThreads = 256;
+constexpr int kDetMaxR = 2048;
+
+__device__ __forceinline__ float det_iou(const float4 a, const float4 b) {
+    const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+    const float area_b = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+    const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+__global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, const float* boxes, const int* count,
+                                                             int R_cap, int NC, double thr, float conf,
+                                                             int* keep_idx, int* keep_count, int* conf_count) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int R = count ? min(*count, R_cap) : R_cap;
+    float4* sbox = reinterpret_cast<float4*>(dsm);                   // [R_cap] boxes by rank
+    float* sc = reinterpret_cast<float*>(sbox + R_cap);              // [R_cap] scores by roi
+    int* order = reinterpret_cast<int*>(sc + R_cap);                 // [R_cap] roi index by rank
+    unsigned char* dead = reinterpret_cast<unsigned char*>(order + R_cap);  // [R_cap] by rank
+    __shared__ int s_nconf;
+    const int cls = blockIdx.x + 1, tid = threadIdx.x;
+    for (int r = tid; r < R; r += kDetThreads) sc[r] = prob[(long)r * NC + cls];
+    if (tid == 0) s_nconf = 0;
+    __syncthreads();
+    for (int r = tid; r < R; r += kDetThreads) {
+        const float s = sc[r];
+        int rank = 0;
+        for (int q = 0; q < R; ++q) {
+            const float t = sc[q];
+            rank += (t > s) || (t == s && q < r);
+        }
+        order[rank] = r;
+        sbox[rank] = reinterpret_cast<const float4*>(boxes)[(long)r * NC + cls];
+        dead[rank] = 0;
+    }
+    __syncthreads();
+    // greedy pass: for pivot i (ascending rank), all threads mark later candidates it suppresses
+    int nk = 0;
+    for (int i = 0; i < R; ++i) {
+        if (dead[i]) { continue; }          // uniform: dead[] is only written before a barrier
+        const float4 a = sbox[i];
+        if (tid == 0) {
+            keep_idx[(long)(cls - 1) * R_cap + nk] = order[i];
+            if (sc[order[i]] >= conf) s_nconf = nk + 1;
+        }
+        ++nk;
+        for (int j = i + 1 + tid; j < R; j += kDetThreads) {
+            if (!dead[j] && (double)det_iou(a, sbox[j]) >= thr) dead[j] = 1;
+        }
+        __syncthreads();
+    }
+    for (int k = nk + tid; k < R_cap; k += kDetThreads) keep_idx[(long)(cls - 1) * R_cap + k] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        keep_count[cls - 1] = nk;
+        conf_count[cls - 1] = s_nconf;
+    }
+}
+
+static int grid_for(long total, int block) {
+    long g = (total + block - 1) / block;
+    const long cap = 148l * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+extern "C" int frcnn_version(void) { return 100; }
+extern "C" const char* frcnn_last_error(void) { return g_err; }
+
+extern "C" int frcnn_pack_image(const float* x_chw, int C, int H, int W, int C_pad, void* y_hi, void* y_lo,
+                                void* stream) {
+    FRCNN_REQUIRE(x_chw && y_hi && C > 0 && H > 0 && W > 0 && C_pad >= C && C_pad % 8 == 0,
+                  "frcnn_pack_image: bad arguments (C=%d H=%d W=%d C_pad=%d)", C, H, W, C_pad);
+    const long total = (long)H * W * C_pad;
+    pack_image_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x_chw, C, H, W, C_pad, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, int kh, int kw, int Cin_pad, void* w_hi,
+                                       void* w_lo, int perm_chw_to_hwc, int pc, int ph, int pw, void* stream) {
+    FRCNN_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && Cin_pad >= Cin && Cin_pad % 8 == 0,
+                  "frcnn_pack_conv_weights: bad arguments");
+    FRCNN_REQUIRE(!perm_chw_to_hwc || (pc * ph * pw == Cin && Cin_pad == Cin),
+                  "frcnn_pack_conv_weights: permutation needs pc*ph*pw == Cin == Cin_pad");
+    const long total = (long)kh * kw * Cout * Cin_pad;
+    pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        w_oihw, Cout, Cin, kh * kw, Cin_pad, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, perm_chw_to_hwc, pc, ph, pw);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_unpack_nhwc(const void* x_hi, const void* x_lo, int H, int W, int C, float* y_chw, void* stream) {
+    FRCNN_REQUIRE(x_hi && y_chw && H > 0 && W > 0 && C > 0, "frcnn_unpack_nhwc: bad arguments");
+    const long total = (long)H * W * C;
+    unpack_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, H, W, C, y_chw);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_maxpool2x2_ceil(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo,
+                                     void* stream) {
+    FRCNN_REQUIRE(x_hi && y_hi && H > 0 && W > 0 && C > 0 && C % 8 == 0, "frcnn_maxpool2x2_ceil: bad arguments (C=%d)", C);
+    FRCNN_REQUIRE((x_lo == nullptr) == (y_lo == nullptr), "frcnn_maxpool2x2_ceil: lo planes must both be given or both NULL");
+    const long total = (long)((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+    maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, H, W, C, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois,
+                              const int* count, int R_cap, int outh, int outw, float scale, void* out_hi, void* out_lo,
+                              float* out_f32, void* stream) {
+    FRCNN_REQUIRE(feat_hi && rois && (out_hi || out_f32) && H > 0 && W > 0 && C > 0 && C % 8 == 0 && R_cap > 0 &&
+                      outh > 0 && outw > 0,
+                  "frcnn_roi_pool: bad arguments");
+    FRCNN_REQUIRE(!out_lo || out_hi, "frcnn_roi_pool: out_lo without out_hi");
+    const long total = (long)R_cap * outh * outw * (C / 8);
+    roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)feat_hi, (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw, scale,
+        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_head_decode(const float* scores, const float* deltas, int ld, const float* rois, const int* count,
+                                 int R_cap, int num_classes, int im_h, int im_w, float* out_prob, float* out_boxes,
+                                 void* stream) {
+    FRCNN_REQUIRE(scores && deltas && rois && out_prob && out_boxes && R_cap > 0 && num_classes > 0 && ld >= num_classes,
+                  "frcnn_head_decode: bad arguments");
+    const int total = R_cap * num_classes;
+    head_decode_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(scores, deltas, ld, rois, count, R_cap,
+                                                                          num_classes, im_h, im_w, out_prob, out_boxes);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_cap, int num_classes,
+                            double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count,
+                            void* stream) {
+    FRCNN_REQUIRE(prob && boxes && keep_idx && keep_count && conf_count && num_classes > 1, "frcnn_detect: bad arguments");
+    FRCNN_REQUIRE(R_cap > 0 && R_cap <= kDetMaxR, "frcnn_detect: R_cap must be in [1,%d] (got %d)", kDetMaxR, R_cap);
+    const size_t smem = (size_t)R_cap * (sizeof(float) + sizeof(int) + sizeof(float4) + 1) + 16;
+    FRCNN_CUDA_OK(cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    detect_kernel<<<num_classes - 1, kDetThreads, smem, (cudaStream_t)stream>>>(prob, boxes, count, R_cap, num_classes,
+                                                                                nms_thresh, conf, keep_idx, keep_count,
+                                                                                conf_count);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}

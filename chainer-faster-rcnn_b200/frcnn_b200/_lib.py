@@ -1,0 +1,80 @@
+"""ctypes binding of libfrcnn_b200.so (the C ABI declared in include/frcnn_b200.h).
+
+There is NO fallback: if the shared library is missing the import raises with build
+instructions; if a call fails the Python wrapper raises FrcnnError with the library's message.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfrcnn_b200.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3
+NMS_GE_DOUBLE, NMS_GT_FLOAT = 0, 1
+
+
+class FrcnnError(RuntimeError):
+    pass
+
+
+c_void_p, c_int, c_long, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t
+c_double, c_float, c_char_p = ctypes.c_double, ctypes.c_float, ctypes.c_char_p
+
+# name -> (restype, argtypes): mirrors include/frcnn_b200.h one to one.
+SIGNATURES = {
+    "frcnn_version": (c_int, []),
+    "frcnn_last_error": (c_char_p, []),
+    "_nms": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int]),
+    "frcnn_cpu_nms_host": (c_int, [c_void_p, c_int, c_double, c_void_p, c_int]),
+    "frcnn_nms_workspace_bytes": (c_size_t, [c_int]),
+    "frcnn_nms": (c_int, [c_void_p, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_proposals_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "frcnn_proposals": (c_int, [c_void_p, c_long, c_long, c_int, c_void_p, c_long, c_long, c_void_p,
+                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
+    "frcnn_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "frcnn_conv2d_set_tile": (None, [c_int, c_int, c_int]),
+    "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                        c_int, c_int, c_int, c_void_p]),
+    "frcnn_pack_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_unpack_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "frcnn_maxpool2x2_ceil": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_roi_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                               c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "frcnn_head_decode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p]),
+    "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and attach prototypes (works on a CPU-only box: no libcuda dependency)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FrcnnError(
+            "libfrcnn_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C chainer-faster-rcnn_b200/csrc` (needs nvcc; there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().frcnn_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status, what):
+    if status != OK:
+        raise FrcnnError("%s failed (status %d): %s" % (what, status, last_error()))

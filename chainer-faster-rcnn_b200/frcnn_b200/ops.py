@@ -1,0 +1,243 @@
+"""torch-tensor front end of the C ABI: PyTorch is only the device-memory / stream vehicle.
+
+Every function takes CUDA tensors, passes raw device pointers and the current torch stream to
+libfrcnn_b200.so, and returns tensors.  Nothing here computes on the CPU and nothing falls back
+to torch operators: a failing native call raises `FrcnnError`.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FrcnnError, check
+
+PRECISIONS = ("bf16x3", "bf16")
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FrcnnError("expected CUDA tensors (the library has no CPU path)")
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act(object):
+    """An NHWC activation: bf16 `hi` plane and optional `lo` plane (value = hi + lo)."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return tuple(self.hi.shape)
+
+    def to_chw_f32(self):
+        """(C,H,W) float32 view of the value, the reference's feature-map layout."""
+        H, W, C = self.hi.shape
+        out = torch.empty((C, H, W), dtype=torch.float32, device=self.hi.device)
+        check(_lib.load().frcnn_unpack_nhwc(_p(self.hi), _p(self.lo), H, W, C, _p(out), _stream()), "frcnn_unpack_nhwc")
+        return out
+
+
+def pack_image(x_chw, c_pad=16, precision="bf16x3"):
+    """(C,H,W) float32 CUDA image -> Act [H,W,c_pad]."""
+    _need_cuda(x_chw)
+    x = x_chw.contiguous().float()
+    C, H, W = x.shape
+    hi = torch.empty((H, W, c_pad), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if precision == "bf16x3" else None
+    check(_lib.load().frcnn_pack_image(_p(x), C, H, W, c_pad, _p(hi), _p(lo), _stream()), "frcnn_pack_image")
+    return Act(hi, lo)
+
+
+def pack_conv_weights(w, cin_pad=None, precision="bf16x3", perm_chw=None):
+    """OIHW (or (Cout, K)) float32 weights -> ([taps, Cout, cin_pad] bf16 hi, lo or None)."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    Cout, Cin, kh, kw = w.shape
+    cin_pad = cin_pad or round_up(Cin, 8)
+    hi = torch.empty((kh * kw, Cout, cin_pad), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if precision == "bf16x3" else None
+    pc, ph, pw = perm_chw if perm_chw else (0, 0, 0)
+    check(_lib.load().frcnn_pack_conv_weights(_p(w), Cout, Cin, kh, kw, cin_pad, _p(hi), _p(lo),
+                                              1 if perm_chw else 0, pc, ph, pw, _stream()), "frcnn_pack_conv_weights")
+    return hi, lo
+
+
+def pad_bias(b, n):
+    out = torch.zeros(round_up(max(n, b.numel()), 32), dtype=torch.float32, device=b.device)
+    out[: b.numel()] = b.float()
+    return out
+
+
+def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=None, out=None, out_f32=None):
+    """frcnn_conv2d: x Act [H,W,Cin]; returns (Act or None, fp32 [H*W, ld_f32] or None)."""
+    H, W, Cin = x.hi.shape
+    taps, Cout, cin_w = w_hi.shape
+    if cin_w != Cin or taps != ksize * ksize:
+        raise FrcnnError("conv2d: weight shape %s does not match input channels %d / ksize %d" % (tuple(w_hi.shape), Cin, ksize))
+    if (x.lo is None) != (w_lo is None):
+        raise FrcnnError("conv2d: activation and weight precision modes differ")
+    y = out
+    if out_act and y is None:
+        yh = torch.empty((H, W, Cout), dtype=torch.bfloat16, device=x.hi.device)
+        y = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    y32 = out_f32
+    if ld_f32 and y32 is None:
+        y32 = torch.empty((H * W, ld_f32), dtype=torch.float32, device=x.hi.device)
+    need = round_up(max(Cout, ld_f32), 32)
+    if bias.numel() < need:
+        raise FrcnnError("conv2d: bias has %d entries, needs %d (use pad_bias)" % (bias.numel(), need))
+    check(_lib.load().frcnn_conv2d(_p(x.hi), _p(x.lo), H, W, Cin, _p(w_hi), _p(w_lo), _p(bias), Cout, ksize,
+                                   1 if relu else 0, _p(y.hi) if y else None, _p(y.lo) if y else None,
+                                   _p(y32), ld_f32, _p(m_valid), _stream()), "frcnn_conv2d")
+    return y, y32
+
+
+def set_conv_tile(block_n=0, tile_h=0, tile_w=0):
+    _lib.load().frcnn_conv2d_set_tile(block_n, tile_h, tile_w)
+
+
+def maxpool2x2_ceil(x, out=None):
+    H, W, C = x.hi.shape
+    if out is None:
+        yh = torch.empty(((H + 1) // 2, (W + 1) // 2, C), dtype=torch.bfloat16, device=x.hi.device)
+        out = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    check(_lib.load().frcnn_maxpool2x2_ceil(_p(x.hi), _p(x.lo), H, W, C, _p(out.hi), _p(out.lo), _stream()),
+          "frcnn_maxpool2x2_ceil")
+    return out
+
+
+def roi_pool(feat, rois, count=None, outh=7, outw=7, scale=1.0 / 16, want_f32=False, out=None):
+    """feat Act [H,W,C]; rois [R_cap,4] f32; count int32[1] or None.
+    Returns (Act [R_cap, outh*outw*C] viewed as [1? no: R_cap rows], fp32 copy or None)."""
+    H, W, C = feat.hi.shape
+    R_cap = rois.shape[0]
+    if out is None:
+        oh = torch.empty((1, R_cap, outh * outw * C), dtype=torch.bfloat16, device=rois.device)
+        out = Act(oh, torch.empty_like(oh) if feat.lo is not None else None)
+    o32 = torch.empty((R_cap, outh * outw, C), dtype=torch.float32, device=rois.device) if want_f32 else None
+    check(_lib.load().frcnn_roi_pool(_p(feat.hi), _p(feat.lo), H, W, C, _p(rois), _p(count), R_cap, outh, outw,
+                                     ctypes.c_float(scale), _p(out.hi), _p(out.lo), _p(o32), _stream()), "frcnn_roi_pool")
+    return out, o32
+
+
+def head_decode(scores_deltas, ld, rois, count, num_classes, im_h, im_w, out_prob=None, out_boxes=None):
+    """scores_deltas fp32 [R_cap, ld]: columns [0,NC) scores, [NC, 5NC) deltas."""
+    R_cap = rois.shape[0]
+    dev = rois.device
+    if out_prob is None:
+        out_prob = torch.empty((R_cap, num_classes), dtype=torch.float32, device=dev)
+    if out_boxes is None:
+        out_boxes = torch.empty((R_cap, 4 * num_classes), dtype=torch.float32, device=dev)
+    deltas_ptr = ctypes.c_void_p(scores_deltas.data_ptr() + 4 * num_classes)
+    check(_lib.load().frcnn_head_decode(_p(scores_deltas), deltas_ptr, ld, _p(rois), _p(count), R_cap, num_classes,
+                                        int(im_h), int(im_w), _p(out_prob), _p(out_boxes), _stream()), "frcnn_head_decode")
+    return out_prob, out_boxes
+
+
+def detect(prob, boxes, count=None, nms_thresh=0.3, conf=0.8):
+    R_cap, NC = prob.shape
+    dev = prob.device
+    keep_idx = torch.empty((NC - 1, R_cap), dtype=torch.int32, device=dev)
+    keep_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
+    conf_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
+    check(_lib.load().frcnn_detect(_p(prob), _p(boxes), _p(count), R_cap, NC, float(nms_thresh), ctypes.c_float(conf),
+                                   _p(keep_idx), _p(keep_count), _p(conf_count), _stream()), "frcnn_detect")
+    return keep_idx, keep_count, conf_count
+
+
+class ProposalWorkspace(object):
+    """Pre-allocated scratch + outputs of frcnn_proposals for one (A,H,W,pre,post) shape."""
+
+    def __init__(self, A, H, W, pre_n, post_n, device, debug=False):
+        lib = _lib.load()
+        self.shape = (A, H, W, pre_n, post_n)
+        nbytes = lib.frcnn_proposals_workspace_bytes(A, H, W, pre_n)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.rois = torch.zeros((post_n, 4), dtype=torch.float32, device=device)
+        self.scores = torch.zeros((post_n,), dtype=torch.float32, device=device)
+        self.count = torch.zeros((1,), dtype=torch.int32, device=device)
+        k_cap = min(pre_n, A * H * W)
+        self.dbg_dets = torch.zeros((k_cap, 5), dtype=torch.float32, device=device) if debug else None
+        self.dbg_idx = torch.zeros((k_cap,), dtype=torch.int32, device=device) if debug else None
+        self.dbg_num = torch.zeros((1,), dtype=torch.int32, device=device) if debug else None
+
+
+def proposals(cls, bbox, anchors, A, H, W, feat_stride, im_h, im_w, min_size, pre_n, post_n, nms_thresh,
+              layout="nchw", ld=0, cls_is_logits=False, work=None, debug=False):
+    """frcnn_proposals.  layout "nchw": cls (2A,H,W), bbox (4A,H,W) planar (the reference's);
+    layout "nhwc": one fp32 matrix [H*W, ld] with cls in columns [0,2A) and bbox in [2A,6A)."""
+    dev = cls.device
+    if work is None or work.shape != (A, H, W, pre_n, post_n) or (debug and work.dbg_dets is None):
+        work = ProposalWorkspace(A, H, W, pre_n, post_n, dev, debug)
+    if layout == "nchw":
+        cs, ps, bcs, bps = H * W, 1, H * W, 1
+        bbox_ptr = _p(bbox)
+    else:
+        cs, ps, bcs, bps = 1, ld, 1, ld
+        bbox_ptr = ctypes.c_void_p(cls.data_ptr() + 4 * 2 * A) if bbox is None else _p(bbox)
+    check(_lib.load().frcnn_proposals(_p(cls), cs, ps, 1 if cls_is_logits else 0, bbox_ptr, bcs, bps, _p(anchors),
+                                      A, H, W, feat_stride, int(im_h), int(im_w), int(min_size), pre_n, post_n,
+                                      float(nms_thresh), _p(work.rois), _p(work.scores), _p(work.count),
+                                      _p(work.dbg_dets), _p(work.dbg_idx), _p(work.dbg_num),
+                                      _p(work.ws), work.ws.numel(), _stream()), "frcnn_proposals")
+    return work
+
+
+def nms(dets, thresh, mode=_lib.NMS_GE_DOUBLE, max_keep=0):
+    """Device greedy NMS over unsorted dets [n,5] (CUDA fp32).  Returns (keep int32[n], count int32[1])."""
+    _need_cuda(dets)
+    dets = dets.contiguous().float()
+    n = dets.shape[0]
+    lib = _lib.load()
+    ws = torch.empty(lib.frcnn_nms_workspace_bytes(n), dtype=torch.uint8, device=dets.device)
+    keep = torch.empty((max(n, 1),), dtype=torch.int32, device=dets.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=dets.device)
+    check(lib.frcnn_nms(_p(dets), n, float(thresh), mode, max_keep, _p(keep), _p(count), _p(ws), ws.numel(), _stream()),
+          "frcnn_nms")
+    return keep, count
+
+
+def cpu_nms_host(dets_np, thresh, device_id=0):
+    """Host-array entry (frcnn_cpu_nms_host): numpy f32 [n,5] in, list[int] out -- the drop-in
+    behind models.cpu_nms.cpu_nms (the arithmetic runs on the GPU)."""
+    d = np.ascontiguousarray(dets_np, dtype=np.float32)
+    if d.ndim != 2 or d.shape[1] != 5:
+        raise FrcnnError("cpu_nms: dets must be (N,5), got %s" % (d.shape,))
+    n = d.shape[0]
+    keep = np.empty(max(n, 1), dtype=np.int32)
+    r = _lib.load().frcnn_cpu_nms_host(d.ctypes.data_as(ctypes.c_void_p), n, float(thresh),
+                                       keep.ctypes.data_as(ctypes.c_void_p), device_id)
+    if r < 0:
+        raise FrcnnError("frcnn_cpu_nms_host failed (status %d): %s" % (r, _lib.last_error()))
+    return [int(v) for v in keep[:r]]
+
+
+def gpu_nms_host(sorted_dets_np, thresh, device_id=0):
+    """The reference FFI `_nms` (models/gpu_nms.hpp:9-10): pre-sorted host boxes, `>` comparison."""
+    d = np.ascontiguousarray(sorted_dets_np, dtype=np.float32)
+    n, dim = d.shape
+    keep = np.empty(max(n, 1), dtype=np.int32)
+    num = ctypes.c_int(0)
+    _lib.load()._nms(keep.ctypes.data_as(ctypes.c_void_p), ctypes.cast(ctypes.pointer(num), ctypes.c_void_p),
+                     d.ctypes.data_as(ctypes.c_void_p), n, dim, ctypes.c_float(thresh), device_id)
+    if num.value < 0:
+        raise FrcnnError("_nms failed: %s" % _lib.last_error())
+    return keep[: num.value].copy()

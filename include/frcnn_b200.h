@@ -1,0 +1,156 @@
+/*
+ * frcnn_b200.h -- C ABI of libfrcnn_b200.so: the Blackwell (sm_100a) Faster R-CNN forward
+ * detection path, a from-scratch replacement for the hot path of mitmul/chainer-faster-rcnn.
+ *
+ * Conventions (differences from the reference's only FFI, models/gpu_nms.hpp:9-10, are deliberate):
+ *   * every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   * every call is stream-ordered on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises and never allocates: scratch comes from the caller (`ws`, sized by the
+ *     matching *_workspace_bytes query);
+ *   * every call returns an int status: 0 = FRCNN_OK, negative = error; the message is available
+ *     from frcnn_last_error().  (The reference prints CUDA errors and continues,
+ *     models/nms_kernel.cu:12-19; this library never does.)
+ *   * data-dependent result counts are written to device ints; result buffers have
+ *     a fixed capacity and rows past the count are zero-filled.
+ *   * the library is re-entrant; the caller owns all buffers.
+ *
+ * Dense operands are NHWC bf16.  "bf16x3" precision: a tensor is a pair of bf16 planes (hi, lo)
+ * with value = hi + lo (16 significant bits); the contraction computes hi*hi + lo*hi + hi*lo
+ * with fp32 accumulation in TMEM.  Passing NULL for the lo planes selects single-pass bf16.
+ */
+#ifndef FRCNN_B200_H_
+#define FRCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRCNN_OK 0
+#define FRCNN_ERR_ARG (-1)        /* invalid argument / unsupported size */
+#define FRCNN_ERR_CUDA (-2)       /* a CUDA runtime / driver call failed */
+#define FRCNN_ERR_WORKSPACE (-3)  /* workspace too small */
+
+/* NMS comparison semantics. */
+#define FRCNN_NMS_GE_DOUBLE 0 /* suppress if (double)iou_f32 >= thresh  -- models/cpu_nms.pyx:66 (live path) */
+#define FRCNN_NMS_GT_FLOAT 1  /* suppress if iou_f32 > (float)thresh     -- models/nms_kernel.cu:71          */
+
+int frcnn_version(void);
+const char* frcnn_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Reference ABI, kept verbatim: models/gpu_nms.hpp:9-10 (`_nms`), bound by models/gpu_nms.pyx:13-14.
+ * HOST pointers; boxes row-major [boxes_num, boxes_dim>=4], pre-sorted by descending score;
+ * keep_out sized boxes_num; blocking; `>` comparison as models/nms_kernel.cu:71.
+ * Unlike the reference, a CUDA failure sets *num_out = -1 (and frcnn_last_error()).
+ */
+void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
+          float nms_overlap_thresh, int device_id);
+
+/* Host-pointer greedy NMS with models/cpu_nms.pyx:18-69 semantics (internal descending sort with
+ * ties -> lower index first, +1 pixel convention, (double)iou >= thresh).  dets_host [n,5].
+ * Returns the number kept (>= 0) or a negative status.  Blocking. */
+int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device NMS on UNSORTED dets [n,5] (x1,y1,x2,y2,score): replaces models/cpu_nms.pyx:18-69.
+ * keep_out (capacity n) receives original indices in descending-score order, *num_out the count;
+ * max_keep > 0 stops after that many survivors (the reference's `keep[:post_nms_top_n]`,
+ * models/proposal_layer.py:189-190), <= 0 keeps all.  n <= 16384.
+ */
+size_t frcnn_nms_workspace_bytes(int n);
+int frcnn_nms(const float* dets, int n, double thresh, int mode, int max_keep, int* keep_out, int* num_out,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ProposalLayer.__call__ (models/proposal_layer.py:102-198) fused on device: all-anchor grid
+ * (:207-221), bbox_transform_inv + clip_boxes + filter_boxes (models/bbox_transform.py:41-109),
+ * fg-score slice (:152-154), descending sort + top pre_nms_top_n (:158-170), greedy NMS
+ * (models/cpu_nms.pyx) and top post_nms_top_n (:189-193).
+ *
+ * cls / bbox element (channel c, pixel p=h*W+w) is read at base[c*chan_stride + p*pix_stride]:
+ *   reference layout (1,2A,H,W)/(1,4A,H,W): chan_stride=H*W, pix_stride=1;  NHWC rows of ld floats:
+ *   chan_stride=1, pix_stride=ld.
+ * cls_is_logits != 0: `cls` holds the 2A RPN logits and the 2A-way channel softmax of
+ *   models/region_proposal_network.py:119 is computed here; else `cls` is rpn_cls_prob.
+ * anchors: [A,4] float64 (models/generate_anchors.py:47-55 output), device memory.
+ * out_rois [post_nms_top_n,4], out_scores [post_nms_top_n], *out_count = R; rows >= R are zero.
+ * Optional debug outputs (may be NULL): dbg_sorted_dets [pre_nms_top_n,5] (the dets handed to NMS),
+ *   dbg_sorted_anchor_idx [pre_nms_top_n], dbg_num_sorted (int).
+ * Limits: pre_nms_top_n <= 16384 (and > 0), A <= 32.
+ */
+size_t frcnn_proposals_workspace_bytes(int A, int H, int W, int pre_nms_top_n);
+int frcnn_proposals(const float* cls, long cls_chan_stride, long cls_pix_stride, int cls_is_logits,
+                    const float* bbox, long bbox_chan_stride, long bbox_pix_stride, const double* anchors,
+                    int A, int H, int W, int feat_stride, int im_h, int im_w, int min_size,
+                    int pre_nms_top_n, int post_nms_top_n, double nms_thresh, float* out_rois,
+                    float* out_scores, int* out_count, float* dbg_sorted_dets, int* dbg_sorted_anchor_idx,
+                    int* dbg_num_sorted, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue):
+ * 3x3 stride-1 pad-1 convolution or 1x1 convolution / GEMM over NHWC bf16, fused bias (+ReLU).
+ * Replaces L.Convolution2D (models/vgg16.py:39-67, models/region_proposal_network.py:53-57) and
+ * L.Linear (models/faster_rcnn.py:33-36; a Linear over R rows is the 1x1 case with H=1, W=R).
+ *   x_hi/x_lo : [H,W,Cin] bf16 (x_lo NULL -> single-pass bf16), Cin % 8 == 0
+ *   w_hi/w_lo : [ksize*ksize, Cout, Cin] bf16 (tap-major, K-major rows), see frcnn_pack_conv_weights
+ *   bias      : [>= round_up(max(Cout, ld_f32), 32)] fp32 (zero padded past Cout)
+ *   y_hi/y_lo : [H,W,Cout] bf16 outputs (may be NULL), Cout % 32 == 0 when used
+ *   y_f32     : [H*W, ld_f32] fp32 output (may be NULL), ld_f32 % 32 == 0, ld_f32 >= Cout;
+ *               padded columns receive 0 (+bias pad)
+ *   m_valid   : optional device int: rows (pixels) >= *m_valid are written as zeros (GEMM over a
+ *               data-dependent number of RoIs); NULL = all valid.
+ */
+int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                 const float* bias, int Cout, int ksize, int relu, void* y_hi, void* y_lo, float* y_f32,
+                 int ld_f32, const int* m_valid, void* stream);
+/* Tuning override for tests / benchmarks: force the N tile (64/128/256) and the pixel tile
+ * (tile_h*tile_w == 128); 0 = automatic. Process-wide. */
+void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w);
+
+/* OIHW fp32 weights (Chainer layout, e.g. trunk/conv1_1/W) -> [kh*kw, Cout, Cin_pad] bf16 hi/lo.
+ * For Linear weights (Cout, K) pass kh=kw=1.  `perm_chw_to_hwc` != 0 with (c,h,w) = (pc,ph,pw)
+ * additionally permutes the K axis from (c,h,w) order (fc6/W over a (C,7,7) pool, models/faster_rcnn.py:127)
+ * to the (h,w,c) order frcnn_roi_pool emits.  w_lo may be NULL. */
+int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, int kh, int kw, int Cin_pad, void* w_hi,
+                            void* w_lo, int perm_chw_to_hwc, int pc, int ph, int pw, void* stream);
+/* (C,H,W) fp32 image (the reference's input layout, forward.py:45) -> [H,W,C_pad] bf16 hi/lo. */
+int frcnn_pack_image(const float* x_chw, int C, int H, int W, int C_pad, void* y_hi, void* y_lo, void* stream);
+/* [H,W,C] bf16 hi(/lo) -> (C,H,W) fp32 (the reference's feature-map layout); for inspection/tests. */
+int frcnn_unpack_nhwc(const void* x_hi, const void* x_lo, int H, int W, int C, float* y_chw, void* stream);
+
+/* F.MaxPooling2D(2,2), Chainer cover_all=True == ceil mode (models/vgg16.py:43,48,55,62).
+ * [H,W,C] -> [ceil(H/2),ceil(W/2),C], C % 8 == 0. */
+int frcnn_maxpool2x2_ceil(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo,
+                          void* stream);
+
+/* F.roi_pooling_2d(feature_map, [0|rois], outh, outw, scale) (models/faster_rcnn.py:123-126), Caffe
+ * semantics.  feat [H,W,C] bf16 hi(/lo); rois [R_cap,4] fp32; *count valid rows (NULL = R_cap).
+ * out_hi/out_lo: [R_cap, outh*outw, C] bf16 (row = one RoI, K order (ph,pw,c)); rows >= count are 0.
+ * out_f32 (optional): same layout in fp32. */
+int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois,
+                   const int* count, int R_cap, int outh, int outw, float scale, void* out_hi, void* out_lo,
+                   float* out_f32, void* stream);
+
+/* Head tail (models/faster_rcnn.py:175-178): softmax over num_classes scores + per-class
+ * bbox_transform_inv + clip_boxes.  scores element (r,c) at scores[r*ld + c], deltas (r,j) at
+ * deltas[r*ld + j] (same ld).  out_prob [R_cap,num_classes], out_boxes [R_cap,4*num_classes];
+ * rows >= *count are zero. */
+int frcnn_head_decode(const float* scores, const float* deltas, int ld, const float* rois, const int* count,
+                      int R_cap, int num_classes, int im_h, int im_w, float* out_prob, float* out_boxes,
+                      void* stream);
+
+/* Per-class detection (forward.py:48-57): for cls 1..num_classes-1 greedy NMS (cpu_nms semantics,
+ * thresh) over (boxes[:,4c:4c+4], prob[:,c]), then score >= conf.
+ * keep_idx [num_classes-1, R_cap] (RoI indices, descending score), keep_count [num_classes-1] =
+ * survivors of the NMS, conf_count [num_classes-1] = how many of those (a prefix) have score >= conf.
+ * R_cap <= 2048. */
+int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_cap, int num_classes,
+                 double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H_ */
