@@ -1,0 +1,223 @@
+"""The whole Faster R-CNN forward detection path as one replayable CUDA graph.
+
+Mirrors FasterRCNN.__call__ (inference branch, /root/reference models/faster_rcnn.py:92-134,175-178):
+
+    trunk (models/vgg16.py:38-82)            13x frcnn_conv2d(3x3)+ReLU, 4x frcnn_maxpool2x2_ceil
+    RPN   (models/region_proposal_network.py:117-124)
+                                             frcnn_conv2d(3x3)+ReLU, ONE frcnn_conv2d(1x1) for the twin
+                                             heads (18 cls + 36 bbox -> fp32 [H*W, 64])
+    ProposalLayer (models/proposal_layer.py:102-198)
+                                             frcnn_proposals (18-way softmax fused, NHWC logits in)
+    RoI pool + head (models/faster_rcnn.py:123-134)
+                                             frcnn_roi_pool, frcnn_conv2d as GEMM for fc6 / fc7 /
+                                             (cls_score | bbox_pred merged: 105 -> fp32 [R, 128])
+    tail  (models/faster_rcnn.py:175-178)    frcnn_head_decode (softmax + decode + clip)
+    caller's per-class NMS (forward.py:48-57) frcnn_detect (optional)
+
+All buffers are allocated once per (image shape, mode); the data-dependent RoI count stays on the
+device (rows past it are zero) so the launch sequence is static and is captured into a CUDA graph.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import FrcnnError
+
+VGG16_LAYERS = [
+    ("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool",
+    ("conv2_1", 64, 128), ("conv2_2", 128, 128), "pool",
+    ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), "pool",
+    ("conv4_1", 256, 512), ("conv4_2", 512, 512), ("conv4_3", 512, 512), "pool",
+    ("conv5_1", 512, 512), ("conv5_2", 512, 512), ("conv5_3", 512, 512),
+]
+
+
+def _t(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float32)
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+
+
+class PackedWeights(object):
+    """Reference-named fp32 parameters (trunk/conv1_1/W ... bbox_pred/b) repacked once
+    into the kernels' layouts: [taps, Cout, Cin] bf16 hi(/lo) + padded fp32 bias."""
+
+    def __init__(self, params, precision="bf16x3", device="cuda", num_classes=21, n_anchors=9,
+                 pool_chw=(512, 7, 7)):
+        if precision not in ops.PRECISIONS:
+            raise FrcnnError("unknown precision %r" % (precision,))
+        self.precision, self.device = precision, device
+        self.num_classes, self.n_anchors = num_classes, n_anchors
+        P = lambda k: _t(params[k], device)
+        self.convs = {}
+        for item in VGG16_LAYERS:
+            if item == "pool":
+                continue
+            name, cin, cout = item
+            w = P("trunk/%s/W" % name)
+            self.convs[name] = self._pack(w, P("trunk/%s/b" % name), cin_pad=16 if cin < 16 else cin)
+        self.rpn3 = self._pack(P("RPN/rpn_conv_3x3/W"), P("RPN/rpn_conv_3x3/b"))
+        # twin 1x1 heads merged along Cout: rows [0,2A) = rpn_cls_score, [2A,6A) = rpn_bbox_pred
+        wh = torch.cat([P("RPN/rpn_cls_score/W"), P("RPN/rpn_bbox_pred/W")], dim=0)
+        bh = torch.cat([P("RPN/rpn_cls_score/b"), P("RPN/rpn_bbox_pred/b")], dim=0)
+        self.rpn_ld = ops.round_up(6 * n_anchors, 32)
+        self.rpn_heads = self._pack(wh, bh, n_bias=self.rpn_ld)
+        self.fc6 = self._pack(P("fc6/W"), P("fc6/b"), perm_chw=pool_chw)
+        self.fc7 = self._pack(P("fc7/W"), P("fc7/b"))
+        wc = torch.cat([P("cls_score/W"), P("bbox_pred/W")], dim=0)
+        bc = torch.cat([P("cls_score/b"), P("bbox_pred/b")], dim=0)
+        self.head_ld = ops.round_up(5 * num_classes, 32)
+        self.head = self._pack(wc, bc, n_bias=self.head_ld)
+        torch.cuda.synchronize(device)
+
+    def _pack(self, w, b, cin_pad=None, perm_chw=None, n_bias=0):
+        hi, lo = ops.pack_conv_weights(w, cin_pad=cin_pad, precision=self.precision, perm_chw=perm_chw)
+        return hi, lo, ops.pad_bias(b, max(n_bias, b.numel()))
+
+
+class ForwardPlan(object):
+    """Buffers + launch sequence for one image shape."""
+
+    def __init__(self, weights, H, W, pre_n=6000, post_n=300, nms_thresh=0.7, min_size=16, feat_stride=16,
+                 anchors=None, with_detect=False, det_nms_thresh=0.3, det_conf=0.8, use_graph=True, keep_rpn_debug=False):
+        self.w, self.H, self.W = weights, H, W
+        dev = weights.device
+        x3 = weights.precision == "bf16x3"
+        self.pre_n, self.post_n, self.nms_thresh, self.min_size, self.feat_stride = pre_n, post_n, nms_thresh, min_size, feat_stride
+        self.with_detect, self.det_nms_thresh, self.det_conf = with_detect, det_nms_thresh, det_conf
+        A = weights.n_anchors
+        if anchors is None:
+            raise FrcnnError("ForwardPlan needs the [A,4] float64 anchor table")
+        self.anchors = torch.from_numpy(np.ascontiguousarray(anchors, dtype=np.float64)).to(dev)
+
+        def act(h, w, c):
+            hi = torch.empty((h, w, c), dtype=torch.bfloat16, device=dev)
+            return ops.Act(hi, torch.empty_like(hi) if x3 else None)
+
+        self.x_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)      # static input (C,H,W)
+        self.img_info = torch.tensor([H, W], dtype=torch.int32, device=dev)      # clip bounds (h, w): static in the graph
+        self.acts = [act(H, W, 16)]
+        h, w_ = H, W
+        self.trunk_steps = []
+        for item in VGG16_LAYERS:
+            if item == "pool":
+                h, w_ = (h + 1) // 2, (w_ + 1) // 2
+                self.acts.append(act(h, w_, self.acts[-1].hi.shape[2]))
+                self.trunk_steps.append(("pool", None))
+            else:
+                self.acts.append(act(h, w_, item[2]))
+                self.trunk_steps.append(("conv", item[0]))
+        self.fh, self.fw = h, w_
+        self.rpn_mid = act(h, w_, 512)
+        self.rpn_out = torch.empty((h * w_, weights.rpn_ld), dtype=torch.float32, device=dev)
+        self.prop = ops.ProposalWorkspace(A, h, w_, pre_n, post_n, dev, debug=keep_rpn_debug)
+        C = self.acts[-1].hi.shape[2]
+        self.pool5 = act(1, post_n, 49 * C)
+        self.fc6 = act(1, post_n, 4096)
+        self.fc7 = act(1, post_n, 4096)
+        self.head_out = torch.empty((post_n, weights.head_ld), dtype=torch.float32, device=dev)
+        self.prob = torch.zeros((post_n, weights.num_classes), dtype=torch.float32, device=dev)
+        self.boxes = torch.zeros((post_n, 4 * weights.num_classes), dtype=torch.float32, device=dev)
+        self.det = None
+        self.graph = None
+        self.use_graph = use_graph
+        self.im_h, self.im_w = H, W
+        self.n_launches = 0
+
+    # -- the launch sequence (static; safe to capture)
+    def _run(self):
+        w = self.w
+        n = 0
+        lib = ops._lib.load()
+        x = self.acts[0]
+        ops.check(lib.frcnn_pack_image(ops._p(self.x_in), 3, self.H, self.W, 16, ops._p(x.hi), ops._p(x.lo), ops._stream()),
+                  "frcnn_pack_image")
+        n += 1
+        i = 0
+        for kind, name in self.trunk_steps:
+            src, dst = self.acts[i], self.acts[i + 1]
+            if kind == "pool":
+                ops.maxpool2x2_ceil(src, out=dst)
+            else:
+                hi, lo, b = w.convs[name]
+                ops.conv2d(src, hi, lo, b, 3, True, out=dst)
+            n += 1
+            i += 1
+        feat = self.acts[-1]
+        hi, lo, b = w.rpn3
+        ops.conv2d(feat, hi, lo, b, 3, True, out=self.rpn_mid)
+        hi, lo, b = w.rpn_heads
+        ops.conv2d(self.rpn_mid, hi, lo, b, 1, False, out_act=False, ld_f32=w.rpn_ld, out_f32=self.rpn_out)
+        ops.proposals(self.rpn_out, None, self.anchors, w.n_anchors, self.fh, self.fw, self.feat_stride,
+                      self.im_h, self.im_w, self.min_size, self.pre_n, self.post_n, self.nms_thresh,
+                      layout="nhwc", ld=w.rpn_ld, cls_is_logits=True, work=self.prop,
+                      debug=self.prop.dbg_dets is not None)
+        n += 2 + 4
+        ops.roi_pool(feat, self.prop.rois, self.prop.count, 7, 7, 1.0 / self.feat_stride, out=self.pool5)
+        hi, lo, b = w.fc6
+        ops.conv2d(self.pool5, hi, lo, b, 1, True, out=self.fc6, m_valid=self.prop.count)
+        hi, lo, b = w.fc7
+        ops.conv2d(self.fc6, hi, lo, b, 1, True, out=self.fc7, m_valid=self.prop.count)
+        hi, lo, b = w.head
+        ops.conv2d(self.fc7, hi, lo, b, 1, False, out_act=False, ld_f32=w.head_ld, out_f32=self.head_out,
+                   m_valid=self.prop.count)
+        ops.head_decode(self.head_out, w.head_ld, self.prop.rois, self.prop.count, w.num_classes, self.im_h, self.im_w,
+                        out_prob=self.prob, out_boxes=self.boxes)
+        n += 5
+        if self.with_detect:
+            self.det = ops.detect(self.prob, self.boxes, self.prop.count, self.det_nms_thresh, self.det_conf)
+            n += 1
+        self.n_launches = n
+
+    def set_clip(self, im_h, im_w):
+        """img_info as the caller passes it (forward.py:93 passes (H, H)).  Changing it
+        invalidates a captured graph (the bounds are kernel arguments)."""
+        if (im_h, im_w) != (self.im_h, self.im_w):
+            self.im_h, self.im_w = int(im_h), int(im_w)
+            self.graph = None
+
+    def forward(self, x_chw=None):
+        """Run one image.  x_chw: (3,H,W) float32 CUDA tensor (copied into the static input) or None
+        to reuse the current contents of `self.x_in`.  Returns (prob, boxes, count) device tensors."""
+        if x_chw is not None:
+            self.x_in.copy_(x_chw, non_blocking=True)
+        if not self.use_graph:
+            self._run()
+        else:
+            if self.graph is None:
+                self._run()                       # warm-up outside capture (func attributes, lazy init)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run()
+                self.graph = g
+            self.graph.replay()
+        return self.prob, self.boxes, self.prop.count
+
+
+class Engine(object):
+    """Weights + per-shape plans.  `engine(x)` -> (prob [R,21], boxes [R,84]) device tensors, R synced."""
+
+    def __init__(self, params, precision="bf16x3", device="cuda", anchors=None, num_classes=21, n_anchors=9,
+                 feat_stride=16, **plan_kwargs):
+        self.weights = PackedWeights(params, precision, device, num_classes, n_anchors)
+        self.anchors, self.feat_stride = anchors, feat_stride
+        self.plan_kwargs = plan_kwargs
+        self.plans = {}
+
+    def plan(self, H, W, **overrides):
+        kw = dict(self.plan_kwargs)
+        kw.update(overrides)
+        key = (H, W, tuple(sorted(kw.items())))
+        if key not in self.plans:
+            self.plans[key] = ForwardPlan(self.weights, H, W, anchors=self.anchors, feat_stride=self.feat_stride, **kw)
+        return self.plans[key]
+
+    def __call__(self, x_chw, img_info=None, **overrides):
+        _, H, W = x_chw.shape
+        p = self.plan(H, W, **overrides)
+        if img_info is not None:
+            p.set_clip(int(img_info[0]), int(img_info[1]))
+        prob, boxes, count = p.forward(x_chw)
+        R = int(count.item())           # the one documented D2H sync
+        return prob[:R], boxes[:R], p

@@ -380,11 +380,16 @@ def detect(cls_prob, pred_boxes, nms_thresh=0.3, conf=0.8):
 
 
 # --------------------------------------------------------------------------- synthetic weights / inputs
-def make_params(seed=1234, num_classes=21, mid_ch=512, n_anchors=9, trunk_std="he"):
+def make_params(seed=1234, num_classes=21, mid_ch=512, n_anchors=9, trunk_std="he", input_scale=1.0 / 64):
     """Random-init parameters with the reference's names (SURVEY.md 5 checkpoint format).
     Heads N(0, 0.01), zero bias (models/faster_rcnn.py:27,33-36; region_proposal_network.py:50-57).
     Trunk: He-normal std=sqrt(2/(9*C_in)), zero bias (SURVEY.md 8d -- Chainer's own default
-    init is un-vendored; N(0,0.01) in the trunk would collapse activations into ties)."""
+    init is un-vendored; N(0,0.01) in the trunk would collapse activations into ties).
+    conv1_1 is additionally scaled by `input_scale` (1/64): the input is a 0..255-range image minus
+    the BGR means, and without it conv5_3 is O(1e3), the RPN logits/deltas have std ~30-200, exp()
+    overflows and the whole ProposalLayer degenerates (17 proposals, saturated ties).  With it the
+    activations are O(1), 21,518 of 21,546 fg scores are distinct and R = 300 -- the role a trained
+    first layer plays."""
     rng = np.random.default_rng(seed)
     p = {}
     for item in VGG16_LAYERS:
@@ -392,6 +397,8 @@ def make_params(seed=1234, num_classes=21, mid_ch=512, n_anchors=9, trunk_std="h
             continue
         name, cin, cout = item
         std = np.sqrt(2.0 / (9 * cin)) if trunk_std == "he" else float(trunk_std)
+        if name == "conv1_1":
+            std = std * input_scale
         p["trunk/%s/W" % name] = (rng.standard_normal((cout, cin, 3, 3)) * std).astype(f32)
         p["trunk/%s/b" % name] = np.zeros(cout, dtype=f32)
 

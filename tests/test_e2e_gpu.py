@@ -1,0 +1,159 @@
+"""GPU end-to-end parity: the whole forward graph (frcnn_b200.engine) against the CPU oracle.
+
+Stage-wise "identical inputs" checks (each stage's oracle is fed the DEVICE's own upstream result, so
+one stage's rounding cannot flip another stage's integer decisions) plus a pure end-to-end comparison
+against the fp32 oracle at the north star's tolerance (1e-4 relative; bit-exact keep indices)."""
+import numpy as np
+import pytest
+import torch
+
+import frcnn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+ANCHORS = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+
+
+def _quant16(a):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=f32))
+    hi = t.to(torch.bfloat16).float()
+    return (hi + (t - hi).to(torch.bfloat16).float()).numpy()
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def params():
+    return orc.make_params(seed=1234)
+
+
+def _engine(params, precision, **kw):
+    from frcnn_b200.engine import Engine
+    return Engine(params, precision=precision, anchors=ANCHORS, keep_rpn_debug=True, **kw)
+
+
+@pytest.mark.parametrize("shape", [(96, 128), (150, 201)])
+def test_forward_stagewise_bf16x3(params, shape):
+    H, W = shape
+    x = orc.make_image(H, W, seed=1)
+    info = np.array([[H, W]], np.int32)
+    eng = _engine(params, "bf16x3", use_graph=False)
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    torch.cuda.synchronize()
+    R = prob.shape[0]
+
+    # ---- trunk: device conv5_3 vs the fp32 oracle (north-star tolerance) and vs the 16-bit-operand oracle
+    feat_dev = plan.acts[-1].to_chw_f32().cpu().numpy()[None]
+    feat_ref = orc.vgg16_forward(x, params)
+    assert feat_dev.shape == feat_ref.shape
+    assert _rel(feat_dev, feat_ref) < 1e-4
+    assert _rel(feat_dev, orc.vgg16_forward(x, params, quant=_quant16)) < 6e-5
+
+    # ---- RPN heads on the device's own feature map
+    fh, fw = plan.fh, plan.fw
+    rpn = plan.rpn_out.cpu().numpy()
+    logits_dev = rpn[:, :18].T.reshape(1, 18, fh, fw)
+    deltas_dev = rpn[:, 18:54].T.reshape(1, 36, fh, fw)
+    h_ref = orc.relu(orc.conv2d(feat_dev, params["RPN/rpn_conv_3x3/W"], params["RPN/rpn_conv_3x3/b"], 1))
+    assert _rel(plan.rpn_mid.to_chw_f32().cpu().numpy()[None], h_ref) < 1e-4
+    h_dev = plan.rpn_mid.to_chw_f32().cpu().numpy()[None]
+    assert _rel(logits_dev, orc.conv2d(h_dev, params["RPN/rpn_cls_score/W"], params["RPN/rpn_cls_score/b"], 0)) < 1e-4
+    assert _rel(deltas_dev, orc.conv2d(h_dev, params["RPN/rpn_bbox_pred/W"], params["RPN/rpn_bbox_pred/b"], 0)) < 1e-4
+
+    # ---- ProposalLayer on identical inputs (the device's logits/deltas): BIT-EXACT
+    dbg = {}
+    want_rois, want_fg = orc.proposal_layer(orc.softmax_axis1(logits_dev), deltas_dev, info, debug=dbg)
+    rois_dev = plan.prop.rois.cpu().numpy()
+    assert R == len(want_rois) and R > 0
+    assert np.array_equal(rois_dev[:R], want_rois)
+    assert np.array_equal(plan.prop.scores.cpu().numpy()[:R], want_fg.ravel())
+    ns = int(plan.prop.dbg_num.item())
+    assert np.array_equal(plan.prop.dbg_dets.cpu().numpy()[:ns], dbg["dets"])
+
+    # ---- RoI pool (exact) and head (1e-4) on the device's feature map and RoIs
+    cls_ref, box_ref, aux = orc.head_forward(feat_dev, rois_dev[:R], params, info)
+    pool_dev = (plan.pool5.hi.float() + plan.pool5.lo.float()).cpu().numpy().reshape(-1, 7, 7, 512)[:R]
+    assert np.array_equal(pool_dev.transpose(0, 3, 1, 2), aux["pool5"])
+    assert _rel((plan.fc6.hi.float() + plan.fc6.lo.float()).cpu().numpy()[0, :R], aux["fc6"]) < 1e-4
+    assert _rel((plan.fc7.hi.float() + plan.fc7.lo.float()).cpu().numpy()[0, :R], aux["fc7"]) < 1e-4
+    np.testing.assert_allclose(prob.cpu().numpy(), cls_ref, rtol=1e-4, atol=1e-7)
+    assert _rel(boxes.cpu().numpy(), box_ref) < 1e-4
+    # tail on identical inputs (device head logits): bit-exact softmax / decode / clip
+    ho = plan.head_out.cpu().numpy()[:R]
+    assert np.array_equal(prob.cpu().numpy(), orc.softmax_axis1(ho[:, :21]))
+    assert np.array_equal(boxes.cpu().numpy(), orc.clip_boxes(orc.bbox_transform_inv(rois_dev[:R], ho[:, 21:105]), (H, W)))
+    assert not plan.prob.cpu().numpy()[R:].any() and not plan.boxes.cpu().numpy()[R:].any()
+
+
+def test_forward_end_to_end_vs_fp32_oracle(params):
+    """Pure end to end against the fp32 oracle.  Scores that differ by ~1e-5 can legitimately reorder
+    near-ties, so proposals are matched by box and the matched fraction must be (almost) everything."""
+    H, W = 128, 160
+    x = orc.make_image(H, W, seed=2)
+    info = np.array([[H, W]], np.int32)
+    eng = _engine(params, "bf16x3")
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    cls_ref, box_ref, aux = orc.faster_rcnn_forward(x, params, info)
+    rois_dev = plan.prop.rois.cpu().numpy()[: prob.shape[0]]
+    rois_ref = aux["proposals"]
+    # match proposals (same box within 1e-4 of the image scale)
+    d = np.abs(rois_dev[:, None, :] - rois_ref[None, :, :]).max(-1)
+    j = d.argmin(1)
+    ok = d[np.arange(len(j)), j] < 1e-4 * max(H, W)
+    assert ok.mean() > 0.97, ok.mean()
+    p, b = prob.cpu().numpy()[ok], boxes.cpu().numpy()[ok]
+    np.testing.assert_allclose(p, cls_ref[j[ok]], rtol=1e-4, atol=1e-7)
+    assert np.abs(b - box_ref[j[ok]]).max() < 1e-4 * max(H, W)
+
+
+def test_graph_replay_is_deterministic_and_matches_eager(params):
+    H, W = 96, 128
+    eng_g = _engine(params, "bf16x3", use_graph=True)
+    eng_e = _engine(params, "bf16x3", use_graph=False)
+    for seed in (3, 4, 3):
+        x = torch.from_numpy(orc.make_image(H, W, seed=seed)[0]).cuda()
+        pg, bg, _ = eng_g(x)
+        pe, be, _ = eng_e(x)
+        assert pg.shape == pe.shape and torch.equal(pg, pe) and torch.equal(bg, be)
+
+
+def test_bf16_fast_mode_runs_and_is_close(params):
+    """Single-pass bf16: same graph, lo planes absent.  Not the parity mode -- only sanity-checked."""
+    H, W = 96, 128
+    x = orc.make_image(H, W, seed=5)
+    eng = _engine(params, "bf16")
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    feat_ref = orc.vgg16_forward(x, params)
+    assert _rel(plan.acts[-1].to_chw_f32().cpu().numpy()[None], feat_ref) < 3e-2
+    assert prob.shape[1] == 21 and prob.shape[0] > 0
+    np.testing.assert_allclose(prob.sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+
+
+def test_headline_config_600x1000(params):
+    """BASELINE config #2 at full size: 600x1000, 300 proposals.  Size-independent properties +
+    exact ProposalLayer parity on the device's own RPN outputs + detect vs the oracle."""
+    H, W = 600, 1000
+    x = orc.make_image(H, W, seed=0)
+    info = np.array([[H, W]], np.int32)
+    eng = _engine(params, "bf16x3", with_detect=True, det_conf=0.05)
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    R = prob.shape[0]
+    assert (plan.fh, plan.fw) == (38, 63) and 0 < R <= 300
+    rpn = plan.rpn_out.cpu().numpy()
+    logits = rpn[:, :18].T.reshape(1, 18, 38, 63)
+    deltas = rpn[:, 18:54].T.reshape(1, 36, 38, 63)
+    probs = orc.softmax_axis1(logits)
+    fg = probs[0, 9:].ravel()
+    print("unique fg scores: %d of %d" % (np.unique(fg).size, fg.size))
+    want_rois, want_fg = orc.proposal_layer(probs, deltas, info)
+    assert R == len(want_rois)
+    assert np.array_equal(plan.prop.rois.cpu().numpy()[:R], want_rois)
+    assert np.array_equal(plan.prop.scores.cpu().numpy()[:R], want_fg.ravel())
+    p, b = prob.cpu().numpy(), boxes.cpu().numpy()
+    np.testing.assert_allclose(p.sum(1), 1.0, rtol=1e-5)
+    assert b.min() >= 0 and b[:, 0::4].max() <= W - 1 and b[:, 1::4].max() <= H - 1
+    keep_idx, keep_count, conf_count = [t.cpu().numpy() for t in plan.det]
+    for c, keep, dets in orc.detect(p, b, 0.3, 0.05):
+        assert keep_idx[c - 1, :conf_count[c - 1]].tolist() == keep.tolist()
