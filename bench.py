@@ -212,7 +212,8 @@ def run_b200_arm(args, rank, local_rank, world):
     eng = Engine(params, precision=args.precision, anchors=anchors, use_graph=True)
     plan = eng.plan(H_IMG, W_IMG)
     n_img = 4                                # rotate distinct images: no step sees the previous step's input
-    imgs_host = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=100 * rank + i)[0]).pin_memory() for i in range(n_img)]
+    from frcnn_b200.shard import image_seed
+    imgs_host = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=image_seed(rank, i))[0]).pin_memory() for i in range(n_img)]
     imgs_dev = [t.cuda() for t in imgs_host]
 
     def barrier():
@@ -238,10 +239,8 @@ def run_b200_arm(args, rank, local_rank, world):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     R_last = int(plan.prop.count.item())
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from frcnn_b200 import shard
+    ms_max = shard.max_over_ranks(ms, device="cuda")          # slowest rank decides
     value = world * args.steps / (ms_max / 1e3)
 
     # ---------------- e2e: host image in, host result out, every step (public call)
@@ -264,10 +263,7 @@ def run_b200_arm(args, rank, local_rank, world):
     for i in range(args.steps):
         e2e_step(i)
     t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * args.steps / float(te.item())
+    e2e_val = world * args.steps / shard.max_over_ranks(t_e2e, device="cuda")
     h2d = imgs_host[0].numel() * 4
     d2h = res_prob.numel() * 4 + res_box.numel() * 4 + 4
 

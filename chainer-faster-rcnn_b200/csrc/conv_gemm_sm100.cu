@@ -35,6 +35,7 @@ struct ConvParams {
     int taps, ksize, cin_blocks;
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
     int num_stages, x3, relu;
+    int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
     int ld_f32, n_cover;
     __nv_bfloat16* y_hi;
     __nv_bfloat16* y_lo;
@@ -94,7 +95,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+        ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -144,7 +145,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
+            const uint32_t d_corr = d_tmem + BN;   // bf16x3: lo*hi + hi*lo accumulate separately (see epilogue)
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
@@ -161,9 +163,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         const uint64_t a_lo = ptx::make_smem_desc(st + C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
                         const uint64_t b_lo = ptx::make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
                     }
                     ptx::mma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
                     if (kb == num_kb - 1) ptx::mma_commit(&tfull_bar[acc]);   // accumulator complete
@@ -171,7 +173,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 __syncwarp();
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ================================ epilogue ================================
@@ -196,18 +198,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.n_cover) break;   // warp-uniform: nothing is stored past the covered columns
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.acc_cols + c0);
+                ptx::tmem_ld_32x32b_x32(taddr, r);
                 ptx::tmem_ld_wait();
                 const int n = n0 + c0;
                 float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.x3) {
+                    // The tensor-core accumulator truncates on every add; keeping the ~2^-8-sized
+                    // correction products in their own accumulator and adding them here with one
+                    // round-to-nearest fp32 add keeps that bias at the single-pass level.
+                    ptx::tmem_ld_32x32b_x32(taddr + BN, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 b = __ldg(b4 + j);
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+                    v[4 * j + 0] += b.x;
+                    v[4 * j + 1] += b.y;
+                    v[4 * j + 2] += b.z;
+                    v[4 * j + 3] += b.w;
                 }
                 if (p.relu) {
 #pragma unroll
@@ -247,7 +261,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -255,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -322,15 +336,19 @@ static int launch_conv(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
                        const CUtensorMap& tb_lo, ConvParams p, cudaStream_t stream) {
     using C = Cfg<BN, BK>;
     const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+    const int budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
     int stages = budget / stage_bytes;
-    if (stages > 8) stages = 8;
+    if (stages > 24) stages = 24;
     if (stages < 2) {
         set_error("conv tile BN=%d BK=%d does not fit 2 pipeline stages", BN, BK);
         return FRCNN_ERR_ARG;
     }
     p.num_stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 512;
+    p.acc_cols = p.x3 ? 2 * BN : BN;
+    p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < p.acc_bufs * p.acc_cols) p.tmem_cols *= 2;
     auto kern = conv_gemm_kernel<BN, BK>;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
@@ -391,7 +409,10 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
         const int sms = device_sm_count();
         double best = 0;
         const int cand[3] = {256, 128, 64};
-        const double cost[3] = {128, 64, 48};
+        // measured cycles per k-block per CTA on B200 (tests/gpu_tune_conv.py): the main loop is
+        // L2->smem bandwidth bound, not MMA bound, so the cost is NOT proportional to BN.
+        const double cost_bf16[3] = {880, 770, 700}, cost_x3[3] = {2230, 1190, 1030};
+        const double* cost = (x_lo != nullptr) ? cost_x3 : cost_bf16;
         for (int i = 0; i < 3; ++i) {
             if (cand[i] > 64 && cand[i] > cout_cover && cand[i] / 2 >= cout_cover) continue;  // too wide
             long tiles = m_tiles * cdiv(cout_cover, cand[i]);

@@ -376,6 +376,54 @@ extern "C" int frcnn_head_decode(const float* scores, const float* deltas, int l
     return FRCNN_OK;
 }
 
+namespace frcnn {
+__global__ void bbox_decode_kernel(const float* boxes, const float* trans, int N, int K, int clip, int im_h, int im_w,
+                                   int min_size, float* out, unsigned char* ok_flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    const int n = i / K;
+    float4 o;
+    if (trans == nullptr) {        // clip / filter only: `boxes` is [N, 4K]
+        o = reinterpret_cast<const float4*>(boxes)[i];
+    } else {
+        const float4 a = reinterpret_cast<const float4*>(boxes)[n];
+        const float4 d = reinterpret_cast<const float4*>(trans)[i];
+        const float bw = __fadd_rn(__fsub_rn(a.z, a.x), 1.0f), bh = __fadd_rn(__fsub_rn(a.w, a.y), 1.0f);
+        const float cx = __fadd_rn(a.x, __fmul_rn(0.5f, bw)), cy = __fadd_rn(a.y, __fmul_rn(0.5f, bh));
+        const float pcx = __fadd_rn(__fmul_rn(d.x, bw), cx), pcy = __fadd_rn(__fmul_rn(d.y, bh), cy);
+        const float pw = __fmul_rn(det_expf(d.z), bw), ph = __fmul_rn(det_expf(d.w), bh);
+        o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+        o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+        o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+        o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+    }
+    if (clip) {
+        const float wmax = (float)(im_w - 1), hmax = (float)(im_h - 1);
+        o.x = fmaxf(fminf(o.x, wmax), 0.0f);
+        o.y = fmaxf(fminf(o.y, hmax), 0.0f);
+        o.z = fmaxf(fminf(o.z, wmax), 0.0f);
+        o.w = fmaxf(fminf(o.w, hmax), 0.0f);
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+    if (ok_flags) {
+        const float ws = __fadd_rn(__fsub_rn(o.z, o.x), 1.0f), hs = __fadd_rn(__fsub_rn(o.w, o.y), 1.0f);
+        ok_flags[i] = (ws >= (float)min_size && hs >= (float)min_size) ? 1 : 0;
+    }
+}
+}  // namespace frcnn
+
+extern "C" int frcnn_bbox_decode(const float* boxes, const float* trans, int N, int K, int clip, int im_h, int im_w,
+                                 int min_size, float* out, unsigned char* ok_flags, void* stream) {
+    FRCNN_REQUIRE(N >= 0 && K > 0, "frcnn_bbox_decode: bad N=%d K=%d", N, K);
+    if (N == 0) return FRCNN_OK;
+    FRCNN_REQUIRE(boxes && out, "frcnn_bbox_decode: NULL argument");   // trans == NULL: clip / filter only
+    FRCNN_REQUIRE(!ok_flags || K == 1, "frcnn_bbox_decode: ok_flags needs K == 1");
+    bbox_decode_kernel<<<cdiv(N * K, 128), 128, 0, (cudaStream_t)stream>>>(boxes, trans, N, K, clip, im_h, im_w, min_size,
+                                                                          out, ok_flags);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
 extern "C" int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_cap, int num_classes,
                             double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count,
                             void* stream) {

@@ -152,6 +152,20 @@ def head_decode(scores_deltas, ld, rois, count, num_classes, im_h, im_w, out_pro
     return out_prob, out_boxes
 
 
+def bbox_decode(boxes, trans, clip_to=None, min_size=None):
+    """frcnn_bbox_decode: boxes [N,4], trans [N,4K] CUDA fp32 -> out [N,4K] (+ uint8 ok flags if min_size)."""
+    _need_cuda(boxes, trans)
+    boxes = boxes.contiguous().float()
+    trans = trans.contiguous().float() if trans is not None else None
+    N, K = boxes.shape[0], (trans if trans is not None else boxes).shape[1] // 4
+    out = torch.empty_like(trans if trans is not None else boxes)
+    flags = torch.empty((N,), dtype=torch.uint8, device=boxes.device) if min_size is not None else None
+    im_h, im_w = (int(clip_to[0]), int(clip_to[1])) if clip_to is not None else (0, 0)
+    check(_lib.load().frcnn_bbox_decode(_p(boxes), _p(trans), N, max(K, 1), 1 if clip_to is not None else 0, im_h, im_w,
+                                        int(min_size or 0), _p(out), _p(flags), _stream()), "frcnn_bbox_decode")
+    return out, flags
+
+
 def detect(prob, boxes, count=None, nms_thresh=0.3, conf=0.8):
     R_cap, NC = prob.shape
     dev = prob.device

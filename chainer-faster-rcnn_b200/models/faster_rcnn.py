@@ -1,0 +1,108 @@
+"""models.faster_rcnn.FasterRCNN -- same class, constructor, train switches, side outputs and call
+signature as /root/reference models/faster_rcnn.py:19-178, inference branch (:92-134,175-178):
+
+    cls_prob, pred_boxes = model(x, img_info)      # Variable (R,21) softmax, ndarray (R,84) boxes
+
+The whole graph (trunk -> RPN -> ProposalLayer -> RoI pool -> fc6/fc7 -> cls/bbox -> softmax/decode/
+clip) is frcnn_b200.engine: hand-written sm_100a kernels behind the C ABI, replayed as ONE CUDA graph
+per image shape.  Link names / parameter paths are the reference's, so `serializers.load_npz` of a
+reference checkpoint (forward.py:29) fills this model.  The RCNN / RPN training branches
+(:115-116,136-173) are "next" rows and raise NotImplementedError.
+"""
+import os
+
+import numpy as np
+import torch
+
+from frcnn_b200 import arrays, links
+from frcnn_b200.engine import Engine
+from models.bbox_transform import bbox_transform_inv, clip_boxes  # noqa: F401  (reference import surface)
+from models.region_proposal_network import RegionProposalNetwork
+from models.vgg16 import VGG16
+
+
+class FasterRCNN(links.Link):
+    type_check_enable = int(os.environ.get('CHAINER_TYPE_CHECK', '1')) != 0
+    precision = "bf16x3"        # "bf16": single-pass fast mode (not the parity mode)
+
+    def __init__(self, trunk_class=VGG16, rpn_in_ch=512, rpn_mid_ch=512, feat_stride=16,
+                 anchor_ratios=(0.5, 1, 2), anchor_scales=(8, 16, 32), num_classes=21, loss_lambda=1,
+                 rpn_delta=3, rcnn_delta=1):
+        super(FasterRCNN, self).__init__()
+        self.add_link("trunk", trunk_class())
+        self.add_link("RPN", RegionProposalNetwork(rpn_in_ch, rpn_mid_ch, feat_stride, anchor_ratios,
+                                                   anchor_scales, num_classes, loss_lambda, rpn_delta))
+        self.add_link("fc6", links.linear_link(rpn_in_ch * 7 * 7, 4096, 0.01))
+        self.add_link("fc7", links.linear_link(4096, 4096, 0.01))
+        self.add_link("cls_score", links.linear_link(4096, num_classes, 0.01))
+        self.add_link("bbox_pred", links.linear_link(4096, num_classes * 4, 0.01))
+        d = self.__dict__
+        d["_feat_stride"], d["_anchor_ratios"], d["_anchor_scales"] = feat_stride, anchor_ratios, anchor_scales
+        d["_num_classes"], d["_spatial_scale"] = num_classes, 1. / feat_stride
+        d["_rpn_delta"], d["_rcnn_delta"] = rpn_delta, rcnn_delta
+        d["_rcnn_train"] = False
+        d["_engine"] = (None, -1)
+        d["rpn_proposals"], d["rpn_probs"] = None, None
+        self.RPN.train = False
+
+    # -- train switches with the reference's coupling (:48-74)
+    @property
+    def rcnn_train(self):
+        return self._rcnn_train
+
+    @rcnn_train.setter
+    def rcnn_train(self, val):
+        self.__dict__["_rcnn_train"] = val
+        if val:
+            self.RPN.train = not val
+        self.trunk.__dict__["train"] = bool(self.rcnn_train or self.rpn_train)
+
+    @property
+    def rpn_train(self):
+        return self.RPN.train
+
+    @rpn_train.setter
+    def rpn_train(self, val):
+        self.RPN.train = val
+        if val:
+            self.__dict__["_rcnn_train"] = not val
+        self.trunk.__dict__["train"] = bool(self.rcnn_train or self.rpn_train)
+
+    def _check_data_type_forward(self, x, img_info, gt_boxes):
+        from chainer import Variable
+        assert isinstance(x, Variable) and isinstance(img_info, Variable)
+        assert x.shape[0] == 1 and arrays.dtype_kind(x) == 'f'
+        assert img_info.shape == (1, 2) and arrays.dtype_kind(img_info) == 'i'
+        if gt_boxes is not None:
+            assert isinstance(gt_boxes, Variable)
+            assert gt_boxes.shape[0] == 1 and gt_boxes.shape[1] > 0 and gt_boxes.shape[2] == 5
+            assert arrays.dtype_kind(gt_boxes) == 'f'
+
+    def engine(self):
+        eng, ver = self._engine
+        if eng is None or ver != self._version:
+            params = self.param_dict()
+            eng = Engine(params, precision=self.precision, anchors=self.RPN.proposal_layer._anchors,
+                         num_classes=self._num_classes, n_anchors=self.RPN.proposal_layer._num_anchors,
+                         feat_stride=self._feat_stride)
+            self.__dict__["_engine"] = (eng, self._version)
+        return eng
+
+    def __call__(self, x, img_info, gt_boxes=None):
+        """x (1,3,H,W) preprocessed image, img_info (1,2) = (height, width) as the caller passes it
+        (forward.py:93 passes (H, H), Q7) -> (Variable softmax (R,num_classes), pred_boxes (R,4*num_classes))."""
+        from chainer import Variable
+        if self.type_check_enable:
+            self._check_data_type_forward(x, img_info, gt_boxes)
+        if gt_boxes is not None and (self.rpn_train or self.rcnn_train):
+            raise NotImplementedError("training branches (models/faster_rcnn.py:115-116,136-173) are outside the forward path")
+        fam = arrays.family(x)
+        t = arrays.to_device(x)
+        hw = arrays.to_host_ints(img_info)
+        pl = self.RPN.proposal_layer
+        prob, boxes, plan = self.engine()(t[0], img_info=(int(hw[0]), int(hw[1])), pre_n=pl._pre_nms_top_n,
+                                          post_n=pl._post_nms_top_n, nms_thresh=pl._nms_thresh, min_size=pl._min_size)
+        R = prob.shape[0]
+        self.__dict__["rpn_proposals"] = arrays.from_device(plan.prop.rois[:R].clone(), fam)
+        self.__dict__["rpn_probs"] = arrays.from_device(plan.prop.scores[:R].reshape(R, 1).clone(), fam)
+        return Variable(arrays.from_device(prob.clone(), fam)), arrays.from_device(boxes.clone(), fam)

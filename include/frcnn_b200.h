@@ -142,6 +142,15 @@ int frcnn_head_decode(const float* scores, const float* deltas, int ld, const fl
                       int R_cap, int num_classes, int im_h, int im_w, float* out_prob, float* out_boxes,
                       void* stream);
 
+/* Stand-alone box algebra, the array-level helpers of models/bbox_transform.py:
+ *   out[n, 4k..4k+3] = bbox_transform_inv(boxes[n], trans[n, 4k..4k+3])   (:41-76), k < K
+ *   clip != 0 additionally applies clip_boxes(out, (im_h, im_w))          (:79-99)
+ *   ok_flags (optional, K == 1): 1 where both sides >= min_size           (filter_boxes, :102-109)
+ * boxes [N,4], trans [N,4K], out [N,4K] fp32; bit-identical to the fused kernels.
+ * trans == NULL: `boxes` is [N,4K] and only the clip / filter steps are applied. */
+int frcnn_bbox_decode(const float* boxes, const float* trans, int N, int K, int clip, int im_h, int im_w,
+                      int min_size, float* out, unsigned char* ok_flags, void* stream);
+
 /* Per-class detection (forward.py:48-57): for cls 1..num_classes-1 greedy NMS (cpu_nms semantics,
  * thresh) over (boxes[:,4c:4c+4], prob[:,c]), then score >= conf.
  * keep_idx [num_classes-1, R_cap] (RoI indices, descending score), keep_count [num_classes-1] =
