@@ -1,9 +1,11 @@
 // conv_gemm_sm100.cu -- implicit-GEMM 3x3 / 1x1 convolution (and plain GEMM) on 5th-gen tensor
 // cores: TMA -> 128B-swizzled shared memory -> tcgen05.mma (kind::f16, bf16 operands, fp32
-// accumulators in TMEM) -> tcgen05.ld epilogue with fused bias + ReLU (+ bf16 hi/lo split).
+// accumulators in TMEM) -> tcgen05.ld epilogue with fused bias + ReLU (+ bf16 hi/lo split,
+// + optional fused 2x2 ceil-mode max-pool) -> swizzled smem staging -> TMA bulk tensor store.
 //
 // Replaces, for the forward path: L.Convolution2D at /root/reference models/vgg16.py:39-67 and
-// models/region_proposal_network.py:53-57, and L.Linear at models/faster_rcnn.py:33-36.
+// models/region_proposal_network.py:53-57, L.Linear at models/faster_rcnn.py:33-36, and (fused)
+// F.MaxPooling2D(2,2) at models/vgg16.py:43,48,55,62.
 //
 // Mapping (NHWC activations, tap-major K-major weights):
 //   M = output pixels, tiled as TH x TW patches of 128 pixels;  N = output channels (BN per tile);
@@ -15,12 +17,17 @@
 //
 // Kernel structure: persistent, one CTA per SM, 6 warps:
 //   warp 0    : TMA producer (one elected lane)         smem ring, full/empty mbarriers
-//   warp 1    : TMEM allocator + MMA issuer (one lane)  double-buffered accumulators in TMEM
+//   warp 1    : TMEM allocator + MMA issuer (one lane)  ring of accumulators in TMEM
 //   warps 2-5 : epilogue (TMEM lane group = warp % 4)   overlaps the next tile's main loop
 //
 // "bf16x3" mode (lo planes present): per k-block the stage holds A_hi, A_lo, B_hi, B_lo and the
-// issuer runs A_hi*B_hi + A_lo*B_hi + A_hi*B_lo into the same accumulator (fp32-class accuracy,
-// 3x the tensor work, 1.33x the smem bytes of the single-pass mode).
+// issuer runs A_hi*B_hi into the main accumulator and A_lo*B_hi + A_hi*B_lo into a separate
+// correction accumulator (the tensor-core accumulator truncates on every add).
+//
+// Epilogue stores: a thread owns one pixel row of the accumulator.  Per 32-channel chunk it writes
+// its 64 B (hi) + 64 B (lo) into a SWIZZLE_64B staging tile (bank-conflict free), and one thread
+// issues a 3-D TMA store {32 ch, TW, TH} which clips the ragged image edge -- 2 bulk stores per
+// chunk instead of 1024 16-byte STG (the first version was store-issue bound on the 64-channel layers).
 #include <cuda.h>
 
 #include <mutex>
@@ -34,11 +41,10 @@ struct ConvParams {
     int H, W, Cout;
     int taps, ksize, cin_blocks;
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
-    int num_stages, x3, relu;
+    int num_stages, x3, relu, pool;
     int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
     int ld_f32, n_cover;
-    __nv_bfloat16* y_hi;
-    __nv_bfloat16* y_lo;
+    int store_bf16, store_lo;            // bf16 outputs go through the staged TMA store
     float* y_f32;
     const float* bias;
     const int* m_valid;
@@ -46,19 +52,31 @@ struct ConvParams {
 
 constexpr int kNumThreads = 192;
 constexpr int kTileM = 128;
+constexpr int kStagePlane = kTileM * 64;          // one staging plane: 128 rows x 32 bf16
+constexpr int kStagingBytes = 2 * 2 * kStagePlane;   // 2 buffers x (hi, lo)
+constexpr int kBarrierBytes = 512;
 
 template <int BN, int BK>
 struct Cfg {
     static constexpr int ROW_BYTES = BK * 2;
     static constexpr int A_BYTES = kTileM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 };
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, float& rb) {
+    // returns packed (bf16(a), bf16(b)); ra/rb = residuals a - hi, b - hi (exact in fp32)
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+    ra = a - __uint_as_float(u << 16);
+    rb = b - __uint_as_float(u & 0xFFFF0000u);
+    return u;
+}
 
 template <int BN, int BK>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
                  const ConvParams p) {
     using C = Cfg<BN, BK>;
     extern __shared__ uint8_t smem_raw[];
@@ -67,7 +85,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
     const int S = p.num_stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint8_t* staging = smem + (size_t)S * stage_bytes;                 // 1024-aligned (stage sizes are multiples of 1 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (p.store_bf16 ? kStagingBytes : 0));
     uint64_t* full_bar = bars;            // [S]
     uint64_t* empty_bar = bars + S;       // [S]
     uint64_t* tfull_bar = bars + 2 * S;   // [2]
@@ -84,6 +103,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             ptx::prefetch_tensormap(&tm_a_lo);
             ptx::prefetch_tensormap(&tm_b_lo);
         }
+        if (p.store_bf16) ptx::prefetch_tensormap(&tm_y_hi);
+        if (p.store_lo) ptx::prefetch_tensormap(&tm_y_lo);
         for (int i = 0; i < S; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -180,13 +201,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int lg = warp & 3;                 // TMEM lane group this warp may access
         const int row = lg * 32 + lane;          // accumulator row == pixel within the tile
         const int m_valid = p.m_valid ? *p.m_valid : 0x7fffffff;
+        const bool issuer = (warp == 2 && lane == 0);     // the one thread that owns the bulk-store groups
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t chunk_i = 0;                    // running chunk counter -> staging buffer parity
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int mt = tile / p.n_tiles;
-            const int h = (mt / p.tiles_w) * p.TH + row / p.TW;
-            const int w = (mt % p.tiles_w) * p.TW + row % p.TW;
+            const int h0 = (mt / p.tiles_w) * p.TH, w0 = (mt % p.tiles_w) * p.TW;
+            const int h = h0 + row / p.TW;
+            const int w = w0 + row % p.TW;
             const int n0 = nt * BN;
             const bool in_img = (h < p.H) && (w < p.W);
             const long pix = (long)h * p.W + w;
@@ -231,31 +255,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.0f;
                 }
-                if (in_img) {
-                    if (p.y_f32 != nullptr && n < p.ld_f32) {
-                        float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.ld_f32 + n);
+                if (in_img && p.y_f32 != nullptr && n < p.ld_f32) {
+                    float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.ld_f32 + n);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                    if (p.y_hi != nullptr && n < p.Cout) {
-                        uint32_t hi[16], lo[16];
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (p.store_bf16 && n < p.Cout) {          // CTA-uniform condition
+                    int srow = row;                         // row of the staging tile this thread fills
+                    bool writer = true;
+                    if (p.pool) {
+                        // F.MaxPooling2D(2,2) ceil mode fused: tile is 8x16 pixels, a warp holds two tile
+                        // rows (lanes 0-15 / 16-31), so the 2x2 window is lanes {l, l^1, l^16, l^17}.
+                        // Out-of-image pixels were zeroed above and every valid value is >= 0 (ReLU), so the
+                        // max over the valid part of a partial window is unchanged (Chainer cover_all=True).
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(v[2 * j], h0, l0);
-                            split_bf16(v[2 * j + 1], h1, l1);
-                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        for (int j = 0; j < 32; ++j) {
+                            float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                            v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
                         }
-                        uint4* dh = reinterpret_cast<uint4*>(p.y_hi + pix * p.Cout + n);
+                        writer = (lane & 17) == 0;
+                        srow = lg * 8 + ((lane & 15) >> 1);     // pooled tile: 4 rows x 8 cols
+                    }
+                    uint8_t* sb = staging + (chunk_i & 1u) * (2 * kStagePlane);
+                    // the bulk store that last read this staging buffer (2 chunks ago) must be done reading
+                    if (issuer) ptx::bulk_wait_group_read<1>();
+                    ptx::named_bar_sync(1, 128);
+                    if (writer) {
+                        const int sw = (srow >> 1) & 3;        // SWIZZLE_64B: 16-B chunk index ^= address bits [7:8]
+                        uint8_t* rowp = sb + srow * 64;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        if (p.y_lo != nullptr) {
-                            uint4* dl = reinterpret_cast<uint4*>(p.y_lo + pix * p.Cout + n);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int q = 0; q < 4; ++q) {
+                            float ra[8];
+                            uint4 hv;
+                            hv.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1], ra[0], ra[1]);
+                            hv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3], ra[2], ra[3]);
+                            hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
+                            hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
+                            *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = hv;
+                            if (p.store_lo) {
+                                float d0, d1;
+                                uint4 lv;
+                                lv.x = pack_bf16x2(ra[0], ra[1], d0, d1);
+                                lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
+                                lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
+                                lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
+                                *reinterpret_cast<uint4*>(rowp + kStagePlane + ((q ^ sw) << 4)) = lv;
+                            }
                         }
                     }
+                    ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
+                    ptx::named_bar_sync(1, 128);
+                    if (issuer) {
+                        const int ow = p.pool ? (w0 >> 1) : w0, oh = p.pool ? (h0 >> 1) : h0;
+                        ptx::tma_store_3d(&tm_y_hi, sb, n, ow, oh);
+                        if (p.store_lo) ptx::tma_store_3d(&tm_y_lo, sb + kStagePlane, n, ow, oh);
+                        ptx::bulk_commit_group();
+                    }
+                    ++chunk_i;
                 }
             }
             ptx::tc_fence_before();
@@ -263,6 +319,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
             if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
+        if (issuer) ptx::bulk_wait_group<0>();     // staging smem must outlive the last bulk store
     }
 
     ptx::tc_fence_before();
@@ -293,7 +350,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D bf16 tensor map: dims (innermost first) {d0,d1,d2}, row pitch d0 elements, box {b0,b1,b2}.
+// 3-D bf16 tensor map: dims (innermost first) {d0,d1,d2}, row pitch d0 elements, box {b0,b1,b2};
+// swizzle span = the box's inner extent in bytes (32 / 64 / 128).
 static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
                         uint32_t b1, uint32_t b2) {
     EncodeTiledFn enc = get_encode_fn();
@@ -332,19 +390,18 @@ static int device_sm_count() {
 }
 
 template <int BN, int BK>
-static int launch_conv(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
-                       const CUtensorMap& tb_lo, ConvParams p, cudaStream_t stream) {
+static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream) {
     using C = Cfg<BN, BK>;
     const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
-    const int budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
-    int stages = budget / stage_bytes;
+    const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0);
+    int stages = (227 * 1024 - fixed) / stage_bytes;
     if (stages > 24) stages = 24;
     if (stages < 2) {
         set_error("conv tile BN=%d BK=%d does not fit 2 pipeline stages", BN, BK);
         return FRCNN_ERR_ARG;
     }
     p.num_stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 512;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
     p.acc_cols = p.x3 ? 2 * BN : BN;
     p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
     p.tmem_cols = 32;
@@ -352,7 +409,7 @@ static int launch_conv(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
     auto kern = conv_gemm_kernel<BN, BK>;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-    kern<<<grid, kNumThreads, smem, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    kern<<<grid, kNumThreads, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }
@@ -368,8 +425,8 @@ extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
 }
 
 extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
-                            const void* w_lo, const float* bias, int Cout, int ksize, int relu, void* y_hi,
-                            void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
+                            const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
+                            void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(x_hi && w_hi && bias, "frcnn_conv2d: x_hi, w_hi and bias are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
@@ -380,14 +437,19 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     FRCNN_REQUIRE(!y_hi || Cout % 32 == 0, "frcnn_conv2d: bf16 output needs Cout %% 32 == 0 (got %d)", Cout);
     FRCNN_REQUIRE(!y_f32 || (ld_f32 % 32 == 0 && ld_f32 >= Cout), "frcnn_conv2d: ld_f32 must be a multiple of 32 and >= Cout");
     FRCNN_REQUIRE(!y_lo || y_hi, "frcnn_conv2d: y_lo without y_hi");
+    FRCNN_REQUIRE(!fuse_pool2x2 || (y_hi && relu && !y_f32 && !m_valid),
+                  "frcnn_conv2d: fuse_pool2x2 needs a bf16 output, relu=1, no fp32 output and no m_valid");
 
     const int BK = (Cin >= 64) ? 64 : (Cin >= 32 ? 32 : 16);
     FRCNN_REQUIRE(BK != 32, "frcnn_conv2d: Cin in [32,64) is not supported (use 16 or >= 64)");
 
-    // ---- pixel tile: minimise padded pixels
+    // ---- pixel tile: minimise padded pixels (the fused pool needs the 8x16 tile: 2x2 windows inside a warp)
     static const int shapes[6][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
     int TH = 8, TW = 16;
-    if (g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM) {
+    if (fuse_pool2x2) {
+        TH = 8;
+        TW = 16;
+    } else if (g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM) {
         TH = g_force_th;
         TW = g_force_tw;
     } else {
@@ -400,7 +462,7 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     const int tiles_h = cdiv(H, TH), tiles_w = cdiv(W, TW);
     const long m_tiles = (long)tiles_h * tiles_w;
 
-    // ---- N tile: minimise waves x per-k-step cost (N=64 is smem-bandwidth bound: 48 vs 32 cycles)
+    // ---- N tile: minimise waves x measured per-k-block cost
     const int cout_cover = y_f32 ? (ld_f32 > Cout ? ld_f32 : Cout) : Cout;
     int BN = 0;
     if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) {
@@ -431,28 +493,43 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     p.num_stages = 0;
     p.x3 = x_lo != nullptr;
     p.relu = relu;
+    p.pool = fuse_pool2x2 ? 1 : 0;
     p.ld_f32 = ld_f32;
     p.n_cover = cdiv(cout_cover, 32) * 32;
-    p.y_hi = static_cast<__nv_bfloat16*>(y_hi);
-    p.y_lo = static_cast<__nv_bfloat16*>(y_lo);
+    p.store_bf16 = y_hi != nullptr;
+    p.store_lo = y_lo != nullptr;
     p.y_f32 = y_f32;
     p.bias = bias;
     p.m_valid = m_valid;
+    p.acc_bufs = p.acc_cols = p.tmem_cols = 0;
 
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    CUtensorMap tm[6];
     int rc;
-    if ((rc = make_tmap_3d(&ta_hi, x_hi, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
-    if ((rc = make_tmap_3d(&tb_hi, w_hi, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+    if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+    if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
     if (p.x3) {
-        if ((rc = make_tmap_3d(&ta_lo, x_lo, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
-        if ((rc = make_tmap_3d(&tb_lo, w_lo, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
     } else {
-        ta_lo = ta_hi;
-        tb_lo = tb_hi;
+        tm[1] = tm[0];
+        tm[3] = tm[2];
+    }
+    if (y_hi) {
+        const int Ho = p.pool ? (H + 1) / 2 : H, Wo = p.pool ? (W + 1) / 2 : W;
+        const int bw = p.pool ? TW / 2 : TW, bh = p.pool ? TH / 2 : TH;
+        if ((rc = make_tmap_3d(&tm[4], y_hi, Cout, Wo, Ho, 32, bw, bh)) != FRCNN_OK) return rc;
+        if (y_lo) {
+            if ((rc = make_tmap_3d(&tm[5], y_lo, Cout, Wo, Ho, 32, bw, bh)) != FRCNN_OK) return rc;
+        } else {
+            tm[5] = tm[4];
+        }
+    } else {
+        tm[4] = tm[0];
+        tm[5] = tm[0];
     }
 
 #define FRCNN_DISPATCH(BN_, BK_) \
-    if (BN == BN_ && BK == BK_) return launch_conv<BN_, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, p, stream);
+    if (BN == BN_ && BK == BK_) return launch_conv<BN_, BK_>(tm, p, stream);
     FRCNN_DISPATCH(256, 64)
     FRCNN_DISPATCH(128, 64)
     FRCNN_DISPATCH(64, 64)

@@ -34,7 +34,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_void_p]),
     "frcnn_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                             c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "frcnn_conv2d_set_tile": (None, [c_int, c_int, c_int]),
     "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_void_p]),

@@ -79,7 +79,8 @@ class ForwardPlan(object):
     """Buffers + launch sequence for one image shape."""
 
     def __init__(self, weights, H, W, pre_n=6000, post_n=300, nms_thresh=0.7, min_size=16, feat_stride=16,
-                 anchors=None, with_detect=False, det_nms_thresh=0.3, det_conf=0.8, use_graph=True, keep_rpn_debug=False):
+                 anchors=None, with_detect=False, det_nms_thresh=0.3, det_conf=0.8, use_graph=True, keep_rpn_debug=False,
+                 fuse_pool=True):
         self.w, self.H, self.W = weights, H, W
         dev = weights.device
         x3 = weights.precision == "bf16x3"
@@ -98,15 +99,22 @@ class ForwardPlan(object):
         self.img_info = torch.tensor([H, W], dtype=torch.int32, device=dev)      # clip bounds (h, w): static in the graph
         self.acts = [act(H, W, 16)]
         h, w_ = H, W
-        self.trunk_steps = []
-        for item in VGG16_LAYERS:
+        self.trunk_steps = []          # (layer name, fuse the following 2x2 pool into the conv epilogue)
+        for i, item in enumerate(VGG16_LAYERS):
             if item == "pool":
+                continue
+            fuse = fuse_pool and i + 1 < len(VGG16_LAYERS) and VGG16_LAYERS[i + 1] == "pool"
+            pooled = i + 1 < len(VGG16_LAYERS) and VGG16_LAYERS[i + 1] == "pool"
+            if fuse:
                 h, w_ = (h + 1) // 2, (w_ + 1) // 2
-                self.acts.append(act(h, w_, self.acts[-1].hi.shape[2]))
-                self.trunk_steps.append(("pool", None))
+                self.acts.append(act(h, w_, item[2]))
+                self.trunk_steps.append((item[0], True, False))
             else:
                 self.acts.append(act(h, w_, item[2]))
-                self.trunk_steps.append(("conv", item[0]))
+                self.trunk_steps.append((item[0], False, pooled))
+                if pooled:
+                    h, w_ = (h + 1) // 2, (w_ + 1) // 2
+                    self.acts.append(act(h, w_, item[2]))
         self.fh, self.fw = h, w_
         self.rpn_mid = act(h, w_, 512)
         self.rpn_out = torch.empty((h * w_, weights.rpn_ld), dtype=torch.float32, device=dev)
@@ -134,15 +142,15 @@ class ForwardPlan(object):
                   "frcnn_pack_image")
         n += 1
         i = 0
-        for kind, name in self.trunk_steps:
-            src, dst = self.acts[i], self.acts[i + 1]
-            if kind == "pool":
-                ops.maxpool2x2_ceil(src, out=dst)
-            else:
-                hi, lo, b = w.convs[name]
-                ops.conv2d(src, hi, lo, b, 3, True, out=dst)
+        for name, fused, pool_after in self.trunk_steps:
+            hi, lo, b = w.convs[name]
+            ops.conv2d(self.acts[i], hi, lo, b, 3, True, out=self.acts[i + 1], fuse_pool=fused)
             n += 1
             i += 1
+            if pool_after:
+                ops.maxpool2x2_ceil(self.acts[i], out=self.acts[i + 1])
+                n += 1
+                i += 1
         feat = self.acts[-1]
         hi, lo, b = w.rpn3
         ops.conv2d(feat, hi, lo, b, 3, True, out=self.rpn_mid)

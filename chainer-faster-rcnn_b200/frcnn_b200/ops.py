@@ -86,8 +86,10 @@ def pad_bias(b, n):
     return out
 
 
-def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=None, out=None, out_f32=None):
-    """frcnn_conv2d: x Act [H,W,Cin]; returns (Act or None, fp32 [H*W, ld_f32] or None)."""
+def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=None, out=None, out_f32=None,
+           fuse_pool=False):
+    """frcnn_conv2d: x Act [H,W,Cin]; returns (Act or None, fp32 [H*W, ld_f32] or None).
+    fuse_pool: the Act output is the 2x2 ceil-mode max-pooled map [ceil(H/2), ceil(W/2), Cout]."""
     H, W, Cin = x.hi.shape
     taps, Cout, cin_w = w_hi.shape
     if cin_w != Cin or taps != ksize * ksize:
@@ -96,7 +98,8 @@ def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=Non
         raise FrcnnError("conv2d: activation and weight precision modes differ")
     y = out
     if out_act and y is None:
-        yh = torch.empty((H, W, Cout), dtype=torch.bfloat16, device=x.hi.device)
+        oh, ow = ((H + 1) // 2, (W + 1) // 2) if fuse_pool else (H, W)
+        yh = torch.empty((oh, ow, Cout), dtype=torch.bfloat16, device=x.hi.device)
         y = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
     y32 = out_f32
     if ld_f32 and y32 is None:
@@ -105,7 +108,7 @@ def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=Non
     if bias.numel() < need:
         raise FrcnnError("conv2d: bias has %d entries, needs %d (use pad_bias)" % (bias.numel(), need))
     check(_lib.load().frcnn_conv2d(_p(x.hi), _p(x.lo), H, W, Cin, _p(w_hi), _p(w_lo), _p(bias), Cout, ksize,
-                                   1 if relu else 0, _p(y.hi) if y else None, _p(y.lo) if y else None,
+                                   1 if relu else 0, 1 if fuse_pool else 0, _p(y.hi) if y else None, _p(y.lo) if y else None,
                                    _p(y32), ld_f32, _p(m_valid), _stream()), "frcnn_conv2d")
     return y, y32
 

@@ -53,12 +53,12 @@ class VGG16Prev(links.Link):
         """(3,H,W) CUDA float32 -> ops.Act [h,w,512] (NHWC bf16 hi/lo)."""
         packed = self._weights(x_chw.device)
         act = ops.pack_image(x_chw, c_pad=16, precision=self.precision)
-        for item in _PLAN:
+        for i, item in enumerate(_PLAN):
             if item is None:
-                act = ops.maxpool2x2_ceil(act)
-            else:
-                hi, lo, b = packed[item[0]]
-                act, _ = ops.conv2d(act, hi, lo, b, 3, True)
+                continue                      # the 2x2 ceil-mode pool is fused into the preceding conv's epilogue
+            hi, lo, b = packed[item[0]]
+            pooled = i + 1 < len(_PLAN) and _PLAN[i + 1] is None
+            act, _ = ops.conv2d(act, hi, lo, b, 3, True, fuse_pool=pooled)
         return act
 
     def __call__(self, x):

@@ -100,11 +100,14 @@ int frcnn_proposals(const float* cls, long cls_chan_stride, long cls_pix_stride,
  *   y_hi/y_lo : [H,W,Cout] bf16 outputs (may be NULL), Cout % 32 == 0 when used
  *   y_f32     : [H*W, ld_f32] fp32 output (may be NULL), ld_f32 % 32 == 0, ld_f32 >= Cout;
  *               padded columns receive 0 (+bias pad)
+ *   fuse_pool2x2 : != 0 fuses F.MaxPooling2D(2,2) (ceil mode, models/vgg16.py:43,48,55,62) into the
+ *               epilogue: y_hi/y_lo are then [ceil(H/2), ceil(W/2), Cout] and the un-pooled map is never
+ *               written (needs relu != 0, bf16 output only)
  *   m_valid   : optional device int: rows (pixels) >= *m_valid are written as zeros (GEMM over a
  *               data-dependent number of RoIs); NULL = all valid.
  */
 int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi, const void* w_lo,
-                 const float* bias, int Cout, int ksize, int relu, void* y_hi, void* y_lo, float* y_f32,
+                 const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2, void* y_hi, void* y_lo, float* y_f32,
                  int ld_f32, const int* m_valid, void* stream);
 /* Tuning override for tests / benchmarks: force the N tile (64/128/256) and the pixel tile
  * (tile_h*tile_w == 128); 0 = automatic. Process-wide. */

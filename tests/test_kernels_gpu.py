@@ -224,6 +224,34 @@ def test_conv2d_first_layer_from_3_channels(ops):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("shape", [(37, 45, 64, 64), (600 // 4, 1000 // 4 + 1, 64, 128), (19, 31, 128, 256)])
+def test_conv2d_fused_maxpool_equals_conv_then_pool(ops, precision, shape):
+    """The fused epilogue (conv + ReLU + 2x2 ceil-mode max-pool, odd H/W included) must give exactly the
+    device's own un-fused conv followed by frcnn_maxpool2x2_ceil -- and match the oracle's pooled map."""
+    H, W, Cin, Cout = shape
+    rng = np.random.default_rng(H + W)
+    x = rng.standard_normal((Cin, H, W)).astype(f32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) * (2.0 / (9 * Cin)) ** 0.5).astype(f32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(f32)
+    act = ops.pack_image(dev(x), c_pad=Cin, precision=precision)
+    wh, wl = ops.pack_conv_weights(dev(w), precision=precision)
+    bias = ops.pad_bias(dev(b), Cout)
+    y_full, _ = ops.conv2d(act, wh, wl, bias, 3, True)
+    want = ops.maxpool2x2_ceil(y_full)
+    got, _ = ops.conv2d(act, wh, wl, bias, 3, True, fuse_pool=True)
+    assert got.hi.shape == ((H + 1) // 2, (W + 1) // 2, Cout)
+    assert torch.equal(got.hi, want.hi)
+    if precision == "bf16x3":
+        assert torch.equal(got.lo, want.lo)
+    q = _quant16 if precision == "bf16x3" else _bf16
+    ref = torch.nn.functional.conv2d(torch.from_numpy(q(x))[None].double(), torch.from_numpy(q(w)).double(),
+                                     torch.from_numpy(b).double(), padding=1).clamp_min(0)
+    ref = torch.nn.functional.max_pool2d(ref, 2, 2, ceil_mode=True)[0].numpy()
+    err = np.abs(got.to_chw_f32().cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < (5e-5 if precision == "bf16x3" else 6e-3), err
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 def test_linear_as_1x1_with_row_count(ops, precision):
     """L.Linear over R RoIs == 1x1 conv with H=1, W=R; rows >= *m_valid come out as zeros."""
     rng = np.random.default_rng(21)
