@@ -41,7 +41,7 @@ struct ConvParams {
     int H, W, Cout;
     int taps, ksize, cin_blocks;
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
-    int num_stages, x3, relu, pool;
+    int num_stages, a_stages, x3, relu, pool;
     int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
     int ld_f32, n_cover;
     int store_bf16, store_lo;            // bf16 outputs go through the staged TMA store
@@ -55,6 +55,14 @@ constexpr int kTileM = 128;
 constexpr int kStagePlane = kTileM * 64;          // one staging plane: 128 rows x 32 bf16
 constexpr int kStagingBytes = 2 * 2 * kStagePlane;   // 2 buffers x (hi, lo)
 constexpr int kBarrierBytes = 512;
+// HALO mode (3x3, Cin >= 64): the pixel tile is 16 rows x 8 columns and ONE (16+2) x (8+2) halo patch of the
+// input (180 pixel rows of 128 B, SWIZZLE_128B) is loaded per 64-channel block and shared by all 9 taps: the A
+// descriptor of tap (r,s) starts at halo row r*10+s and strides 10 rows (SBO = 1280 B) between its 8-row groups.
+// (tests/experiments/umma_desc_probe.cu: with the descriptor's base-offset field 0 the MMA reads rows linearly
+// from any 128-B-aligned start with any SBO, swizzle intact.)  Cuts the L2->smem traffic of A by 6.4x.
+constexpr int kHaloTH = 16, kHaloTW = 8, kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;
+constexpr int kHaloTxBytes = kHaloW * kHaloH * 128;          // bytes one halo TMA box delivers (23,040)
+constexpr int kHaloBytes = (kHaloTxBytes + 1023) / 1024 * 1024;   // slot size, keeps 1024-B alignment (23,552)
 
 template <int BN, int BK>
 struct Cfg {
@@ -62,6 +70,16 @@ struct Cfg {
     static constexpr int A_BYTES = kTileM * ROW_BYTES;
     static constexpr int B_BYTES = BN * ROW_BYTES;
 };
+
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {   // SWIZZLE_128B, SBO = 10 rows
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((kHaloW * 128) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, float& rb) {
     // returns packed (bf16(a), bf16(b)); ra/rb = residuals a - hi, b - hi (exact in fp32)
@@ -72,7 +90,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, flo
     return u;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -83,15 +101,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // 1024-B alignment required by SWIZZLE_128B tiles.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
+    // non-HALO: one ring, a stage = A tile(s) + B tile(s).  HALO: an A ring of halo patches (one per
+    // 64-channel block) followed by a B ring (one weight tile per tap).
+    const int planes = p.x3 ? 2 : 1;
+    const int a_stage_bytes = HALO ? planes * kHaloBytes : 0;
+    const int AS = HALO ? p.a_stages : 0;
+    const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
     const int S = p.num_stages;
-    uint8_t* staging = smem + (size_t)S * stage_bytes;                 // 1024-aligned (stage sizes are multiples of 1 KB)
+    uint8_t* ring = smem + (size_t)AS * a_stage_bytes;
+    uint8_t* staging = ring + (size_t)S * stage_bytes;                 // 1024-aligned (all slot sizes are multiples of 1 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (p.store_bf16 ? kStagingBytes : 0));
     uint64_t* full_bar = bars;            // [S]
     uint64_t* empty_bar = bars + S;       // [S]
     uint64_t* tfull_bar = bars + 2 * S;   // [2]
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    uint64_t* afull_bar = bars + 2 * S + 4;   // [AS]
+    uint64_t* aempty_bar = afull_bar + AS;    // [AS]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + AS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -113,6 +139,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], 4);
         }
+        for (int i = 0; i < AS; ++i) {
+            ptx::mbar_init(&afull_bar[i], 1);
+            ptx::mbar_init(&aempty_bar[i], 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -132,18 +162,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            (void)as; (void)aphase;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int mt = tile / p.n_tiles;
                 const int h0 = (mt / p.tiles_w) * p.TH;
                 const int w0 = (mt % p.tiles_w) * p.TW;
                 const int n0 = nt * BN;
+                if constexpr (HALO) {
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        ptx::mbar_wait(&aempty_bar[as], aphase ^ 1);
+                        uint8_t* sa = smem + (size_t)as * a_stage_bytes;
+                        ptx::mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)(planes * kHaloTxBytes));
+                        ptx::tma_load_3d(sa, &tm_a_hi, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
+                        if (p.x3) ptx::tma_load_3d(sa + kHaloBytes, &tm_a_lo, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
+                        if (++as == AS) { as = 0; aphase ^= 1; }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* st = ring + (size_t)stage * stage_bytes;
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                            ptx::tma_load_3d(st, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
+                            if (p.x3) ptx::tma_load_3d(st + C::B_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
+                            if (++stage == S) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / p.cin_blocks;
                     const int cb = kb - tap * p.cin_blocks;
                     const int r = tap / p.ksize, s = tap - r * p.ksize;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* st = smem + (size_t)stage * stage_bytes;
+                    uint8_t* st = ring + (size_t)stage * stage_bytes;
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                     ptx::tma_load_3d(st, &tm_a_hi, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
                     ptx::tma_load_3d(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
@@ -163,16 +215,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        (void)as; (void)aphase;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
             const uint32_t d_corr = d_tmem + BN;   // bf16x3: lo*hi + hi*lo accumulate separately (see epilogue)
+            if constexpr (HALO) {
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    ptx::mbar_wait(&afull_bar[as], aphase);
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)as * a_stage_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ptx::mbar_wait(&full_bar[stage], phase);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint32_t arow = sa + (uint32_t)(((tap / 3) * kHaloW + (tap % 3)) * 128);
+                            const uint32_t st = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
+                            const uint64_t a_hi = make_halo_desc(arow);
+                            const uint64_t b_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
+                            if (p.x3) {
+                                const uint64_t a_lo = make_halo_desc(arow + kHaloBytes);
+                                const uint64_t b_lo = ptx::make_smem_desc(st + C::B_BYTES, C::ROW_BYTES);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    ptx::mma_f16_ss(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                            }
+                            ptx::mma_commit(&empty_bar[stage]);                    // weight slot free
+                            if (tap == 8) ptx::mma_commit(&aempty_bar[as]);         // halo patch free
+                            if (tap == 8 && cb == p.cin_blocks - 1) ptx::mma_commit(&tfull_bar[acc]);
+                        }
+                        __syncwarp();
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                    if (++as == AS) { as = 0; aphase ^= 1; }
+                }
+                if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
-                    const uint32_t st = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t st = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
                     const uint64_t a_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
                     const uint64_t b_hi = ptx::make_smem_desc(st + C::A_BYTES, C::ROW_BYTES);
 #pragma unroll
@@ -264,17 +355,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     int srow = row;                         // row of the staging tile this thread fills
                     bool writer = true;
                     if (p.pool) {
-                        // F.MaxPooling2D(2,2) ceil mode fused: tile is 8x16 pixels, a warp holds two tile
-                        // rows (lanes 0-15 / 16-31), so the 2x2 window is lanes {l, l^1, l^16, l^17}.
+                        // F.MaxPooling2D(2,2) ceil mode fused: the tile is TH x TW pixels with TW = 16 or 8, a
+                        // warp holds 32/TW consecutive tile rows, so the 2x2 window is lanes {l, l^1, l^TW, l^(TW+1)}.
                         // Out-of-image pixels were zeroed above and every valid value is >= 0 (ReLU), so the
                         // max over the valid part of a partial window is unchanged (Chainer cover_all=True).
+                        const int tw_mask = p.TW;                // 16 or 8 (power of two)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                            v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                            v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, tw_mask));
                         }
-                        writer = (lane & 17) == 0;
-                        srow = lg * 8 + ((lane & 15) >> 1);     // pooled tile: 4 rows x 8 cols
+                        writer = (lane & (1 | tw_mask)) == 0;
+                        // pooled tile is (TH/2) x (TW/2): row-major index of this thread's window
+                        srow = ((row / p.TW) >> 1) * (p.TW >> 1) + ((row % p.TW) >> 1);
                     }
                     uint8_t* sb = staging + (chunk_i & 1u) * (2 * kStagePlane);
                     // the bulk store that last read this staging buffer (2 chunks ago) must be done reading
@@ -389,24 +482,32 @@ static int device_sm_count() {
     return sms;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool HALO>
 static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream) {
     using C = Cfg<BN, BK>;
-    const int stage_bytes = (p.x3 ? 2 : 1) * (C::A_BYTES + C::B_BYTES);
+    const int planes = p.x3 ? 2 : 1;
+    const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
     const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0);
-    int stages = (227 * 1024 - fixed) / stage_bytes;
-    if (stages > 24) stages = 24;
+    int a_stages = 0, a_bytes = 0;
+    if (HALO) {
+        // two halo slots when at least 3 weight slots still fit, else one
+        a_stages = ((227 * 1024 - fixed - 2 * planes * kHaloBytes) / stage_bytes >= 3) ? 2 : 1;
+        a_bytes = a_stages * planes * kHaloBytes;
+    }
+    int stages = (227 * 1024 - fixed - a_bytes) / stage_bytes;
+    if (stages > 20) stages = 20;
     if (stages < 2) {
-        set_error("conv tile BN=%d BK=%d does not fit 2 pipeline stages", BN, BK);
+        set_error("conv tile BN=%d BK=%d halo=%d does not fit 2 pipeline stages", BN, BK, (int)HALO);
         return FRCNN_ERR_ARG;
     }
     p.num_stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    p.a_stages = a_stages;
+    const size_t smem = (size_t)stages * stage_bytes + a_bytes + fixed;
     p.acc_cols = p.x3 ? 2 * BN : BN;
     p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_bufs * p.acc_cols) p.tmem_cols *= 2;
-    auto kern = conv_gemm_kernel<BN, BK>;
+    auto kern = conv_gemm_kernel<BN, BK, HALO>;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     kern<<<grid, kNumThreads, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
@@ -446,10 +547,16 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     // ---- pixel tile: minimise padded pixels (the fused pool needs the 8x16 tile: 2x2 windows inside a warp)
     static const int shapes[6][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
     int TH = 8, TW = 16;
-    if (fuse_pool2x2) {
+    const bool forced_tile = g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM;
+    // HALO (shared halo patch for the 9 taps) needs the 16x8 tile; a forced other tile selects the per-tap path
+    const bool halo = ksize == 3 && BK == 64 && (!forced_tile || (g_force_th == kHaloTH && g_force_tw == kHaloTW));
+    if (halo) {
+        TH = kHaloTH;
+        TW = kHaloTW;
+    } else if (fuse_pool2x2) {
         TH = 8;
         TW = 16;
-    } else if (g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM) {
+    } else if (forced_tile) {
         TH = g_force_th;
         TW = g_force_tw;
     } else {
@@ -505,10 +612,11 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
 
     CUtensorMap tm[6];
     int rc;
-    if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+    const int abw = halo ? kHaloW : TW, abh = halo ? kHaloH : TH;     // A box: the tile, or the tile + 1-pixel halo
+    if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
     if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
     if (p.x3) {
-        if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, TW, TH)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
         if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
     } else {
         tm[1] = tm[0];
@@ -528,14 +636,17 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
         tm[5] = tm[0];
     }
 
-#define FRCNN_DISPATCH(BN_, BK_) \
-    if (BN == BN_ && BK == BK_) return launch_conv<BN_, BK_>(tm, p, stream);
-    FRCNN_DISPATCH(256, 64)
-    FRCNN_DISPATCH(128, 64)
-    FRCNN_DISPATCH(64, 64)
-    FRCNN_DISPATCH(256, 16)
-    FRCNN_DISPATCH(128, 16)
-    FRCNN_DISPATCH(64, 16)
+#define FRCNN_DISPATCH(BN_, BK_, HALO_) \
+    if (BN == BN_ && BK == BK_ && halo == HALO_) return launch_conv<BN_, BK_, HALO_>(tm, p, stream);
+    FRCNN_DISPATCH(256, 64, true)
+    FRCNN_DISPATCH(128, 64, true)
+    FRCNN_DISPATCH(64, 64, true)
+    FRCNN_DISPATCH(256, 64, false)
+    FRCNN_DISPATCH(128, 64, false)
+    FRCNN_DISPATCH(64, 64, false)
+    FRCNN_DISPATCH(256, 16, false)
+    FRCNN_DISPATCH(128, 16, false)
+    FRCNN_DISPATCH(64, 16, false)
 #undef FRCNN_DISPATCH
     set_error("frcnn_conv2d: no kernel for BN=%d BK=%d", BN, BK);
     return FRCNN_ERR_ARG;

@@ -145,20 +145,98 @@ struct SortArgs {
     float* dbg_dets; int* dbg_idx; int* dbg_num;
 };
 
-// dynamic smem: uint64 comp[P], P = next_pow2(min(top_k, n))
-__global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortArgs a, const int P) {
+// Bitonic compare-exchange network over P = 1024*EPT composites, EPT consecutive elements per thread:
+//   j <  EPT        partner inside the thread            -> registers
+//   j <  32*EPT     partner thread in the same warp       -> 64-bit shuffles
+//   j >= 32*EPT     partner in another warp               -> shared memory + block barrier
+// (the first version did all 91 stages of P=8192 through shared memory with a barrier each: 50+ us)
+template <int EPT>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long (&v)[EPT], unsigned long long* comp, const int P) {
+    const int tid = threadIdx.x;
+    const int base = tid * EPT;
+    for (int k = 2; k <= P; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= EPT; j >>= 1) {
+            if (j < 32 * EPT) {
+                const int tj = j / EPT;                       // partner lane distance
+                const bool lower = (tid & tj) == 0;
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const bool up = ((base + i) & k) == 0;
+                    const unsigned long long mine = v[i];
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, tj);
+                    const bool keep_min = (lower == up);
+                    v[i] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+                }
+            } else {
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) comp[base + i] = v[i];
+                __syncthreads();
+                const bool lower = (base & j) == 0;
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    const bool up = ((base + i) & k) == 0;
+                    const unsigned long long mine = v[i];
+                    const unsigned long long other = comp[(base + i) ^ j];
+                    const bool keep_min = (lower == up);
+                    v[i] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
+                }
+            }
+        }
+        // remaining stages (j < EPT) stay inside the thread; jj is a compile-time constant so v[] stays in registers
+#pragma unroll
+        for (int jj = EPT / 2; jj >= 1; jj >>= 1) {
+            if (jj <= j) {
+#pragma unroll
+                for (int i = 0; i < EPT; ++i) {
+                    if ((i & jj) == 0) {
+                        const bool up = ((base + i) & k) == 0;
+                        const unsigned long long x = v[i], y = v[i | jj];
+                        if ((x > y) == up) { v[i] = y; v[i | jj] = x; }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) comp[base + i] = v[i];
+    __syncthreads();
+}
+
+template <int EPT>
+__device__ __forceinline__ void bitonic_sort_dispatch(unsigned long long* comp, const int P) {
+    unsigned long long v[EPT];
+    const int base = threadIdx.x * EPT;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) v[i] = comp[base + i];
+    bitonic_sort_regs<EPT>(v, comp, P);
+}
+
+// dynamic smem: uint64 comp[P] (P = max(2048, next_pow2(min(top_k, n)))) followed, when it fits,
+// by a copy of the n keys (the select passes then never touch global memory again).
+__global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortArgs a, const int P, const int cache_keys) {
     extern __shared__ unsigned long long comp[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long red[33];
     __shared__ unsigned int s_prefix, s_need;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int n = a.n;
+    const int n_pad = (n + 31) & ~31;                 // whole warps iterate together (warp-aggregated atomics)
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(comp + P);
+    const uint32_t* keys = a.keys;
 
-    // ---- count candidates (key != 0)
+    // ---- count candidates (key != 0), filling the smem copy on the way
     unsigned int cnt = 0;
-    for (int i = tid; i < n; i += kSortThreads) cnt += a.keys[i] != 0u;
+    for (int i = tid; i < n; i += kSortThreads) {
+        const uint32_t k = a.keys[i];
+        if (cache_keys) skeys[i] = k;
+        cnt += k != 0u;
+    }
     unsigned long long tot;
-    block_exclusive_scan(cnt, red, &tot);
+    block_exclusive_scan(cnt, red, &tot);             // (has the barriers that publish skeys)
+    if (cache_keys) keys = skeys;
     const int n_valid = (int)tot;
     const int K = n_valid < a.top_k ? n_valid : a.top_k;      // how many we keep
 
@@ -170,9 +248,13 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
             const unsigned int mask_hi = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += kSortThreads) {
-                const unsigned int k = a.keys[i];
-                if (k != 0u && (k & mask_hi) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            for (int i = tid; i < n_pad; i += kSortThreads) {
+                const unsigned int k = i < n ? keys[i] : 0u;
+                const bool act = k != 0u && (k & mask_hi) == prefix;
+                // lanes with the same digit elect one leader that adds the whole group's count
+                const unsigned int digit = act ? ((k >> shift) & 255u) : (256u + (unsigned int)lane);
+                const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+                if (act && (__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
             }
             __syncthreads();
             // suffix counts: bin b is chosen if  sum(hist[b+1..255]) < need <= sum(hist[b..255])
@@ -201,7 +283,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
     const int i0 = tid * chunk, i1 = min(n, i0 + chunk);
     unsigned int c_gt = 0, c_eq = 0;
     for (int i = i0; i < i1; ++i) {
-        const unsigned int k = a.keys[i];
+        const unsigned int k = keys[i];
         if (k == 0u) continue;
         if (take_all || k > T) ++c_gt; else if (k == T) ++c_eq;
     }
@@ -211,7 +293,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
     const unsigned int gt_total = (unsigned int)(tot2 & 0xFFFFFFFFu);
     const unsigned int eq_take = take_all ? 0u : need;
     for (int i = i0; i < i1; ++i) {
-        const unsigned int k = a.keys[i];
+        const unsigned int k = keys[i];
         if (k == 0u) continue;
         // composite: ascending order == (key descending, index ascending)
         const unsigned long long c = ((unsigned long long)(~k) << 32) | (unsigned int)i;
@@ -225,18 +307,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
     for (int i = K + tid; i < P; i += kSortThreads) comp[i] = ~0ull;    // padding sorts last
     __syncthreads();
 
-    // ---- bitonic sort of P composites (ascending)
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += kSortThreads) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // index with bit j clear
-                const int hi = lo | j;
-                const bool up = (lo & k) == 0;
-                const unsigned long long x = comp[lo], y = comp[hi];
-                if ((x > y) == up) { comp[lo] = y; comp[hi] = x; }
-            }
-            __syncthreads();
-        }
+    // ---- bitonic sort of P composites (ascending), P = 1024 * EPT
+    switch (P / kSortThreads) {
+        case 2: bitonic_sort_dispatch<2>(comp, P); break;
+        case 4: bitonic_sort_dispatch<4>(comp, P); break;
+        case 8: bitonic_sort_dispatch<8>(comp, P); break;
+        default: bitonic_sort_dispatch<16>(comp, P); break;
     }
 
     // ---- gather boxes / scores into sorted order
@@ -258,6 +334,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
         if (a.dbg_num) *a.dbg_num = K;
     }
 }
+
 
 // ------------------------------------------------------------------------------------------ 3. IoU bitmask
 // IoU exactly as models/cpu_nms.pyx:58-65 (float32, one rounding per op, true division).
@@ -292,8 +369,26 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* boxes, const
     const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
     unsigned long long bits = 0ull;
     const int start = (rb == cb) ? t + 1 : 0;
+    // Fast exact-safe pre-test: with u = area_a + area_b - inter, the decision "inter/u >= thr" is certain
+    // whenever inter is outside [thr*u*(1-1e-5), thr*u*(1+1e-5)] (the float roundings involved are < 1e-6
+    // relative); only inside that sliver the reference's exact sequence (float divide, double compare) runs.
+    const float thr_lo = thr_f * (1.0f - 1e-5f), thr_hi = thr_f * (1.0f + 1e-5f);
+    const bool fast_ok = thr_f > 1e-3f;
     for (int j = start; j < ccount; ++j) {
-        if (suppresses(iou_plus1(a, area_a, cbox[j]), thr_d, thr_f, mode)) bits |= 1ull << j;
+        const float4 b = cbox[j];
+        const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+        const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+        const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+        const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+        const float inter = __fmul_rn(w, h);
+        if (fast_ok && inter == 0.0f) continue;                    // disjoint: iou == 0 < thr
+        const float area_b = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+        const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+        bool sup;
+        if (fast_ok && uni > 0.0f && inter > thr_hi * uni) sup = true;
+        else if (fast_ok && uni > 0.0f && inter < thr_lo * uni) sup = false;
+        else sup = suppresses(__fdiv_rn(inter, uni), thr_d, thr_f, mode);
+        if (sup) bits |= 1ull << j;
     }
     mask[(long)ri * col_blocks + cb] = bits;
 }
@@ -423,16 +518,20 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
                         int* keep_out, int* num_out, float* out_rois, float* out_scores, int out_cap,
                         float* dbg_dets, int* dbg_idx, int* dbg_num, bool map_to_original, cudaStream_t stream) {
     const int k_cap = top_k < n_all ? top_k : n_all;
-    const int P = next_pow2(k_cap < 2 ? 2 : k_cap);
+    int P = next_pow2(k_cap < 2 ? 2 : k_cap);
+    if (P < 2 * kSortThreads) P = 2 * kSortThreads;      // the register bitonic network needs >= 2 elements per thread
     SortArgs sa;
     sa.keys = w.keys; sa.n = n_all; sa.top_k = top_k;
     sa.boxes = w.boxes; sa.scores = w.scores;
     sa.sorted_boxes = w.sorted_boxes; sa.sorted_scores = w.sorted_scores; sa.sorted_idx = w.sorted_idx;
     sa.num_sorted = w.num_sorted;
     sa.dbg_dets = dbg_dets; sa.dbg_idx = dbg_idx; sa.dbg_num = dbg_num;
-    const size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
+    size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
+    const size_t keys_bytes = sizeof(uint32_t) * (size_t)n_all;
+    const int cache_keys = sort_smem + keys_bytes <= 200 * 1024;     // smem copy of the keys when it fits
+    if (cache_keys) sort_smem += keys_bytes;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    topk_sort_kernel<<<1, kSortThreads, sort_smem, stream>>>(sa, P);
+    topk_sort_kernel<<<1, kSortThreads, sort_smem, stream>>>(sa, P, cache_keys);
     FRCNN_LAUNCH_OK();
 
     const int cbs = cdiv(k_cap, 64);

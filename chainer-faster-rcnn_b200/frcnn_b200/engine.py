@@ -203,6 +203,73 @@ class ForwardPlan(object):
         return self.prob, self.boxes, self.prop.count
 
 
+class StreamRunner(object):
+    """Host-to-host streaming front end of a ForwardPlan: images come from (pinned) HOST memory and
+    results go back to pinned HOST memory, every image.  Depth-2 pipeline on two CUDA streams: the H2D
+    copy of image i+1 runs on the copy stream while image i's graph runs on the compute stream; the
+    D2H of (prob, boxes, count) is queued behind the graph.  Nothing is skipped per image -- the copies
+    are overlapped, not removed -- so the steady-state rate is max(H2D, graph), not their sum."""
+
+    def __init__(self, plan):
+        import torch
+        self.plan = plan
+        dev = plan.x_in.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [torch.empty_like(plan.x_in) for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.step_done = [torch.cuda.Event() for _ in range(2)]
+        nc = plan.w.num_classes
+        self.res = [dict(prob=torch.empty((plan.post_n, nc), dtype=torch.float32).pin_memory(),
+                         boxes=torch.empty((plan.post_n, 4 * nc), dtype=torch.float32).pin_memory(),
+                         count=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+        self.h2d_bytes = plan.x_in.numel() * 4
+        self.d2h_bytes = (plan.post_n * nc + plan.post_n * 4 * nc) * 4 + 4
+        if plan.graph is None:
+            plan.forward(None)                       # capture outside the stream loop
+
+    def _prefetch(self, host_img, slot, after=None):
+        import torch
+        with torch.cuda.stream(self.copy_stream):
+            if after is not None:
+                self.copy_stream.wait_event(after)   # the previous user of this staging slot has consumed it
+            self.stage[slot].copy_(host_img, non_blocking=True)
+            self.h2d_done[slot].record(self.copy_stream)
+
+    def run(self, host_images, on_result=None):
+        """host_images: sequence of pinned (3,H,W) float32 host tensors.  Calls on_result(i, res) with the
+        pinned result dict of image i (valid until image i+2 is submitted).  Returns the proposal counts."""
+        import torch
+        plan, n = self.plan, len(host_images)
+        cur = torch.cuda.current_stream()
+        counts = []
+        if n == 0:
+            return counts
+        self._prefetch(host_images[0], 0)
+        for i in range(n):
+            s = i & 1
+            if i + 1 < n:
+                self._prefetch(host_images[i + 1], s ^ 1, after=self.step_done[s ^ 1] if i >= 1 else None)
+            cur.wait_event(self.h2d_done[s])
+            plan.x_in.copy_(self.stage[s], non_blocking=True)           # D2D into the graph's static input
+            plan.graph.replay()
+            r = self.res[s]
+            r["prob"].copy_(plan.prob, non_blocking=True)
+            r["boxes"].copy_(plan.boxes, non_blocking=True)
+            r["count"].copy_(plan.prop.count, non_blocking=True)
+            self.step_done[s].record(cur)
+            if i >= 1:                                                   # hand image i-1's result to the host
+                self.step_done[s ^ 1].synchronize()
+                counts.append(int(self.res[s ^ 1]["count"][0]))
+                if on_result is not None:
+                    on_result(i - 1, self.res[s ^ 1])
+        last = (n - 1) & 1
+        self.step_done[last].synchronize()
+        counts.append(int(self.res[last]["count"][0]))
+        if on_result is not None:
+            on_result(n - 1, self.res[last])
+        return counts
+
+
 class Engine(object):
     """Weights + per-shape plans.  `engine(x)` -> (prob [R,21], boxes [R,84]) device tensors, R synced."""
 

@@ -240,9 +240,12 @@ def test_conv2d_fused_maxpool_equals_conv_then_pool(ops, precision, shape):
     want = ops.maxpool2x2_ceil(y_full)
     got, _ = ops.conv2d(act, wh, wl, bias, 3, True, fuse_pool=True)
     assert got.hi.shape == ((H + 1) // 2, (W + 1) // 2, Cout)
-    assert torch.equal(got.hi, want.hi)
     if precision == "bf16x3":
-        assert torch.equal(got.lo, want.lo)
+        # the VALUE hi+lo must be identical; the (hi, lo) pair itself may differ at round-to-even ties
+        # (the un-fused path re-splits an already 16-bit-rounded value)
+        assert torch.equal(got.hi.float() + got.lo.float(), want.hi.float() + want.lo.float())
+    else:
+        assert torch.equal(got.hi, want.hi)
     q = _quant16 if precision == "bf16x3" else _bf16
     ref = torch.nn.functional.conv2d(torch.from_numpy(q(x))[None].double(), torch.from_numpy(q(w)).double(),
                                      torch.from_numpy(b).double(), padding=1).clamp_min(0)
