@@ -143,79 +143,13 @@ struct SortArgs {
     const float4* boxes; const float* scores;
     float4* sorted_boxes; float* sorted_scores; int* sorted_idx; int* num_sorted;
     float* dbg_dets; int* dbg_idx; int* dbg_num;
+    long long* dbg_clocks;     // optional: 8 phase timestamps (clock64 of thread 0)
+    unsigned long long* comp_out;   // [k_cap] selected composites (key desc | index), unordered
 };
 
-// Bitonic compare-exchange network over P = 1024*EPT composites, EPT consecutive elements per thread:
-//   j <  EPT        partner inside the thread            -> registers
-//   j <  32*EPT     partner thread in the same warp       -> 64-bit shuffles
-//   j >= 32*EPT     partner in another warp               -> shared memory + block barrier
-// (the first version did all 91 stages of P=8192 through shared memory with a barrier each: 50+ us)
-template <int EPT>
-__device__ __forceinline__ void bitonic_sort_regs(unsigned long long (&v)[EPT], unsigned long long* comp, const int P) {
-    const int tid = threadIdx.x;
-    const int base = tid * EPT;
-    for (int k = 2; k <= P; k <<= 1) {
-        int j = k >> 1;
-        for (; j >= EPT; j >>= 1) {
-            if (j < 32 * EPT) {
-                const int tj = j / EPT;                       // partner lane distance
-                const bool lower = (tid & tj) == 0;
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) {
-                    const bool up = ((base + i) & k) == 0;
-                    const unsigned long long mine = v[i];
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, tj);
-                    const bool keep_min = (lower == up);
-                    v[i] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
-                }
-            } else {
-                __syncthreads();
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) comp[base + i] = v[i];
-                __syncthreads();
-                const bool lower = (base & j) == 0;
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) {
-                    const bool up = ((base + i) & k) == 0;
-                    const unsigned long long mine = v[i];
-                    const unsigned long long other = comp[(base + i) ^ j];
-                    const bool keep_min = (lower == up);
-                    v[i] = keep_min ? (mine < other ? mine : other) : (mine > other ? mine : other);
-                }
-            }
-        }
-        // remaining stages (j < EPT) stay inside the thread; jj is a compile-time constant so v[] stays in registers
-#pragma unroll
-        for (int jj = EPT / 2; jj >= 1; jj >>= 1) {
-            if (jj <= j) {
-#pragma unroll
-                for (int i = 0; i < EPT; ++i) {
-                    if ((i & jj) == 0) {
-                        const bool up = ((base + i) & k) == 0;
-                        const unsigned long long x = v[i], y = v[i | jj];
-                        if ((x > y) == up) { v[i] = y; v[i | jj] = x; }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) comp[base + i] = v[i];
-    __syncthreads();
-}
-
-template <int EPT>
-__device__ __forceinline__ void bitonic_sort_dispatch(unsigned long long* comp, const int P) {
-    unsigned long long v[EPT];
-    const int base = threadIdx.x * EPT;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) v[i] = comp[base + i];
-    bitonic_sort_regs<EPT>(v, comp, P);
-}
-
-// dynamic smem: uint64 comp[P] (P = max(2048, next_pow2(min(top_k, n)))) followed, when it fits,
-// by a copy of the n keys (the select passes then never touch global memory again).
+// Selection step (ONE CTA): count, 4-pass radix select of the top_k-th key, order-preserving compaction.
+// dynamic smem: uint64 comp[P] (P >= min(top_k, n)) followed, when it fits, by a copy of the n keys
+// (the select passes then never touch global memory again).
 __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortArgs a, const int P, const int cache_keys) {
     extern __shared__ unsigned long long comp[];
     __shared__ unsigned int hist[256];
@@ -226,6 +160,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
     const int n_pad = (n + 31) & ~31;                 // whole warps iterate together (warp-aggregated atomics)
     uint32_t* skeys = reinterpret_cast<uint32_t*>(comp + P);
     const uint32_t* keys = a.keys;
+#define SORT_MARK(i) do { if (a.dbg_clocks && tid == 0) a.dbg_clocks[i] = clock64(); } while (0)
+    SORT_MARK(0);
 
     // ---- count candidates (key != 0), filling the smem copy on the way
     unsigned int cnt = 0;
@@ -239,6 +175,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
     if (cache_keys) keys = skeys;
     const int n_valid = (int)tot;
     const int K = n_valid < a.top_k ? n_valid : a.top_k;      // how many we keep
+    SORT_MARK(1);
 
     // ---- radix select: the K-th largest key T (MSB-first, 8 bits per pass)
     unsigned int prefix = 0, need = (unsigned int)K;     // need = rank (1-based) inside the current bucket
@@ -252,7 +189,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
                 const unsigned int k = i < n ? keys[i] : 0u;
                 const bool act = k != 0u && (k & mask_hi) == prefix;
                 // lanes with the same digit elect one leader that adds the whole group's count
-                const unsigned int digit = act ? ((k >> shift) & 255u) : (256u + (unsigned int)lane);
+                const unsigned int digit = act ? ((k >> shift) & 255u) : 256u;
                 const unsigned int peers = __match_any_sync(0xffffffffu, digit);
                 if (act && (__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
             }
@@ -274,6 +211,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
             __syncthreads();
         }
     }
+    SORT_MARK(2);
     // Now: keys > T are all taken; among keys == T the `need` lowest indices are taken.
     const unsigned int T = (K > 0 && K < n_valid) ? prefix : 1u;       // K == n_valid: take every candidate
     const bool take_all = !(K > 0 && K < n_valid);
@@ -304,20 +242,43 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
             ++eq_before;
         }
     }
-    for (int i = K + tid; i < P; i += kSortThreads) comp[i] = ~0ull;    // padding sorts last
     __syncthreads();
-
-    // ---- bitonic sort of P composites (ascending), P = 1024 * EPT
-    switch (P / kSortThreads) {
-        case 2: bitonic_sort_dispatch<2>(comp, P); break;
-        case 4: bitonic_sort_dispatch<4>(comp, P); break;
-        case 8: bitonic_sort_dispatch<8>(comp, P); break;
-        default: bitonic_sort_dispatch<16>(comp, P); break;
+    SORT_MARK(3);
+    // ---- hand the K selected composites (unordered) to the chip-wide rank kernel
+    for (int r = tid; r < K; r += kSortThreads) a.comp_out[r] = comp[r];
+    SORT_MARK(4);
+    SORT_MARK(5);
+#undef SORT_MARK
+    if (tid == 0) {
+        *a.num_sorted = K;
+        if (a.dbg_num) *a.dbg_num = K;
     }
+}
 
-    // ---- gather boxes / scores into sorted order
-    for (int r = tid; r < K; r += kSortThreads) {
-        const int idx = (int)(comp[r] & 0xFFFFFFFFull);
+// Ordering step: rank-by-counting across the whole chip.  The composites are unique (they contain the
+// index), so rank(i) = #{j : comp[j] < comp[i]} is a permutation; 6000^2 64-bit compares are ~3 us on 148
+// SMs, where a single-CTA bitonic network of the same 6000 elements took 50-170 us (instruction-issue
+// bound on one SM).  Each block ranks 32 elements (8 threads per element, each scanning 1/8 of the list from
+// a shared-memory copy) and scatters box / score / index straight to the sorted position.
+constexpr int kRankThreads = 256, kRankPerBlock = 32;
+__global__ void __launch_bounds__(kRankThreads) rank_scatter_kernel(const SortArgs a) {
+    extern __shared__ unsigned long long scomp[];
+    const int K = *a.num_sorted;
+    const int e0 = blockIdx.x * kRankPerBlock;
+    if (e0 >= K) return;
+    for (int i = threadIdx.x; i < K; i += kRankThreads) scomp[i] = a.comp_out[i];
+    __syncthreads();
+    const int e = e0 + (threadIdx.x >> 3), part = threadIdx.x & 7;
+    const bool live = e < K;
+    const unsigned long long mine = live ? scomp[e] : 0ull;
+    int cnt = 0;
+    for (int j = part; j < K; j += 8) cnt += scomp[j] < mine;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+    if (live && part == 0) {
+        const int r = cnt;
+        const int idx = (int)(mine & 0xFFFFFFFFull);
         const float4 b = a.boxes[idx];
         const float s = a.scores[idx];
         a.sorted_boxes[r] = b;
@@ -328,10 +289,6 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
             o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = s;
         }
         if (a.dbg_idx) a.dbg_idx[r] = idx;
-    }
-    if (tid == 0) {
-        *a.num_sorted = K;
-        if (a.dbg_num) *a.dbg_num = K;
     }
 }
 
@@ -401,6 +358,7 @@ struct ScanArgs {
     int* keep_out; int* num_out;   // optional
     const float4* sorted_boxes; const float* sorted_scores;   // optional gather
     float* out_rois; float* out_scores; int out_cap;
+    int diag_in_smem;
 };
 
 __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
@@ -413,6 +371,11 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
     const int nb = (n + 63) / 64;
     const int limit = a.max_keep > 0 ? a.max_keep : 0x7fffffff;
     for (int w = tid; w < a.col_blocks; w += blockDim.x) removed[w] = 0ull;
+    // Pre-load every row's DIAGONAL word (the bits inside its own 64-block) into shared memory: the serial
+    // walk below then has no global load on its critical path for the intra-block decisions.
+    unsigned long long* diag = removed + a.col_blocks;          // [n_cap] when a.diag_in_smem
+    if (a.diag_in_smem)
+        for (int r = tid; r < n; r += blockDim.x) diag[r] = a.mask[(long)r * a.col_blocks + (r >> 6)];
     if (tid == 0) s_total = 0;
     __syncthreads();
 
@@ -421,8 +384,13 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
             const int rows = min(64, n - blk * 64);
             // diagonal words of this block's rows: lane holds rows `lane` and `lane+32`
             unsigned long long d0 = 0ull, d1 = 0ull;
-            if (lane < rows) d0 = a.mask[(long)(blk * 64 + lane) * a.col_blocks + blk];
-            if (lane + 32 < rows) d1 = a.mask[(long)(blk * 64 + lane + 32) * a.col_blocks + blk];
+            if (a.diag_in_smem) {
+                if (lane < rows) d0 = diag[blk * 64 + lane];
+                if (lane + 32 < rows) d1 = diag[blk * 64 + lane + 32];
+            } else {
+                if (lane < rows) d0 = a.mask[(long)(blk * 64 + lane) * a.col_blocks + blk];
+                if (lane + 32 < rows) d1 = a.mask[(long)(blk * 64 + lane + 32) * a.col_blocks + blk];
+            }
             unsigned long long cand = ~removed[blk];
             if (rows < 64) cand &= (1ull << rows) - 1ull;
             int total = s_total, nk = 0;
@@ -477,6 +445,7 @@ struct NmsWs {
     float4* sorted_boxes; float* sorted_scores; int* sorted_idx;  // [k_cap]
     int* num_sorted;
     unsigned long long* mask;                                  // [k_cap * col_blocks]
+    unsigned long long* comp;                                  // [k_cap]
     int col_blocks;
     size_t total;
 };
@@ -495,6 +464,7 @@ static NmsWs carve(void* ws, int n_all, int k_cap) {
     size_t o_si = take(sizeof(int) * (size_t)k_cap);
     size_t o_ns = take(sizeof(int) * 4);
     size_t o_mask = take(sizeof(unsigned long long) * (size_t)k_cap * w.col_blocks);
+    size_t o_comp = take(sizeof(unsigned long long) * (size_t)k_cap);
     w.total = off;
     w.boxes = reinterpret_cast<float4*>(base + o_boxes);
     w.scores = reinterpret_cast<float*>(base + o_scores);
@@ -504,8 +474,11 @@ static NmsWs carve(void* ws, int n_all, int k_cap) {
     w.sorted_idx = reinterpret_cast<int*>(base + o_si);
     w.num_sorted = reinterpret_cast<int*>(base + o_ns);
     w.mask = reinterpret_cast<unsigned long long*>(base + o_mask);
+    w.comp = reinterpret_cast<unsigned long long*>(base + o_comp);
     return w;
 }
+
+static long long* g_sort_clocks = nullptr;     // debug hook, see frcnn_debug_sort_clocks
 
 static int next_pow2(int v) {
     int p = 1;
@@ -518,20 +491,25 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
                         int* keep_out, int* num_out, float* out_rois, float* out_scores, int out_cap,
                         float* dbg_dets, int* dbg_idx, int* dbg_num, bool map_to_original, cudaStream_t stream) {
     const int k_cap = top_k < n_all ? top_k : n_all;
-    int P = next_pow2(k_cap < 2 ? 2 : k_cap);
-    if (P < 2 * kSortThreads) P = 2 * kSortThreads;      // the register bitonic network needs >= 2 elements per thread
+    const int P = next_pow2(k_cap < 2 ? 2 : k_cap);
     SortArgs sa;
     sa.keys = w.keys; sa.n = n_all; sa.top_k = top_k;
     sa.boxes = w.boxes; sa.scores = w.scores;
     sa.sorted_boxes = w.sorted_boxes; sa.sorted_scores = w.sorted_scores; sa.sorted_idx = w.sorted_idx;
     sa.num_sorted = w.num_sorted;
     sa.dbg_dets = dbg_dets; sa.dbg_idx = dbg_idx; sa.dbg_num = dbg_num;
+    sa.dbg_clocks = g_sort_clocks;
+    sa.comp_out = w.comp;
     size_t sort_smem = sizeof(unsigned long long) * (size_t)P;
     const size_t keys_bytes = sizeof(uint32_t) * (size_t)n_all;
     const int cache_keys = sort_smem + keys_bytes <= 200 * 1024;     // smem copy of the keys when it fits
     if (cache_keys) sort_smem += keys_bytes;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     topk_sort_kernel<<<1, kSortThreads, sort_smem, stream>>>(sa, P, cache_keys);
+    FRCNN_LAUNCH_OK();
+    const size_t rank_smem = sizeof(unsigned long long) * (size_t)k_cap;
+    FRCNN_CUDA_OK(cudaFuncSetAttribute(rank_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
+    rank_scatter_kernel<<<cdiv(k_cap, kRankPerBlock), kRankThreads, rank_smem, stream>>>(sa);
     FRCNN_LAUNCH_OK();
 
     const int cbs = cdiv(k_cap, 64);
@@ -547,7 +525,11 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
     sc.keep_out = keep_out; sc.num_out = num_out;
     sc.sorted_boxes = w.sorted_boxes; sc.sorted_scores = w.sorted_scores;
     sc.out_rois = out_rois; sc.out_scores = out_scores; sc.out_cap = out_cap;
-    nms_scan_kernel<<<1, 256, sizeof(unsigned long long) * (size_t)w.col_blocks, stream>>>(sc);
+    size_t scan_smem = sizeof(unsigned long long) * (size_t)w.col_blocks;
+    sc.diag_in_smem = (scan_smem + sizeof(unsigned long long) * (size_t)k_cap) <= 200 * 1024;
+    if (sc.diag_in_smem) scan_smem += sizeof(unsigned long long) * (size_t)k_cap;
+    FRCNN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    nms_scan_kernel<<<1, 256, scan_smem, stream>>>(sc);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }
@@ -672,3 +654,7 @@ extern "C" void _nms(int* keep_out, int* num_out, const float* boxes_host, int b
 extern "C" int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id) {
     return nms_host_impl(dets_host, n, 5, thresh, FRCNN_NMS_GE_DOUBLE, 0, keep_out_host, device_id);
 }
+
+// Debug / profiling hook (not part of the drop-in surface): device buffer of 8 int64 that receives the
+// per-phase clock64() stamps of the next topk_sort_kernel launches; NULL disables.
+extern "C" void frcnn_debug_sort_clocks(long long* dev_buf) { g_sort_clocks = dev_buf; }

@@ -47,6 +47,7 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     "frcnn_bbox_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
+    "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
 }

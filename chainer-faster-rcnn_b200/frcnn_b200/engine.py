@@ -160,7 +160,7 @@ class ForwardPlan(object):
                       self.im_h, self.im_w, self.min_size, self.pre_n, self.post_n, self.nms_thresh,
                       layout="nhwc", ld=w.rpn_ld, cls_is_logits=True, work=self.prop,
                       debug=self.prop.dbg_dets is not None)
-        n += 2 + 4
+        n += 2 + 5          # rpn 3x3, rpn heads; decode, select, rank/scatter, IoU mask, mask scan
         ops.roi_pool(feat, self.prop.rois, self.prop.count, 7, 7, 1.0 / self.feat_stride, out=self.pool5)
         hi, lo, b = w.fc6
         ops.conv2d(self.pool5, hi, lo, b, 1, True, out=self.fc6, m_valid=self.prop.count)

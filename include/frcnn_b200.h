@@ -162,6 +162,10 @@ int frcnn_bbox_decode(const float* boxes, const float* trans, int N, int K, int 
 int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_cap, int num_classes,
                  double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count, void* stream);
 
+/* Profiling hook (not part of the drop-in surface): a device buffer of 8 int64 that receives the
+ * per-phase clock64() stamps of subsequent top-k sort launches; NULL disables. */
+void frcnn_debug_sort_clocks(long long* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif
