@@ -64,12 +64,28 @@ constexpr int kHaloTH = 16, kHaloTW = 8, kHaloW = kHaloTW + 2, kHaloH = kHaloTH 
 constexpr int kHaloTxBytes = kHaloW * kHaloH * 128;          // bytes one halo TMA box delivers (23,040)
 constexpr int kHaloBytes = (kHaloTxBytes + 1023) / 1024 * 1024;   // slot size, keeps 1024-B alignment (23,552)
 
-template <int BN, int BK>
+template <int BN, int BK, int CG = 1>
 struct Cfg {
     static constexpr int ROW_BYTES = BK * 2;
     static constexpr int A_BYTES = kTileM * ROW_BYTES;
-    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int B_BYTES = (BN / CG) * ROW_BYTES;     // a CTA of a pair holds half of the B tile
 };
+
+// CG = 1: one CTA per tile (M = 128).  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256-pixel tile --
+// each CTA feeds its own 128 pixel rows of A and HALF of the weight tile, which halves the shared-memory
+// operand traffic per MMA (the 1-CTA kernel is smem-bandwidth bound at N = 128).
+template <int CG>
+__device__ __forceinline__ void tma_ld(void* s, const void* d, uint64_t* bar, int c0, int c1, int c2) {
+    if constexpr (CG == 2) ptx::tma_load_3d_2sm(s, d, bar, c0, c1, c2); else ptx::tma_load_3d(s, d, bar, c0, c1, c2);
+}
+template <int CG>
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (CG == 2) ptx::mma_f16_ss_2sm(d, a, b, idesc, acc); else ptx::mma_f16_ss(d, a, b, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void mma_cm(uint64_t* bar) {
+    if constexpr (CG == 2) ptx::mma_commit_2sm(bar); else ptx::mma_commit(bar);
+}
 
 __device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {   // SWIZZLE_128B, SBO = 10 rows
     uint64_t d = 0;
@@ -90,13 +106,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b, float& ra, flo
     return u;
 }
 
-template <int BN, int BK, bool HALO>
+template <int BN, int BK, bool HALO, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
                  const ConvParams p) {
-    using C = Cfg<BN, BK>;
+    using C = Cfg<BN, BK, CG>;
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment required by SWIZZLE_128B tiles.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -121,6 +137,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;   // position in the CTA pair
+    const bool leader = rank == 0;
+    const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a_hi);
@@ -137,7 +157,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&tempty_bar[i], 4 * CG);      // every epilogue warp of the pair arrives on the leader
         }
         for (int i = 0; i < AS; ++i) {
             ptx::mbar_init(&afull_bar[i], 1);
@@ -146,11 +166,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
-        ptx::tmem_relinquish();
+        if constexpr (CG == 2) {
+            ptx::tmem_alloc_2sm(tmem_ptr, (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();      // peer barriers initialised before any remote arrive / TMA signal
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -165,26 +191,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             int as = 0;
             uint32_t aphase = 0;
             (void)as; (void)aphase;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int nt = tile % p.n_tiles;
-                const int mt = tile / p.n_tiles;
+                const int mt = (tile / p.n_tiles) * CG + (int)rank;      // an out-of-range tile of an odd pair loads zeros, stores nothing
                 const int h0 = (mt / p.tiles_w) * p.TH;
                 const int w0 = (mt % p.tiles_w) * p.TW;
-                const int n0 = nt * BN;
+                const int n0 = nt * BN + (int)rank * (BN / CG);        // this CTA's half of the weight tile
                 if constexpr (HALO) {
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         ptx::mbar_wait(&aempty_bar[as], aphase ^ 1);
                         uint8_t* sa = smem + (size_t)as * a_stage_bytes;
-                        ptx::mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)(planes * kHaloTxBytes));
-                        ptx::tma_load_3d(sa, &tm_a_hi, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
-                        if (p.x3) ptx::tma_load_3d(sa + kHaloBytes, &tm_a_lo, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
+                        if (leader) ptx::mbar_arrive_expect_tx(&afull_bar[as], (uint32_t)(planes * kHaloTxBytes * CG));
+                        tma_ld<CG>(sa, &tm_a_hi, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
+                        if (p.x3) tma_ld<CG>(sa + kHaloBytes, &tm_a_lo, &afull_bar[as], cb * BK, w0 - 1, h0 - 1);
                         if (++as == AS) { as = 0; aphase ^= 1; }
                         for (int tap = 0; tap < 9; ++tap) {
                             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* st = ring + (size_t)stage * stage_bytes;
-                            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                            ptx::tma_load_3d(st, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
-                            if (p.x3) ptx::tma_load_3d(st + C::B_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
+                            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * CG));
+                            tma_ld<CG>(st, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
+                            if (p.x3) tma_ld<CG>(st + C::B_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
                             if (++stage == S) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -196,13 +222,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const int r = tap / p.ksize, s = tap - r * p.ksize;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = ring + (size_t)stage * stage_bytes;
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    ptx::tma_load_3d(st, &tm_a_hi, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
-                    ptx::tma_load_3d(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * CG));
+                    tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
+                    tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
                     if (p.x3) {
                         uint8_t* st2 = st + C::A_BYTES + C::B_BYTES;
-                        ptx::tma_load_3d(st2, &tm_a_lo, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
-                        ptx::tma_load_3d(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
+                        tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
+                        tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -210,7 +236,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, /*bf16*/ 1);
+        constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM * CG, BN, /*bf16*/ 1);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -218,7 +244,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         int as = 0;
         uint32_t aphase = 0;
         (void)as; (void)aphase;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; leader && tile < p.num_tiles; tile += tile_step) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_cols);
@@ -237,19 +263,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                             const uint64_t b_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
+                                mma_ss<CG>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
                             if (p.x3) {
                                 const uint64_t a_lo = make_halo_desc(arow + kHaloBytes);
                                 const uint64_t b_lo = ptx::make_smem_desc(st + C::B_BYTES, C::ROW_BYTES);
 #pragma unroll
                                 for (int k = 0; k < BK / 16; ++k)
-                                    ptx::mma_f16_ss(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
+                                    mma_ss<CG>(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (cb | tap | k) != 0);
 #pragma unroll
-                                for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                                for (int k = 0; k < BK / 16; ++k) mma_ss<CG>(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
                             }
-                            ptx::mma_commit(&empty_bar[stage]);                    // weight slot free
-                            if (tap == 8) ptx::mma_commit(&aempty_bar[as]);         // halo patch free
-                            if (tap == 8 && cb == p.cin_blocks - 1) ptx::mma_commit(&tfull_bar[acc]);
+                            mma_cm<CG>(&empty_bar[stage]);                    // weight slot free
+                            if (tap == 8) mma_cm<CG>(&aempty_bar[as]);         // halo patch free
+                            if (tap == 8 && cb == p.cin_blocks - 1) mma_cm<CG>(&tfull_bar[acc]);
                         }
                         __syncwarp();
                         if (++stage == S) { stage = 0; phase ^= 1; }
@@ -269,18 +295,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle span: +2 in (addr>>4)
-                        ptx::mma_f16_ss(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                        mma_ss<CG>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
                     }
                     if (p.x3) {
                         const uint64_t a_lo = ptx::make_smem_desc(st + C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
                         const uint64_t b_lo = ptx::make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) mma_ss<CG>(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) ptx::mma_f16_ss(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                        for (int k = 0; k < BK / 16; ++k) mma_ss<CG>(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
                     }
-                    ptx::mma_commit(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
-                    if (kb == num_kb - 1) ptx::mma_commit(&tfull_bar[acc]);   // accumulator complete
+                    mma_cm<CG>(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
+                    if (kb == num_kb - 1) mma_cm<CG>(&tfull_bar[acc]);   // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == S) { stage = 0; phase ^= 1; }
@@ -296,9 +322,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t chunk_i = 0;                    // running chunk counter -> staging buffer parity
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
             const int nt = tile % p.n_tiles;
-            const int mt = tile / p.n_tiles;
+            const int mt = (tile / p.n_tiles) * CG + (int)rank;
             const int h0 = (mt / p.tiles_w) * p.TH, w0 = (mt % p.tiles_w) * p.TW;
             const int h = h0 + row / p.TW;
             const int w = w0 + row % p.TW;
@@ -409,7 +435,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[acc]); else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
         }
         if (issuer) ptx::bulk_wait_group<0>();     // staging smem must outlive the last bulk store
@@ -417,9 +445,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync();      // the peer may still signal our barriers / read our smem until here
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if constexpr (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -469,7 +499,7 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
     return FRCNN_OK;
 }
 
-static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0;
+static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0;
 
 static int device_sm_count() {
     static int sms = 0;
@@ -482,9 +512,9 @@ static int device_sm_count() {
     return sms;
 }
 
-template <int BN, int BK, bool HALO>
+template <int BN, int BK, bool HALO, int CG>
 static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream) {
-    using C = Cfg<BN, BK>;
+    using C = Cfg<BN, BK, CG>;
     const int planes = p.x3 ? 2 : 1;
     const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
     const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0);
@@ -507,10 +537,23 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_bufs * p.acc_cols) p.tmem_cols *= 2;
-    auto kern = conv_gemm_kernel<BN, BK, HALO>;
+    auto kern = conv_gemm_kernel<BN, BK, HALO, CG>;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
-    kern<<<grid, kNumThreads, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    const int units = device_sm_count() / CG;            // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+    const int grid = CG * (p.num_tiles < units ? p.num_tiles : units);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    FRCNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }
@@ -518,6 +561,8 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
 }  // namespace frcnn
 
 using namespace frcnn;
+
+extern "C" void frcnn_conv2d_set_cta_group(int cta_group) { g_force_cg = cta_group; }
 
 extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
     g_force_bn = block_n;
@@ -595,8 +640,12 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     p.ksize = ksize; p.taps = ksize * ksize; p.cin_blocks = cdiv(Cin, BK);
     p.TH = TH; p.TW = TW; p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     p.n_tiles = cdiv(cout_cover, BN);
+    // CTA pairs (cta_group::2) for the wide-N tiles of layers with at least two pixel tiles
+    int CG = (BN >= 128 && BK == 64 && m_tiles >= 2) ? 2 : 1;
+    if (g_force_cg == 1) CG = 1;
+    if (g_force_cg == 2 && BN >= 128 && BK == 64) CG = 2;
     FRCNN_REQUIRE(m_tiles * p.n_tiles < (1l << 30), "frcnn_conv2d: too many tiles");
-    p.num_tiles = (int)(m_tiles * p.n_tiles);
+    p.num_tiles = (int)(cdiv((int)m_tiles, CG) * p.n_tiles);     // tiles (CG = 1) or pair-tiles (CG = 2)
     p.num_stages = 0;
     p.x3 = x_lo != nullptr;
     p.relu = relu;
@@ -614,10 +663,10 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     int rc;
     const int abw = halo ? kHaloW : TW, abh = halo ? kHaloH : TH;     // A box: the tile, or the tile + 1-pixel halo
     if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
-    if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+    if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, p.taps, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     if (p.x3) {
         if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
-        if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, p.taps, BK, BN, 1)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, p.taps, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     } else {
         tm[1] = tm[0];
         tm[3] = tm[2];
@@ -636,17 +685,21 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
         tm[5] = tm[0];
     }
 
-#define FRCNN_DISPATCH(BN_, BK_, HALO_) \
-    if (BN == BN_ && BK == BK_ && halo == HALO_) return launch_conv<BN_, BK_, HALO_>(tm, p, stream);
-    FRCNN_DISPATCH(256, 64, true)
-    FRCNN_DISPATCH(128, 64, true)
-    FRCNN_DISPATCH(64, 64, true)
-    FRCNN_DISPATCH(256, 64, false)
-    FRCNN_DISPATCH(128, 64, false)
-    FRCNN_DISPATCH(64, 64, false)
-    FRCNN_DISPATCH(256, 16, false)
-    FRCNN_DISPATCH(128, 16, false)
-    FRCNN_DISPATCH(64, 16, false)
+#define FRCNN_DISPATCH(BN_, BK_, HALO_, CG_) \
+    if (BN == BN_ && BK == BK_ && halo == HALO_ && CG == CG_) return launch_conv<BN_, BK_, HALO_, CG_>(tm, p, stream);
+    FRCNN_DISPATCH(256, 64, true, 2)
+    FRCNN_DISPATCH(128, 64, true, 2)
+    FRCNN_DISPATCH(256, 64, false, 2)
+    FRCNN_DISPATCH(128, 64, false, 2)
+    FRCNN_DISPATCH(256, 64, true, 1)
+    FRCNN_DISPATCH(128, 64, true, 1)
+    FRCNN_DISPATCH(64, 64, true, 1)
+    FRCNN_DISPATCH(256, 64, false, 1)
+    FRCNN_DISPATCH(128, 64, false, 1)
+    FRCNN_DISPATCH(64, 64, false, 1)
+    FRCNN_DISPATCH(256, 16, false, 1)
+    FRCNN_DISPATCH(128, 16, false, 1)
+    FRCNN_DISPATCH(64, 16, false, 1)
 #undef FRCNN_DISPATCH
     set_error("frcnn_conv2d: no kernel for BN=%d BK=%d", BN, BK);
     return FRCNN_ERR_ARG;

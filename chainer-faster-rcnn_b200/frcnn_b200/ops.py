@@ -117,6 +117,11 @@ def set_conv_tile(block_n=0, tile_h=0, tile_w=0):
     _lib.load().frcnn_conv2d_set_tile(block_n, tile_h, tile_w)
 
 
+def set_conv_cta_group(cta_group=0):
+    """0 = automatic, 1 = single-CTA MMAs only, 2 = CTA pairs (cta_group::2) wherever the tile allows."""
+    _lib.load().frcnn_conv2d_set_cta_group(cta_group)
+
+
 def maxpool2x2_ceil(x, out=None):
     H, W, C = x.hi.shape
     if out is None:

@@ -112,6 +112,9 @@ int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, cons
 /* Tuning override for tests / benchmarks: force the N tile (64/128/256) and the pixel tile
  * (tile_h*tile_w == 128); 0 = automatic. Process-wide. */
 void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w);
+/* 0 = automatic (CTA pairs / cta_group::2 for N tiles >= 128), 1 = force single-CTA MMAs, 2 = force pairs
+ * where the tile allows it.  Process-wide; for tests and A/B timing. */
+void frcnn_conv2d_set_cta_group(int cta_group);
 
 /* OIHW fp32 weights (Chainer layout, e.g. trunk/conv1_1/W) -> [kh*kw, Cout, Cin_pad] bf16 hi/lo.
  * For Linear weights (Cout, K) pass kh=kw=1.  `perm_chw_to_hwc` != 0 with (c,h,w) = (pc,ph,pw)

@@ -5,25 +5,23 @@ import subprocess
 import sys
 
 CONFIGS = [
-    # H, W, Cin, Cout, k, precision, tile(bn,th,tw) or None
-    (16, 8, 64, 64, 1, "bf16", None),
-    (16, 8, 64, 64, 3, "bf16", None),
-    (24, 40, 64, 64, 3, "bf16", None),
-    (24, 40, 64, 64, 3, "bf16x3", None),
-    (19, 33, 64, 128, 3, "bf16", None),
-    (13, 21, 128, 256, 3, "bf16", None),
-    (13, 21, 128, 256, 3, "bf16x3", None),
-    (11, 17, 16, 64, 3, "bf16", None),
-    (11, 17, 16, 64, 3, "bf16x3", None),
-    (38, 63, 512, 512, 3, "bf16x3", None),
-    (1, 300, 1024, 128, 1, "bf16x3", None),
+    # H, W, Cin, Cout, k, precision, tile(bn,th,tw) or None, cta_group
+    (32, 16, 64, 128, 3, "bf16", None, 2),
+    (32, 16, 64, 128, 1, "bf16", None, 2),
+    (33, 41, 128, 256, 3, "bf16", None, 2),
+    (33, 41, 128, 256, 3, "bf16x3", None, 2),
+    (33, 41, 128, 256, 3, "bf16x3", None, 1),
+    (38, 63, 512, 512, 3, "bf16x3", None, 2),
+    (1, 300, 1024, 256, 1, "bf16x3", None, 2),
+    (75, 125, 256, 512, 3, "bf16", (256, 16, 8), 2),
 ]
 
 CHILD = r'''
 import sys, json, numpy as np, torch
 sys.path[:0] = ["chainer-faster-rcnn_b200", "oracle", "tests"]
 from frcnn_b200 import ops
-H, W, Cin, Cout, k, prec, tile = json.loads(sys.argv[1])
+H, W, Cin, Cout, k, prec, tile, cg = json.loads(sys.argv[1])
+ops.set_conv_cta_group(cg)
 rng = np.random.default_rng(1)
 x = rng.standard_normal((Cin, H, W)).astype(np.float32)
 w = (rng.standard_normal((Cout, Cin, k, k)) * (2.0 / (Cin * k * k)) ** 0.5).astype(np.float32)

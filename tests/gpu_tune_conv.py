@@ -25,21 +25,25 @@ for prec in precisions:
         gflop = 2.0 * H * W * Cout * k * k * Cin / 1e9
         res = []
         tiles = TILES if H > 1 else [(1, 128)]
-        for bn in (64, 128, 256):
-            if bn > Cout:
-                continue
-            for (th, tw) in tiles:
-                ops.set_conv_tile(bn, th, tw)
-                for _ in range(2):
-                    ops.conv2d(act, wh, wl, bias, k, True, out=out)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(5):
-                    ops.conv2d(act, wh, wl, bias, k, True, out=out)
-                e1.record()
-                torch.cuda.synchronize()
-                res.append((e0.elapsed_time(e1) / 5, bn, th, tw))
+        tiles = [(16, 8), (8, 16)] if H > 1 else [(1, 128)]     # (16,8) = halo path for 3x3
+        for cg in (1, 2):
+            for bn in (64, 128, 256):
+                if bn > Cout or (cg == 2 and bn < 128):
+                    continue
+                for (th, tw) in tiles:
+                    ops.set_conv_tile(bn, th, tw)
+                    ops.set_conv_cta_group(cg)
+                    for _ in range(2):
+                        ops.conv2d(act, wh, wl, bias, k, True, out=out)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(5):
+                        ops.conv2d(act, wh, wl, bias, k, True, out=out)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    res.append((e0.elapsed_time(e1) / 5, bn, th, tw, cg))
         ops.set_conv_tile(0, 0, 0)
+        ops.set_conv_cta_group(0)
         for _ in range(2):
             ops.conv2d(act, wh, wl, bias, k, True, out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,4 +57,4 @@ for prec in precisions:
         best = res[0]
         print("%s %4dx%4dx%5d->%4d k%d  auto %.4f ms (%.0f TF) | best %.4f ms bn%d %dx%d (%.0f TF) | %s" % (
             prec, H, W, Cin, Cout, k, auto, gflop / auto, best[0], best[1], best[2], best[3], gflop / best[0],
-            " ".join("bn%d/%dx%d:%.3f" % (r[1], r[2], r[3], r[0]) for r in res[:6])), flush=True)
+            " ".join("cg%d/bn%d/%dx%d:%.3f" % (r[4], r[1], r[2], r[3], r[0]) for r in res[:8])), flush=True)

@@ -208,6 +208,21 @@ def test_conv2d_tile_shapes(ops, tile):
     _conv_case(ops, 37, 45, 64, 256, 3, "bf16", seed=5, tile=tile, ld_f32=256)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("shape", [(33, 41, 128, 256, 3),     # odd number of pixel tiles: the last pair has a dummy CTA
+                                   (16, 8, 64, 128, 3),       # a single pixel tile (pairs not applicable)
+                                   (1, 300, 512, 256, 1)])    # GEMM rows, 3 tiles
+def test_conv2d_single_cta_and_cta_pair_agree_with_oracle(ops, precision, cta_group, shape):
+    """cta_group::1 and cta_group::2 (CTA pairs, M = 256 MMAs, half of B per CTA) must both match the oracle."""
+    H, W, Cin, Cout, k = shape
+    ops.set_conv_cta_group(cta_group)
+    try:
+        _conv_case(ops, H, W, Cin, Cout, k, precision, seed=77, ld_f32=(Cout + 31) // 32 * 32)
+    finally:
+        ops.set_conv_cta_group(0)
+
+
 def test_conv2d_first_layer_from_3_channels(ops):
     """conv1_1: C_in=3 padded to 16 channels (zeros), K-block = one tap x 16 channels."""
     rng = np.random.default_rng(11)
