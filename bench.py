@@ -181,8 +181,8 @@ def conv_layer_table(plan, torch, reps=3):
         e1.record()
         Hh, Ww, Cin = x.hi.shape
         taps, Cout, _ = w_hi.shape
-        cin_true = 3 if Cin == 16 else Cin
-        rows.append([(e0, e1), 2.0 * Hh * Ww * Cout * taps * cin_true / 1e9, "%dx%dx%d->%d k%d" % (Hh, Ww, Cin, Cout, ksize)])
+        k_true = 27 if (Cin == 32 and taps == 1 and Hh > 1) else taps * Cin     # conv1_1 = im2col GEMM, 27 real K
+        rows.append([(e0, e1), 2.0 * Hh * Ww * Cout * k_true / 1e9, "%dx%dx%d->%d k%d" % (Hh, Ww, Cin, Cout, ksize)])
         return r
     ops.conv2d = timed
     acc = {}

@@ -587,7 +587,7 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
                   "frcnn_conv2d: fuse_pool2x2 needs a bf16 output, relu=1, no fp32 output and no m_valid");
 
     const int BK = (Cin >= 64) ? 64 : (Cin >= 32 ? 32 : 16);
-    FRCNN_REQUIRE(BK != 32, "frcnn_conv2d: Cin in [32,64) is not supported (use 16 or >= 64)");
+    FRCNN_REQUIRE(BK != 32 || Cin == 32, "frcnn_conv2d: Cin in (32,64) is not supported (use 16, 32 or >= 64)");
 
     // ---- pixel tile: minimise padded pixels (the fused pool needs the 8x16 tile: 2x2 windows inside a warp)
     static const int shapes[6][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
@@ -697,6 +697,8 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     FRCNN_DISPATCH(256, 64, false, 1)
     FRCNN_DISPATCH(128, 64, false, 1)
     FRCNN_DISPATCH(64, 64, false, 1)
+    FRCNN_DISPATCH(128, 32, false, 1)
+    FRCNN_DISPATCH(64, 32, false, 1)
     FRCNN_DISPATCH(256, 16, false, 1)
     FRCNN_DISPATCH(128, 16, false, 1)
     FRCNN_DISPATCH(64, 16, false, 1)

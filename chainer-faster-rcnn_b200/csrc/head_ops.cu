@@ -98,6 +98,53 @@ __global__ void pack_weights_kernel(const float* w, int Cout, int Cin, int taps,
     }
 }
 
+// First-layer im2col: (C<=3,H,W) fp32 -> [H][W][32] bf16 hi/lo with K index (r*3+s)*C + c (zero padded
+// borders, zeros for k >= 9*C).  conv1_1 (C_in = 3, K = 27) then runs as ONE 64-byte-row k-block per tile
+// instead of nine 32-byte-row blocks.  One thread per pixel; neighbouring threads share their loads in L1.
+__global__ void pack_image_im2col_kernel(const float* x, int C, int H, int W, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const long total = (long)H * W;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+        const int h = (int)(p / W), w = (int)(p % W);
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int hh = h + r - 1, ww = w + s - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (c < C) v[(r * 3 + s) * C + c] = x[((long)c * H + hh) * W + ww];
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            F8 f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f.v[j] = v[8 * q + j];
+            store8(hi, lo, p * 32 + 8 * q, f);
+        }
+    }
+}
+
+// OIHW 3x3 weights (Cin <= 3) -> [1][Cout][32] bf16 hi/lo with the same K order as pack_image_im2col_kernel.
+__global__ void pack_weights_im2col_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * 32) return;
+    const int o = i / 32, k = i % 32;
+    float v = 0.0f;
+    if (k < 9 * Cin) {
+        const int tap = k / Cin, c = k % Cin;
+        v = w[((long)o * Cin + c) * 9 + tap];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+}
+
 __global__ void unpack_nhwc_kernel(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int H, int W, int C, float* y) {
     const long total = (long)H * W * C;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -325,6 +372,23 @@ extern "C" int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, i
     const long total = (long)kh * kw * Cout * Cin_pad;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w_oihw, Cout, Cin, kh * kw, Cin_pad, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, perm_chw_to_hwc, pc, ph, pw);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_pack_image_im2col3x3(const float* x_chw, int C, int H, int W, void* y_hi, void* y_lo, void* stream) {
+    FRCNN_REQUIRE(x_chw && y_hi && C > 0 && C <= 3 && H > 0 && W > 0, "frcnn_pack_image_im2col3x3: needs 1 <= C <= 3 (got %d)", C);
+    pack_image_im2col_kernel<<<grid_for((long)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+        x_chw, C, H, W, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_pack_conv_weights_im2col3x3(const float* w_oihw, int Cout, int Cin, void* w_hi, void* w_lo,
+                                                 void* stream) {
+    FRCNN_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && Cin <= 3, "frcnn_pack_conv_weights_im2col3x3: needs 1 <= Cin <= 3");
+    pack_weights_im2col_kernel<<<cdiv(Cout * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+        w_oihw, Cout, Cin, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }

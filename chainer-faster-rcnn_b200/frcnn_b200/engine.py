@@ -55,7 +55,13 @@ class PackedWeights(object):
                 continue
             name, cin, cout = item
             w = P("trunk/%s/W" % name)
-            self.convs[name] = self._pack(w, P("trunk/%s/b" % name), cin_pad=16 if cin < 16 else cin)
+            if cin <= 3:
+                # first layer as a K=32 GEMM over the im2col-packed image (ops.pack_image_im2col)
+                hi, lo = ops.pack_conv_weights_im2col(w, precision=precision)
+                b = P("trunk/%s/b" % name)
+                self.convs[name] = (hi, lo, ops.pad_bias(b, b.numel()))
+            else:
+                self.convs[name] = self._pack(w, P("trunk/%s/b" % name), cin_pad=cin)
         self.rpn3 = self._pack(P("RPN/rpn_conv_3x3/W"), P("RPN/rpn_conv_3x3/b"))
         # twin 1x1 heads merged along Cout: rows [0,2A) = rpn_cls_score, [2A,6A) = rpn_bbox_pred
         wh = torch.cat([P("RPN/rpn_cls_score/W"), P("RPN/rpn_bbox_pred/W")], dim=0)
@@ -97,7 +103,7 @@ class ForwardPlan(object):
 
         self.x_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)      # static input (C,H,W)
         self.img_info = torch.tensor([H, W], dtype=torch.int32, device=dev)      # clip bounds (h, w): static in the graph
-        self.acts = [act(H, W, 16)]
+        self.acts = [act(H, W, 32)]          # im2col-packed image: 27 taps*channels + 5 zeros per pixel
         h, w_ = H, W
         self.trunk_steps = []          # (layer name, fuse the following 2x2 pool into the conv epilogue)
         for i, item in enumerate(VGG16_LAYERS):
@@ -138,13 +144,13 @@ class ForwardPlan(object):
         n = 0
         lib = ops._lib.load()
         x = self.acts[0]
-        ops.check(lib.frcnn_pack_image(ops._p(self.x_in), 3, self.H, self.W, 16, ops._p(x.hi), ops._p(x.lo), ops._stream()),
-                  "frcnn_pack_image")
+        ops.pack_image_im2col(self.x_in, out=x)
         n += 1
         i = 0
         for name, fused, pool_after in self.trunk_steps:
             hi, lo, b = w.convs[name]
-            ops.conv2d(self.acts[i], hi, lo, b, 3, True, out=self.acts[i + 1], fuse_pool=fused)
+            ksize = 1 if i == 0 else 3          # conv1_1 runs as a 1x1 over the im2col image
+            ops.conv2d(self.acts[i], hi, lo, b, ksize, True, out=self.acts[i + 1], fuse_pool=fused)
             n += 1
             i += 1
             if pool_after:

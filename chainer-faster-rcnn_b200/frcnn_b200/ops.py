@@ -80,6 +80,33 @@ def pack_conv_weights(w, cin_pad=None, precision="bf16x3", perm_chw=None):
     return hi, lo
 
 
+def pack_image_im2col(x_chw, precision="bf16x3", out=None):
+    """(C<=3,H,W) float32 CUDA image -> Act [H,W,32]: every pixel's zero-padded 3x3xC neighbourhood."""
+    _need_cuda(x_chw)
+    x = x_chw.contiguous().float()
+    C, H, W = x.shape
+    if out is None:
+        hi = torch.empty((H, W, 32), dtype=torch.bfloat16, device=x.device)
+        out = Act(hi, torch.empty_like(hi) if precision == "bf16x3" else None)
+    check(_lib.load().frcnn_pack_image_im2col3x3(_p(x), C, H, W, _p(out.hi), _p(out.lo), _stream()),
+          "frcnn_pack_image_im2col3x3")
+    return out
+
+
+def pack_conv_weights_im2col(w, precision="bf16x3"):
+    """OIHW (Cout, Cin<=3, 3, 3) float32 -> ([1, Cout, 32] bf16 hi, lo or None), K order of pack_image_im2col."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    Cout, Cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise FrcnnError("pack_conv_weights_im2col: 3x3 kernels only")
+    hi = torch.empty((1, Cout, 32), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if precision == "bf16x3" else None
+    check(_lib.load().frcnn_pack_conv_weights_im2col3x3(_p(w), Cout, Cin, _p(hi), _p(lo), _stream()),
+          "frcnn_pack_conv_weights_im2col3x3")
+    return hi, lo
+
+
 def pad_bias(b, n):
     out = torch.zeros(round_up(max(n, b.numel()), 32), dtype=torch.float32, device=b.device)
     out[: b.numel()] = b.float()

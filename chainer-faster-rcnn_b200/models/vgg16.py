@@ -44,7 +44,10 @@ class VGG16Prev(links.Link):
                 name, cin, _ = item
                 l = getattr(self, name)
                 w = torch.from_numpy(l.W.data).to(device)
-                hi, lo = ops.pack_conv_weights(w, cin_pad=16 if cin < 16 else cin, precision=self.precision)
+                if cin <= 3:      # first layer: K = 27 (+5 zeros) GEMM over the im2col-packed image
+                    hi, lo = ops.pack_conv_weights_im2col(w, precision=self.precision)
+                else:
+                    hi, lo = ops.pack_conv_weights(w, cin_pad=cin, precision=self.precision)
                 packed[name] = (hi, lo, ops.pad_bias(torch.from_numpy(l.b.data).to(device), l.b.data.size))
             self.__dict__["_packed"] = (packed, self._version)
         return packed
@@ -52,13 +55,13 @@ class VGG16Prev(links.Link):
     def forward_device(self, x_chw):
         """(3,H,W) CUDA float32 -> ops.Act [h,w,512] (NHWC bf16 hi/lo)."""
         packed = self._weights(x_chw.device)
-        act = ops.pack_image(x_chw, c_pad=16, precision=self.precision)
+        act = ops.pack_image_im2col(x_chw, precision=self.precision)
         for i, item in enumerate(_PLAN):
             if item is None:
                 continue                      # the 2x2 ceil-mode pool is fused into the preceding conv's epilogue
             hi, lo, b = packed[item[0]]
             pooled = i + 1 < len(_PLAN) and _PLAN[i + 1] is None
-            act, _ = ops.conv2d(act, hi, lo, b, 3, True, fuse_pool=pooled)
+            act, _ = ops.conv2d(act, hi, lo, b, 1 if i == 0 else 3, True, fuse_pool=pooled)
         return act
 
     def __call__(self, x):

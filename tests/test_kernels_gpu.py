@@ -239,6 +239,29 @@ def test_conv2d_first_layer_from_3_channels(ops):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_conv2d_first_layer_as_im2col_gemm(ops, precision):
+    """conv1_1 the way the engine runs it: frcnn_pack_image_im2col3x3 + a K=32 (27 real) 1x1 GEMM with
+    SWIZZLE_64B tiles.  Same oracle as the 16-channel-padded 3x3 path."""
+    rng = np.random.default_rng(12)
+    x = (rng.uniform(0, 255, (3, 45, 70)) - 110).astype(f32)
+    w = (rng.standard_normal((64, 3, 3, 3)) * 0.27 / 64).astype(f32)
+    b = (rng.standard_normal(64) * 0.1).astype(f32)
+    q = _quant16 if precision == "bf16x3" else _bf16
+    ref = torch.nn.functional.conv2d(torch.from_numpy(q(x))[None].double(), torch.from_numpy(q(w)).double(),
+                                     torch.from_numpy(b).double(), padding=1)[0].clamp_min(0).numpy()
+    act = ops.pack_image_im2col(dev(x), precision=precision)
+    assert act.hi.shape == (45, 70, 32)
+    # the packed image itself: centre tap == the pixel, zero padding at the border, zeros for k >= 27
+    v = act.hi.float() + (act.lo.float() if act.lo is not None else 0)
+    assert torch.equal(v[:, :, 12:15].permute(2, 0, 1).cpu(), torch.from_numpy(q(x)))
+    assert not v[:, :, 27:].any() and not v[0, :, 0:9].any() and not v[:, 0, 0:27:9].any()
+    wh, wl = ops.pack_conv_weights_im2col(dev(w), precision=precision)
+    y, _ = ops.conv2d(act, wh, wl, ops.pad_bias(dev(b), 64), 1, True)
+    err = np.abs(y.to_chw_f32().cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < (5e-5 if precision == "bf16x3" else 6e-3), err
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 @pytest.mark.parametrize("shape", [(37, 45, 64, 64), (600 // 4, 1000 // 4 + 1, 64, 128), (19, 31, 128, 256)])
 def test_conv2d_fused_maxpool_equals_conv_then_pool(ops, precision, shape):
     """The fused epilogue (conv + ReLU + 2x2 ceil-mode max-pool, odd H/W included) must give exactly the
