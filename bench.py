@@ -248,13 +248,23 @@ def run_b200_arm(args, rank, local_rank, world):
     res_box = torch.empty((plan.post_n, 84), dtype=torch.float32).pin_memory()
     res_cnt = torch.empty((1,), dtype=torch.int32).pin_memory()
 
+    dbg = os.environ.get("FRCNN_BENCH_DEBUG") == "1"
+    dbg_rows = []
+
     def e2e_step(i):
+        t = [time.perf_counter()]
         plan.x_in.copy_(imgs_host[i % n_img], non_blocking=True)        # H2D from pinned memory
+        t.append(time.perf_counter())
         prob, boxes, count = plan.forward(None)
+        t.append(time.perf_counter())
         res_prob.copy_(prob, non_blocking=True)                         # D2H
         res_box.copy_(boxes, non_blocking=True)
         res_cnt.copy_(count, non_blocking=True)
+        t.append(time.perf_counter())
         torch.cuda.synchronize()                                        # the caller reads the result
+        t.append(time.perf_counter())
+        if dbg:
+            dbg_rows.append([1e3 * (b - a) for a, b in zip(t, t[1:])])
         return int(res_cnt[0])
     for i in range(3):
         e2e_step(i)
@@ -263,6 +273,9 @@ def run_b200_arm(args, rank, local_rank, world):
     for i in range(args.steps):
         e2e_step(i)
     t_serial = time.perf_counter() - t0                      # one image at a time: latency, not throughput
+    if dbg:
+        print("e2e serial phases ms [h2d-call, replay-call, d2h-calls, sync] median:",
+              np.round(np.median(np.array(dbg_rows[3:]), 0), 3), file=sys.stderr)
     # the public streaming call: host image in, host result out for EVERY step; the H2D of image i+1
     # overlaps the graph of image i (frcnn_b200.engine.StreamRunner)
     from frcnn_b200.engine import StreamRunner
@@ -292,6 +305,12 @@ def run_b200_arm(args, rank, local_rank, world):
     conv_ms = sum(r[1] for r in conv_rows)
     all_ms = sum(r[1] for r in table)
     exec_mult = 3.0 if args.precision == "bf16x3" else 1.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_stack_dram.json")
+    if args.precision == "bf16x3" and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["conv_stack_dram_bytes_per_step"], tj["source"]
     achieved = CONV_STACK_GFLOP / conv_ms          # GFLOP/ms == TFLOP/s (algorithmic flops)
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM, %d launches/step)" % len(table),
@@ -299,7 +318,12 @@ def run_b200_arm(args, rank, local_rank, world):
         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a step)" % peak_src,
         "algorithmic_gflop_per_step": CONV_STACK_GFLOP, "conv_stack_ms": conv_ms, "all_gemm_ms": all_ms,
         "executed_mma_flop_multiplier": exec_mult, "executed_tflops": achieved * exec_mult,
-        "traffic": None,
+        "traffic": traffic,     # DRAM read+write bytes of the conv-stack launches of one step, from the committed ncu pass
+        "traffic_source": traffic_src,
+        # every conv-stack activation written once + read once (hi+lo planes, 4 B/elem), the im2col input read
+        # once, weights (17.1 M params, hi+lo) read once: 1.02 GB; measured DRAM traffic below that
+        # means part of the producer->consumer traffic stays in the 126 MB L2, above it would mean re-reads
+        "algorithmic_bytes_per_step": 1.02e9 if args.precision == "bf16x3" else 0.51e9,
         "layers": [{"shape": n, "ms": round(m, 4), "tflops_algorithmic": round(g / m, 1)} for n, m, g in table],
     }
 

@@ -641,9 +641,9 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     p.TH = TH; p.TW = TW; p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     p.n_tiles = cdiv(cout_cover, BN);
     // CTA pairs (cta_group::2) for the wide-N tiles of layers with at least two pixel tiles
-    int CG = (BN >= 128 && BK == 64 && m_tiles >= 2) ? 2 : 1;
+    int CG = (BK == 64 && m_tiles >= 2) ? 2 : 1;      // measured: pairs win at every N (conv1_2, N = 64: -27 %)
     if (g_force_cg == 1) CG = 1;
-    if (g_force_cg == 2 && BN >= 128 && BK == 64) CG = 2;
+    if (g_force_cg == 2 && BK == 64) CG = 2;
     FRCNN_REQUIRE(m_tiles * p.n_tiles < (1l << 30), "frcnn_conv2d: too many tiles");
     p.num_tiles = (int)(cdiv((int)m_tiles, CG) * p.n_tiles);     // tiles (CG = 1) or pair-tiles (CG = 2)
     p.num_stages = 0;
@@ -691,6 +691,8 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     FRCNN_DISPATCH(128, 64, true, 2)
     FRCNN_DISPATCH(256, 64, false, 2)
     FRCNN_DISPATCH(128, 64, false, 2)
+    FRCNN_DISPATCH(64, 64, true, 2)
+    FRCNN_DISPATCH(64, 64, false, 2)
     FRCNN_DISPATCH(256, 64, true, 1)
     FRCNN_DISPATCH(128, 64, true, 1)
     FRCNN_DISPATCH(64, 64, true, 1)

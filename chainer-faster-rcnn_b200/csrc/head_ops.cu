@@ -102,30 +102,27 @@ __global__ void pack_weights_kernel(const float* w, int Cout, int Cin, int taps,
 // borders, zeros for k >= 9*C).  conv1_1 (C_in = 3, K = 27) then runs as ONE 64-byte-row k-block per tile
 // instead of nine 32-byte-row blocks.  One thread per pixel; neighbouring threads share their loads in L1.
 __global__ void pack_image_im2col_kernel(const float* x, int C, int H, int W, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    const long total = (long)H * W;
-    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+    // 4 threads per pixel, each producing one 16-byte chunk (8 consecutive k): consecutive threads write
+    // consecutive 16-B chunks -> fully coalesced stores of both planes.
+    const long total = (long)H * W * 4;
+    const int kmax = 9 * C;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long p = t >> 2;
+        const int q = (int)(t & 3);
         const int h = (int)(p / W), w = (int)(p % W);
-        float v[32];
+        F8 f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = 0.0f;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int hh = h + r - 1, ww = w + s - 1;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (c < C) v[(r * 3 + s) * C + c] = x[((long)c * H + hh) * W + ww];
-                }
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * q + j;
+            float v = 0.0f;
+            if (k < kmax) {
+                const int tap = k / C, c = k - tap * C;
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((long)c * H + hh) * W + ww];
             }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            F8 f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f.v[j] = v[8 * q + j];
-            store8(hi, lo, p * 32 + 8 * q, f);
+            f.v[j] = v;
         }
+        store8(hi, lo, p * 32 + 8 * q, f);
     }
 }
 
@@ -378,7 +375,7 @@ extern "C" int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, i
 
 extern "C" int frcnn_pack_image_im2col3x3(const float* x_chw, int C, int H, int W, void* y_hi, void* y_lo, void* stream) {
     FRCNN_REQUIRE(x_chw && y_hi && C > 0 && C <= 3 && H > 0 && W > 0, "frcnn_pack_image_im2col3x3: needs 1 <= C <= 3 (got %d)", C);
-    pack_image_im2col_kernel<<<grid_for((long)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+    pack_image_im2col_kernel<<<grid_for((long)H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
         x_chw, C, H, W, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;

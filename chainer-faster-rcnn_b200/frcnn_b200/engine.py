@@ -253,8 +253,6 @@ class StreamRunner(object):
         self._prefetch(host_images[0], 0)
         for i in range(n):
             s = i & 1
-            if i + 1 < n:
-                self._prefetch(host_images[i + 1], s ^ 1, after=self.step_done[s ^ 1] if i >= 1 else None)
             cur.wait_event(self.h2d_done[s])
             plan.x_in.copy_(self.stage[s], non_blocking=True)           # D2D into the graph's static input
             plan.graph.replay()
@@ -263,6 +261,10 @@ class StreamRunner(object):
             r["boxes"].copy_(plan.boxes, non_blocking=True)
             r["count"].copy_(plan.prop.count, non_blocking=True)
             self.step_done[s].record(cur)
+            # image i's graph is queued: now feed image i+1 (the H2D call may hold the host thread for the
+            # duration of the copy on some hosts -- it overlaps the GPU work just queued either way)
+            if i + 1 < n:
+                self._prefetch(host_images[i + 1], s ^ 1, after=self.step_done[s ^ 1] if i >= 1 else None)
             if i >= 1:                                                   # hand image i-1's result to the host
                 self.step_done[s ^ 1].synchronize()
                 counts.append(int(self.res[s ^ 1]["count"][0]))

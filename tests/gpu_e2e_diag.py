@@ -1,49 +1,20 @@
-"""Diagnostic (not a pytest file): why is a single graph replay slow after an H2D copy / idle gap?"""
-import sys, time
+"""Diagnostic (not a pytest file): does an nvidia-smi poller stall cudaMemcpyAsync? does terminate() kill it?"""
+import os, signal, sys, time, subprocess
 import numpy as np, torch
-sys.path[:0] = ["chainer-faster-rcnn_b200", "oracle"]
-import frcnn_oracle as orc
-from frcnn_b200.engine import Engine
-eng = Engine(orc.make_params(seed=1234), anchors=orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32)))
-plan = eng.plan(600, 1000)
-host = torch.from_numpy(orc.make_image(600, 1000, seed=0)[0]).pin_memory()
-dev_img = host.cuda()
-other = torch.empty_like(dev_img)
-plan.forward(dev_img); torch.cuda.synchronize()
-
-def timed_replay(label, pre):
-    res = []
-    for _ in range(8):
-        pre()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a = time.perf_counter()
-        e0.record(); plan.graph.replay(); e1.record()
-        torch.cuda.synchronize()
-        b = time.perf_counter()
-        res.append(((b - a) * 1e3, e0.elapsed_time(e1)))
-    print("%-38s wall %s | gpu %s" % (label, " ".join("%.2f" % r[0] for r in res), " ".join("%.2f" % r[1] for r in res)))
-
-timed_replay("A: nothing before", lambda: None)
-timed_replay("B: H2D into x_in", lambda: plan.x_in.copy_(host, non_blocking=True))
-timed_replay("C: D2D into x_in", lambda: plan.x_in.copy_(dev_img, non_blocking=True))
-timed_replay("D: H2D into other buffer", lambda: other.copy_(host, non_blocking=True))
-timed_replay("E: 5 ms host sleep", lambda: time.sleep(0.005))
-timed_replay("F: 50 ms host sleep", lambda: time.sleep(0.05))
-# eager (no graph) single shot
-def eager(label, pre):
-    res = []
-    for _ in range(5):
-        pre(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a = time.perf_counter(); e0.record(); plan._run(); e1.record(); torch.cuda.synchronize(); b = time.perf_counter()
-        res.append(((b - a) * 1e3, e0.elapsed_time(e1)))
-    print("%-38s wall %s | gpu %s" % (label, " ".join("%.2f" % r[0] for r in res), " ".join("%.2f" % r[1] for r in res)))
-eager("G: eager after nothing", lambda: None)
-eager("H: eager after H2D", lambda: plan.x_in.copy_(host, non_blocking=True))
-# back-to-back
-torch.cuda.synchronize(); a = time.perf_counter()
-for _ in range(20): plan.graph.replay()
-torch.cuda.synchronize(); print("I: 20 back-to-back replays: %.3f ms each" % ((time.perf_counter() - a) / 20 * 1e3))
-import subprocess
-print(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,pstate,power.draw", "--format=csv"], capture_output=True, text=True).stdout)
+x = torch.empty((3, 600, 1000), dtype=torch.float32).pin_memory(); d = torch.empty_like(x, device="cuda")
+def pattern(label, n=300):
+    ts = []
+    for _ in range(n):
+        a = time.perf_counter(); d.copy_(x, non_blocking=True); torch.cuda.synchronize(); ts.append(1e3 * (time.perf_counter() - a))
+    ts = np.array(ts)
+    print("%-44s median %.2f ms, max %.1f ms, stalls>5ms: %d of %d, total %.0f ms" % (label, np.median(ts), ts.max(), (ts > 5).sum(), n, ts.sum()))
+pattern("before any nvidia-smi")
+cmd = ["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm", "--format=csv,noheader,nounits", "-lms", "100"]
+p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+time.sleep(0.5); pattern("while nvidia-smi -lms 100 runs")
+p.terminate(); time.sleep(0.5); pattern("after Popen.terminate() (poll=%s)" % p.poll())
+print(subprocess.run("ps -eo pid,ppid,pgid,cmd | grep -i nvidia-smi | grep -v grep", shell=True, capture_output=True, text=True).stdout)
+p2 = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, start_new_session=True)
+time.sleep(0.5)
+os.killpg(os.getpgid(p2.pid), signal.SIGKILL); time.sleep(0.5); pattern("after killpg of a new-session sampler")
+print(subprocess.run("ps -eo pid,ppid,pgid,cmd | grep -i nvidia-smi | grep -v grep; file $(which nvidia-smi)", shell=True, capture_output=True, text=True).stdout)

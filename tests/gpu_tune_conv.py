@@ -28,7 +28,7 @@ for prec in precisions:
         tiles = [(16, 8), (8, 16)] if H > 1 else [(1, 128)]     # (16,8) = halo path for 3x3
         for cg in (1, 2):
             for bn in (64, 128, 256):
-                if bn > Cout or (cg == 2 and bn < 128):
+                if bn > Cout:
                     continue
                 for (th, tw) in tiles:
                     ops.set_conv_tile(bn, th, tw)
