@@ -126,6 +126,48 @@ __global__ void pack_image_im2col_kernel(const float* x, int C, int H, int W, __
     }
 }
 
+// Caller-side preprocessing (forward.py:34-45, img_preprocessing): uint8 BGR HWC image -> float32(pixel - mean)
+// -> cv.resize(INTER_LINEAR) -> (3,H,W) float32.  One thread per output pixel, all three channels.  OpenCV's
+// float bilinear, restated: coordinate / floor / fraction in double, weight cast to float,
+// h = fma(S[x1] - S[x0], tx, S[x0]) on both source rows, out = fma(h1 - h0, ty, h0).
+struct PreArgs {
+    const unsigned char* src; int h0, w0;
+    double m0, m1, m2, sx, sy;
+    int H, W;
+    float* out;
+};
+__global__ void preprocess_bgr8_kernel(const PreArgs a) {
+    const long total = (long)a.H * a.W;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+        const int y = (int)(p / a.W), x = (int)(p % a.W);
+        const double fyd = ((double)y + 0.5) * a.sy - 0.5;
+        int y0 = (int)floor(fyd);
+        float ty = (float)(fyd - (double)y0);
+        if (y0 < 0) { y0 = 0; ty = 0.0f; }
+        if (y0 >= a.h0 - 1) { y0 = a.h0 - 1; ty = 0.0f; }
+        const int y1 = min(y0 + 1, a.h0 - 1);
+        const double fxd = ((double)x + 0.5) * a.sx - 0.5;
+        int x0 = (int)floor(fxd);
+        float tx = (float)(fxd - (double)x0);
+        if (x0 < 0) { x0 = 0; tx = 0.0f; }
+        if (x0 >= a.w0 - 1) { x0 = a.w0 - 1; tx = 0.0f; }
+        const int x1 = min(x0 + 1, a.w0 - 1);
+        const unsigned char* r0 = a.src + (long)y0 * a.w0 * 3;
+        const unsigned char* r1 = a.src + (long)y1 * a.w0 * 3;
+        const double mean[3] = {a.m0, a.m1, a.m2};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p00 = (float)((double)r0[x0 * 3 + c] - mean[c]);
+            const float p01 = (float)((double)r0[x1 * 3 + c] - mean[c]);
+            const float p10 = (float)((double)r1[x0 * 3 + c] - mean[c]);
+            const float p11 = (float)((double)r1[x1 * 3 + c] - mean[c]);
+            const float ha = __fmaf_rn(__fsub_rn(p01, p00), tx, p00);
+            const float hb = __fmaf_rn(__fsub_rn(p11, p10), tx, p10);
+            a.out[((long)c * a.H + y) * a.W + x] = __fmaf_rn(__fsub_rn(hb, ha), ty, ha);
+        }
+    }
+}
+
 // OIHW 3x3 weights (Cin <= 3) -> [1][Cout][32] bf16 hi/lo with the same K order as pack_image_im2col_kernel.
 __global__ void pack_weights_im2col_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* hi, __nv_bfloat16* lo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,6 +411,20 @@ extern "C" int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, i
     const long total = (long)kh * kw * Cout * Cin_pad;
     pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w_oihw, Cout, Cin, kh * kw, Cin_pad, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo, perm_chw_to_hwc, pc, ph, pw);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_preprocess_bgr8(const unsigned char* img_hwc, int h0, int w0, double mean_b, double mean_g,
+                                     double mean_r, double im_scale, int H, int W, float* out_chw, void* stream) {
+    FRCNN_REQUIRE(img_hwc && out_chw && h0 > 0 && w0 > 0 && H > 0 && W > 0 && im_scale > 0.0,
+                  "frcnn_preprocess_bgr8: bad arguments");
+    PreArgs a;
+    a.src = img_hwc; a.h0 = h0; a.w0 = w0;
+    a.m0 = mean_b; a.m1 = mean_g; a.m2 = mean_r;
+    a.sx = 1.0 / im_scale; a.sy = 1.0 / im_scale;
+    a.H = H; a.W = W; a.out = out_chw;
+    preprocess_bgr8_kernel<<<grid_for((long)H * W, 256), 256, 0, (cudaStream_t)stream>>>(a);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }

@@ -40,6 +40,8 @@ SIGNATURES = {
     "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "frcnn_pack_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_preprocess_bgr8": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int, c_int,
+                                      c_void_p, c_void_p]),
     "frcnn_pack_image_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_pack_conv_weights_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_unpack_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

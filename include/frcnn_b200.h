@@ -124,6 +124,14 @@ int frcnn_pack_conv_weights(const float* w_oihw, int Cout, int Cin, int kh, int 
                             void* w_lo, int perm_chw_to_hwc, int pc, int ph, int pw, void* stream);
 /* (C,H,W) fp32 image (the reference's input layout, forward.py:45) -> [H,W,C_pad] bf16 hi/lo. */
 int frcnn_pack_image(const float* x_chw, int C, int H, int W, int C_pad, void* y_hi, void* y_lo, void* stream);
+/* Caller-side preprocessing on the device ("next" row): forward.py:34-45 img_preprocessing.
+ * img_hwc: uint8 [h0,w0,3] BGR (what cv.imread returns); out_chw: float32 [3,H,W] =
+ * cv.resize(float32(img) - (mean_b,mean_g,mean_r), fx=fy=im_scale, INTER_LINEAR) transposed to CHW -- the tensor
+ * forward.py:90-92 uploads.  H, W = round-half-even(h0*im_scale), round-half-even(w0*im_scale) (caller computes,
+ * forward.py:38-41).  Uploading the raw uint8 image cuts the H2D bytes 4x or more. */
+int frcnn_preprocess_bgr8(const unsigned char* img_hwc, int h0, int w0, double mean_b, double mean_g, double mean_r,
+                          double im_scale, int H, int W, float* out_chw, void* stream);
+
 /* First layer as a GEMM: (C<=3,H,W) fp32 image -> [H,W,32] bf16 hi/lo whose 32 "channels" are the pixel's
  * zero-padded 3x3xC neighbourhood (k = (r*3+s)*C + c, zeros for k >= 9C), and the matching weight pack
  * OIHW (Cout,Cin<=3,3,3) -> [1,Cout,32].  conv1_1 (models/vgg16.py:39) is then frcnn_conv2d with ksize = 1,

@@ -68,6 +68,9 @@ def _lib():
         L.orc_roi_pool.restype = None
         L.orc_bbox_overlaps.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, dp]
         L.orc_bbox_overlaps.restype = None
+        L.orc_preprocess_bgr8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_int, ctypes.c_int, fp]
+        L.orc_preprocess_bgr8.restype = None
         _LIB = L
     return _LIB
 
@@ -416,6 +419,28 @@ def make_params(seed=1234, num_classes=21, mid_ch=512, n_anchors=9, trunk_std="h
 
 
 PIXEL_MEANS = np.array([102.9801, 115.9465, 122.7717], dtype=np.float64)   # forward.py:22 (BGR)
+
+
+def preprocess_plan(h0, w0, scale=600, max_size=1000):
+    """Scale factor and output size of forward.py:34-45 (img_preprocessing): shortest side -> `scale`
+    unless the longest would exceed `max_size`; cv.resize rounds the output size half-to-even."""
+    im_scale = float(scale) / float(min(h0, w0))
+    if np.round(im_scale * max(h0, w0)) > max_size:
+        im_scale = float(max_size) / float(max(h0, w0))
+    return im_scale, int(np.rint(h0 * im_scale)), int(np.rint(w0 * im_scale))
+
+
+def img_preprocessing(orig_img, pixel_means=PIXEL_MEANS, max_size=1000, scale=600):
+    """forward.py:34-45 restated (oracle_c.c orc_preprocess_bgr8): uint8 (h0,w0,3) BGR image ->
+    ((3,H,W) float32, im_scale).  Bit-identical to cv2.resize(float32(img) - means, fx, fy, INTER_LINEAR)."""
+    img = np.ascontiguousarray(orig_img, dtype=np.uint8)
+    h0, w0, _ = img.shape
+    im_scale, H, W = preprocess_plan(h0, w0, scale, max_size)
+    out = np.empty((3, H, W), dtype=f32)
+    m = np.ascontiguousarray(np.asarray(pixel_means, dtype=np.float64).reshape(-1)[:3])
+    _lib().orc_preprocess_bgr8(img.ctypes.data_as(ctypes.c_void_p), h0, w0, m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                               im_scale, im_scale, H, W, _fp(out))
+    return out, im_scale
 
 
 def make_image(h=600, w=1000, seed=0):

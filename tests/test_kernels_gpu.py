@@ -393,3 +393,31 @@ def test_detect_per_class_nms(ops):
         want = orc.cpu_nms(dets, 0.3)
         assert keep_idx[c - 1, :keep_count[c - 1]].tolist() == want
         assert conf_count[c - 1] == int((dets[want, 4] >= 0.3).sum())
+
+
+# ------------------------------------------------------------------------------- caller-side preprocessing ("next" row)
+@pytest.mark.parametrize("shape", [(375, 500), (333, 500), (720, 1280), (600, 600), (97, 211)])
+def test_preprocess_bgr8_bit_exact_vs_oracle(ops, shape):
+    from frcnn_b200 import preprocess
+    rng = np.random.default_rng(shape[0])
+    img = rng.integers(0, 256, (shape[0], shape[1], 3), dtype=np.uint8)
+    want, s = orc.img_preprocessing(img)
+    got, s2 = preprocess.img_preprocessing(img)
+    assert s2 == s and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_detections_assembly_matches_forward_py_loop(ops):
+    from frcnn_b200 import preprocess
+    rng = np.random.default_rng(31)
+    R, NC = 120, 21
+    logits = rng.standard_normal((R, NC)) * 4
+    prob = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(f32)
+    boxes = (np.tile(gi._clustered_dets(R, 9, ncl=6)[:, :4], (1, NC)) + rng.standard_normal((R, 4 * NC)) * 2).astype(f32)
+    got = preprocess.detections(dev(prob), dev(boxes), 1.6, nms_thresh=0.3, conf=0.5)
+    want = []
+    for c, keep, dets in orc.detect(prob, boxes, 0.3, 0.5):                 # forward.py:50-57
+        for d in dets:
+            x1, y1, x2, y2 = map(int, d[:4] / 1.6)                           # forward.py:58
+            want.append((c, x1, y1, x2, y2, float(d[4])))
+    assert got == want and len(got) > 0
