@@ -370,7 +370,7 @@ def run_b200_arm(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "mode": "StreamRunner: pinned host image H2D + graph + D2H of (prob, boxes, count) every step, "
-                        "depth-2 pipeline (copy of image i+1 overlaps compute of image i)",
+                        "ring of %d slots on two streams (H2D of later images overlaps earlier graphs)" % runner.depth,
                 "latency_ms_one_image_serial": e2e_serial_ms,
                 "raw_uint8_input": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
                                     "note": "375x625 uint8 BGR in, preprocessing (mean-sub + bilinear resize) on device"}},

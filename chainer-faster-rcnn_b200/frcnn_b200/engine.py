@@ -210,63 +210,66 @@ class ForwardPlan(object):
 
 
 class StreamRunner(object):
-    """Host-to-host streaming front end of a ForwardPlan: images come from (pinned) HOST memory and
-    results go back to pinned HOST memory, every image.  Depth-2 pipeline on two CUDA streams: the H2D
-    copy of image i+1 runs on the copy stream while image i's graph runs on the compute stream; the
-    D2H of (prob, boxes, count) is queued behind the graph.  Nothing is skipped per image -- the copies
-    are overlapped, not removed -- so the steady-state rate is max(H2D, graph), not their sum."""
+    """Host-to-host streaming front end of a ForwardPlan: images come from (pinned) HOST memory and results go
+    back to pinned HOST memory, for every image.  A ring of `depth` slots on two CUDA streams: the H2D copy of a
+    later image runs on the copy stream while earlier images' graphs run on the compute stream; the D2H of
+    (prob, boxes, count) is queued behind each graph.  Nothing is skipped per image -- the copies are overlapped,
+    not removed -- so the steady-state rate is max(H2D, graph), not their sum.  The host only blocks when it
+    reuses a slot (image i waits for image i-depth), so a stalled driver call (some hosts block cudaMemcpyAsync
+    for tens of ms) does not drain the GPU queue."""
 
-    def __init__(self, plan, src_hw=None, pixel_means=None):
+    def __init__(self, plan, src_hw=None, pixel_means=None, depth=8):
         """src_hw=None: host images are the preprocessed (3,H,W) float32 tensors forward.py uploads.
         src_hw=(h0,w0): host images are RAW uint8 (h0,w0,3) BGR images; mean subtraction + bilinear resize run
         on the device (frcnn_preprocess_bgr8) -- 4x+ fewer H2D bytes."""
-        import torch
         self.plan = plan
         dev = plan.x_in.device
+        self.depth = D = max(2, int(depth))
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.src_hw, self.pixel_means = src_hw, pixel_means
         if src_hw is None:
-            self.stage = [torch.empty_like(plan.x_in) for _ in range(2)]
+            self.stage = [torch.empty_like(plan.x_in) for _ in range(D)]
         else:
             from . import preprocess
             s, H, W = preprocess.plan_size(src_hw[0], src_hw[1])
             if (H, W) != (plan.H, plan.W):
                 raise FrcnnError("source %s resizes to %s, but the plan is for %s" % (src_hw, (H, W), (plan.H, plan.W)))
-            self.stage = [torch.empty((src_hw[0], src_hw[1], 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
-        self.step_done = [torch.cuda.Event() for _ in range(2)]
+            self.stage = [torch.empty((src_hw[0], src_hw[1], 3), dtype=torch.uint8, device=dev) for _ in range(D)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(D)]
+        self.step_done = [torch.cuda.Event() for _ in range(D)]
         nc = plan.w.num_classes
         self.res = [dict(prob=torch.empty((plan.post_n, nc), dtype=torch.float32).pin_memory(),
                          boxes=torch.empty((plan.post_n, 4 * nc), dtype=torch.float32).pin_memory(),
-                         count=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+                         count=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(D)]
         self.h2d_bytes = self.stage[0].numel() * self.stage[0].element_size()
         self.d2h_bytes = (plan.post_n * nc + plan.post_n * 4 * nc) * 4 + 4
         if plan.graph is None:
             plan.forward(None)                       # capture outside the stream loop
 
-    def _prefetch(self, host_img, slot, after=None):
-        import torch
-        with torch.cuda.stream(self.copy_stream):
-            if after is not None:
-                self.copy_stream.wait_event(after)   # the previous user of this staging slot has consumed it
-            self.stage[slot].copy_(host_img, non_blocking=True)
-            self.h2d_done[slot].record(self.copy_stream)
+    def _deliver(self, i, counts, on_result):
+        s = i % self.depth
+        self.step_done[s].synchronize()
+        counts.append(int(self.res[s]["count"][0]))
+        if on_result is not None:
+            on_result(i, self.res[s])
 
     def run(self, host_images, on_result=None):
-        """host_images: sequence of pinned (3,H,W) float32 host tensors.  Calls on_result(i, res) with the
-        pinned result dict of image i (valid until image i+2 is submitted).  Returns the proposal counts."""
-        import torch
-        plan, n = self.plan, len(host_images)
+        """host_images: sequence of pinned host tensors ((3,H,W) float32, or (h0,w0,3) uint8 with src_hw).
+        Calls on_result(i, res) in order with the pinned result dict of image i (valid until image i+depth is
+        submitted).  Returns the proposal counts."""
+        plan, n, D = self.plan, len(host_images), self.depth
         cur = torch.cuda.current_stream()
         counts = []
-        if n == 0:
-            return counts
-        self._prefetch(host_images[0], 0)
         for i in range(n):
-            s = i & 1
+            s = i % D
+            if i >= D:
+                self._deliver(i - D, counts, on_result)         # slot reuse: image i-D must be finished and handed over
+            with torch.cuda.stream(self.copy_stream):
+                self.stage[s].copy_(host_images[i], non_blocking=True)          # H2D, overlaps earlier images' graphs
+                self.h2d_done[s].record(self.copy_stream)
             cur.wait_event(self.h2d_done[s])
             if self.src_hw is None:
-                plan.x_in.copy_(self.stage[s], non_blocking=True)       # D2D into the graph's static input
+                plan.x_in.copy_(self.stage[s], non_blocking=True)               # D2D into the graph's static input
             else:
                 from . import preprocess
                 if self.pixel_means is None:
@@ -279,21 +282,10 @@ class StreamRunner(object):
             r["boxes"].copy_(plan.boxes, non_blocking=True)
             r["count"].copy_(plan.prop.count, non_blocking=True)
             self.step_done[s].record(cur)
-            # image i's graph is queued: now feed image i+1 (the H2D call may hold the host thread for the
-            # duration of the copy on some hosts -- it overlaps the GPU work just queued either way)
-            if i + 1 < n:
-                self._prefetch(host_images[i + 1], s ^ 1, after=self.step_done[s ^ 1] if i >= 1 else None)
-            if i >= 1:                                                   # hand image i-1's result to the host
-                self.step_done[s ^ 1].synchronize()
-                counts.append(int(self.res[s ^ 1]["count"][0]))
-                if on_result is not None:
-                    on_result(i - 1, self.res[s ^ 1])
-        last = (n - 1) & 1
-        self.step_done[last].synchronize()
-        counts.append(int(self.res[last]["count"][0]))
-        if on_result is not None:
-            on_result(n - 1, self.res[last])
+        for i in range(max(0, n - D), n):
+            self._deliver(i, counts, on_result)
         return counts
+
 
 
 class Engine(object):
