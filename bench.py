@@ -93,9 +93,13 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------- CPU (reference-equivalent) arm
-def cpu_pipeline_once(orc, params, x, info, ref_nms=None):
-    """One image through the reference-equivalent CPU path.  Returns (seconds, nms_seconds)."""
+def cpu_pipeline_once(orc, params, x, info, ref_nms=None, raw=None):
+    """One image through the reference-equivalent CPU path.  Returns (seconds, nms_seconds).
+    raw: optional uint8 (h0,w0,3) BGR image -- then forward.py's img_preprocessing (34-45) is part of the timed work
+    and replaces `x`, like the B200 arm's e2e."""
     t0 = time.perf_counter()
+    if raw is not None:
+        x = orc.img_preprocessing(raw)[0][None]
     if ref_nms is not None:
         saved = orc.cpu_nms
         tn = [0.0]
@@ -124,26 +128,49 @@ def cpu_pipeline_once(orc, params, x, info, ref_nms=None):
     return time.perf_counter() - t0, tn[0]
 
 
+def pick_cpu_threads(torch):
+    """Give the CPU arm its best case: time one mid-trunk 3x3 convolution at a few intra-op thread counts and keep the
+    fastest (all hardware threads is often NOT the fastest for torch-CPU on a many-core host)."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16) if 1 <= c <= cores}, reverse=True)
+    x = torch.randn(1, 256, 150, 250)
+    w = torch.randn(256, 256, 3, 3)
+    best, best_t = cores, None
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(x, w, padding=1)
+        t = None
+        for _ in range(5):
+            t0 = time.perf_counter()
+            torch.nn.functional.conv2d(x, w, padding=1)
+            dt = time.perf_counter() - t0
+            t = dt if t is None else min(t, dt)
+        if best_t is None or t < 0.9 * best_t:          # fewer threads only when clearly (>10%) faster
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     import torch
     import frcnn_oracle as orc
     import build_ref
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads(torch)
     ref_nms = build_ref.load()
     params = orc.make_params(seed=1234)
-    x = orc.make_image(H_IMG, W_IMG, seed=0)
+    x = None
+    raw = np.random.default_rng(7).integers(0, 256, (375, 625, 3), dtype=np.uint8)     # resizes to 600x1000
     info = np.array([[H_IMG, W_IMG]], np.int32)
     for _ in range(max(1, min(args.warmup, 1))):
-        t_probe, _ = cpu_pipeline_once(orc, params, x, info, ref_nms)
+        t_probe, _ = cpu_pipeline_once(orc, params, x, info, ref_nms, raw=raw)
     steps = args.steps
     if t_probe * steps > 240.0:                 # keep the whole run within a few minutes
         steps = max(1, int(240.0 / t_probe))
     ts, tn = [], []
     for _ in range(steps):
-        a, b = cpu_pipeline_once(orc, params, x, info, ref_nms)
+        a, b = cpu_pipeline_once(orc, params, x, info, ref_nms, raw=raw)
         ts.append(a)
         tn.append(b)
     total = sum(ts)
@@ -157,8 +184,8 @@ def run_reference_arm(args, rank):
         "config": {"workload": "VGG16 Faster R-CNN forward, synthetic 600x1000, 300 proposals (config #2)",
                    "device": "host CPU", "requested_steps": args.steps},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
-                         "sample": "%d whole image(s), 600x1000; dense ops torch-CPU fp32 (Chainer not installable "
-                                   "offline), NMS = %s; NMS share %.1f%%" %
+                         "sample": "%d whole image(s): raw uint8 375x625 -> preprocessing -> 600x1000 forward -> per-class "
+                                   "NMS; dense ops torch-CPU fp32 (Chainer not installable offline), NMS = %s; NMS share %.1f%%" %
                                    (steps, "reference cpu_nms.pyx (oracle/_ref)" if ref_nms is not None else "C port",
                                     100.0 * sum(tn) / total)},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -343,16 +370,15 @@ def run_b200_arm(args, rank, local_rank, world):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         import build_ref
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        cores = pick_cpu_threads(torch)
         ref_nms = build_ref.load()
-        x = orc.make_image(H_IMG, W_IMG, seed=0)
+        raw0 = np.random.default_rng(7).integers(0, 256, (375, 625, 3), dtype=np.uint8)
         info = np.array([[H_IMG, W_IMG]], np.int32)
-        cpu_pipeline_once(orc, params, x, info, ref_nms)          # warm-up
-        tt, tn = cpu_pipeline_once(orc, params, x, info, ref_nms)
+        cpu_pipeline_once(orc, params, None, info, ref_nms, raw=raw0)          # warm-up
+        tt, tn = cpu_pipeline_once(orc, params, None, info, ref_nms, raw=raw0)
         cpu_baseline = {"value": 1.0 / tt, "unit": "images/s", "cores": cores,
                         "kind": "reference" if ref_nms is not None else "port",
-                        "sample": "1 whole image 600x1000 after 1 warm-up (%.2f s, NMS %.2f s); dense ops torch-CPU fp32 "
+                        "sample": "1 whole image (raw 375x625 -> 600x1000) after 1 warm-up (%.2f s, NMS %.2f s); dense ops torch-CPU fp32 "
                                   "stand-in for Chainer, NMS = %s" %
                                   (tt, tn, "reference cpu_nms.pyx" if ref_nms is not None else "C port of cpu_nms.pyx")}
 
@@ -368,13 +394,17 @@ def run_b200_arm(args, rank, local_rank, world):
                    "l2": "per-step working set (activations+weights ~1.5 GB) exceeds the 126 MB L2; 4 input images rotated",
                    "cuda_graph": True, "frac_of_conv_roofline": (value / world) * CONV_STACK_GFLOP / 1e3 / peak_tf},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "mode": "StreamRunner: pinned host image H2D + graph + D2H of (prob, boxes, count) every step, "
-                        "ring of %d slots on two streams (H2D of later images overlaps earlier graphs)" % runner.depth,
-                "latency_ms_one_image_serial": e2e_serial_ms,
-                "raw_uint8_input": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
-                                    "note": "375x625 uint8 BGR in, preprocessing (mean-sub + bilinear resize) on device"}},
-        "gpu_launches": plan.n_launches * args.steps,
+        # headline e2e = the public streaming call fed with what a caller actually has: the decoded RAW image.
+        # Every step: H2D of a pinned uint8 375x625 BGR image, device preprocessing (forward.py:34-45: mean-sub +
+        # OpenCV-compatible bilinear resize to 600x1000), the whole graph, D2H of (prob, boxes, count).
+        "e2e": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes, "d2h_bytes_per_step": d2h,
+                "mode": "StreamRunner(src_hw=(375,625)): pinned RAW uint8 image H2D + device preprocessing + graph + D2H "
+                        "of (prob, boxes, count) every step; ring of %d slots on two streams" % runner8.depth,
+                "float32_chw_input": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                                      "note": "the reference's model-input interface: the already preprocessed "
+                                              "(3,600,1000) float32 tensor is uploaded every step (7.2 MB)"},
+                "latency_ms_one_image_serial_float32_input": e2e_serial_ms},
+        "gpu_launches": (plan.n_launches + 1) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
