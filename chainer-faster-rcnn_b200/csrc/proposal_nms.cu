@@ -8,13 +8,15 @@
 // contraction), in the reference's operation order, so results are bit-identical to the CPU oracle.
 // These are HBM/latency-bound integer/float kernels -- no tensor cores by design.
 //
-// Pipeline (4 launches, no host sync, data-dependent counts stay on device):
+// Pipeline (5 launches, no host sync, data-dependent counts stay on device):
 //   1. rpn_decode_kernel   one thread per anchor: [2A-way softmax ->] fg score, anchor from index,
 //                          decode + clip + min-size test -> box[i], score[i], sort key[i] (0 = filtered)
 //   2. topk_sort_kernel    ONE CTA: 4-pass radix select of the pre_nms_top_n-th key, order-preserving
-//                          compaction, bitonic sort of (key desc, index asc) in shared memory, gather
-//   3. nms_mask_kernel     upper-triangular 64x64 IoU tiles -> uint64 suppression bitmask
-//   4. nms_scan_kernel     ONE CTA walks the mask (device-side; the reference copies it to the host,
+//                          compaction of the survivors' (key | ~index) composites
+//   3. rank_scatter_kernel chip-wide rank-by-counting of the unique composites = argsort(key desc, index
+//                          asc); scatters box / score / index to the sorted position
+//   4. nms_mask_kernel     upper-triangular 64x64 IoU tiles -> uint64 suppression bitmask
+//   5. nms_scan_kernel     ONE CTA walks the mask (device-side; the reference copies it to the host,
 //                          nms_kernel.cu:124-139), stops at post_nms_top_n, gathers the output rows
 #include "common.cuh"
 

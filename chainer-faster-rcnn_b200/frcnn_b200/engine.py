@@ -2,7 +2,9 @@
 
 Mirrors FasterRCNN.__call__ (inference branch, /root/reference models/faster_rcnn.py:92-134,175-178):
 
-    trunk (models/vgg16.py:38-82)            13x frcnn_conv2d(3x3)+ReLU, 4x frcnn_maxpool2x2_ceil
+    input                                    frcnn_pack_image_im2col3x3 (float CHW) or frcnn_preprocess_bgr8 (raw uint8)
+    trunk (models/vgg16.py:38-82)            13x frcnn_conv2d(3x3)+ReLU (first layer = K=32 GEMM over the im2col image),
+                                             the 4 ceil-mode 2x2 max-pools fused into the producing conv's epilogue
     RPN   (models/region_proposal_network.py:117-124)
                                              frcnn_conv2d(3x3)+ReLU, ONE frcnn_conv2d(1x1) for the twin
                                              heads (18 cls + 36 bbox -> fp32 [H*W, 64])
