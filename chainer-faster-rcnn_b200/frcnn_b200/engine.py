@@ -90,6 +90,9 @@ class ForwardPlan(object):
                  anchors=None, with_detect=False, det_nms_thresh=0.3, det_conf=0.8, use_graph=True, keep_rpn_debug=False,
                  fuse_pool=True):
         self.w, self.H, self.W = weights, H, W
+        self._ctor = dict(pre_n=pre_n, post_n=post_n, nms_thresh=nms_thresh, min_size=min_size, feat_stride=feat_stride,
+                          anchors=anchors, with_detect=with_detect, det_nms_thresh=det_nms_thresh, det_conf=det_conf,
+                          use_graph=use_graph, keep_rpn_debug=keep_rpn_debug, fuse_pool=fuse_pool)
         dev = weights.device
         x3 = weights.precision == "bf16x3"
         self.pre_n, self.post_n, self.nms_thresh, self.min_size, self.feat_stride = pre_n, post_n, nms_thresh, min_size, feat_stride
@@ -185,6 +188,12 @@ class ForwardPlan(object):
             n += 1
         self.n_launches = n
 
+    def clone(self):
+        """A second set of buffers (and its own graph) over the SAME packed weights: lets another image be in flight."""
+        p = ForwardPlan(self.w, self.H, self.W, **self._ctor)
+        p.set_clip(self.im_h, self.im_w)
+        return p
+
     def set_clip(self, im_h, im_w):
         """img_info as the caller passes it (forward.py:93 passes (H, H)).  Changing it
         invalidates a captured graph (the bounds are kernel arguments)."""
@@ -211,6 +220,48 @@ class ForwardPlan(object):
         return self.prob, self.boxes, self.prop.count
 
 
+class LanePool(object):
+    """`lanes` independent images in flight on one GPU: one ForwardPlan (buffers + CUDA graph) and one CUDA stream
+    per lane over shared weights.  The reference processes one image per call (batch hard-wired to 1, SURVEY.md
+    Q10); images are independent, so a second/third image's tensor-core layers fill the SMs that image one's
+    single-CTA steps (radix select, NMS scan) and ragged last waves leave idle.  Each image still runs the whole
+    path; nothing is batched or skipped, and results are bit-identical to the single-lane run (tests)."""
+
+    def __init__(self, plan, lanes=3):
+        self.plans = [plan] + [plan.clone() for _ in range(max(1, int(lanes)) - 1)]
+        dev = plan.x_in.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.plans]
+        for p, st in zip(self.plans, self.streams):
+            if p.use_graph and p.graph is None:
+                with torch.cuda.stream(st):
+                    p.forward(None)
+        torch.cuda.synchronize(dev)
+
+    def __len__(self):
+        return len(self.plans)
+
+    def fork(self):
+        """Lane streams start after everything queued so far on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        for st in self.streams:
+            st.wait_event(ev)
+
+    def submit(self, i, x_chw=None):
+        """Queue image number i on lane i % lanes.  Returns that lane's plan (its outputs are valid once the lane's
+        stream reaches this point; the next image on the same lane overwrites them)."""
+        k = i % len(self.plans)
+        with torch.cuda.stream(self.streams[k]):
+            self.plans[k].forward(x_chw)
+        return self.plans[k]
+
+    def join(self):
+        """The current stream waits for every lane."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            cur.wait_stream(st)
+
+
 class StreamRunner(object):
     """Host-to-host streaming front end of a ForwardPlan: images come from (pinned) HOST memory and results go
     back to pinned HOST memory, for every image.  A ring of `depth` slots on two CUDA streams: the H2D copy of a
@@ -220,13 +271,15 @@ class StreamRunner(object):
     reuses a slot (image i waits for image i-depth), so a stalled driver call (some hosts block cudaMemcpyAsync
     for tens of ms) does not drain the GPU queue."""
 
-    def __init__(self, plan, src_hw=None, pixel_means=None, depth=8):
-        """src_hw=None: host images are the preprocessed (3,H,W) float32 tensors forward.py uploads.
+    def __init__(self, plan, src_hw=None, pixel_means=None, depth=8, lanes=1):
+        """lanes: images in flight on the compute side (LanePool; lane = image index % lanes).
+        src_hw=None: host images are the preprocessed (3,H,W) float32 tensors forward.py uploads.
         src_hw=(h0,w0): host images are RAW uint8 (h0,w0,3) BGR images; mean subtraction + bilinear resize run
         on the device (frcnn_preprocess_bgr8) -- 4x+ fewer H2D bytes."""
-        self.plan = plan
+        self.pool = plan if isinstance(plan, LanePool) else LanePool(plan, lanes)
+        self.plan = plan = self.pool.plans[0]
         dev = plan.x_in.device
-        self.depth = D = max(2, int(depth))
+        self.depth = D = max(2, int(depth), 2 * len(self.pool))
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.src_hw, self.pixel_means = src_hw, pixel_means
         if src_hw is None:
@@ -245,8 +298,6 @@ class StreamRunner(object):
                          count=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(D)]
         self.h2d_bytes = self.stage[0].numel() * self.stage[0].element_size()
         self.d2h_bytes = (plan.post_n * nc + plan.post_n * 4 * nc) * 4 + 4
-        if plan.graph is None:
-            plan.forward(None)                       # capture outside the stream loop
 
     def _deliver(self, i, counts, on_result):
         s = i % self.depth
@@ -259,33 +310,36 @@ class StreamRunner(object):
         """host_images: sequence of pinned host tensors ((3,H,W) float32, or (h0,w0,3) uint8 with src_hw).
         Calls on_result(i, res) in order with the pinned result dict of image i (valid until image i+depth is
         submitted).  Returns the proposal counts."""
-        plan, n, D = self.plan, len(host_images), self.depth
-        cur = torch.cuda.current_stream()
+        n, D, L = len(host_images), self.depth, len(self.pool)
+        self.pool.fork()
         counts = []
         for i in range(n):
             s = i % D
+            plan, cur = self.pool.plans[i % L], self.pool.streams[i % L]
             if i >= D:
                 self._deliver(i - D, counts, on_result)         # slot reuse: image i-D must be finished and handed over
             with torch.cuda.stream(self.copy_stream):
                 self.stage[s].copy_(host_images[i], non_blocking=True)          # H2D, overlaps earlier images' graphs
                 self.h2d_done[s].record(self.copy_stream)
-            cur.wait_event(self.h2d_done[s])
-            if self.src_hw is None:
-                plan.x_in.copy_(self.stage[s], non_blocking=True)               # D2D into the graph's static input
-            else:
-                from . import preprocess
-                if self.pixel_means is None:
-                    preprocess.img_preprocessing(self.stage[s], out=plan.x_in)
+            with torch.cuda.stream(cur):
+                cur.wait_event(self.h2d_done[s])
+                if self.src_hw is None:
+                    plan.x_in.copy_(self.stage[s], non_blocking=True)           # D2D into the graph's static input
                 else:
-                    preprocess.img_preprocessing(self.stage[s], self.pixel_means, out=plan.x_in)
-            plan.graph.replay()
-            r = self.res[s]
-            r["prob"].copy_(plan.prob, non_blocking=True)
-            r["boxes"].copy_(plan.boxes, non_blocking=True)
-            r["count"].copy_(plan.prop.count, non_blocking=True)
-            self.step_done[s].record(cur)
+                    from . import preprocess
+                    if self.pixel_means is None:
+                        preprocess.img_preprocessing(self.stage[s], out=plan.x_in)
+                    else:
+                        preprocess.img_preprocessing(self.stage[s], self.pixel_means, out=plan.x_in)
+                plan.forward(None)
+                r = self.res[s]
+                r["prob"].copy_(plan.prob, non_blocking=True)
+                r["boxes"].copy_(plan.boxes, non_blocking=True)
+                r["count"].copy_(plan.prop.count, non_blocking=True)
+                self.step_done[s].record(cur)
         for i in range(max(0, n - D), n):
             self._deliver(i, counts, on_result)
+        self.pool.join()
         return counts
 
 

@@ -157,6 +157,38 @@ def test_stream_runner_host_to_host_matches_direct_forward(params):
         assert c == wc and torch.equal(p, wp) and torch.equal(b, wb)
 
 
+def test_lanes_in_flight_are_bit_identical_to_single_lane(params):
+    """3 images in flight on 3 streams (LanePool) and the lane-aware StreamRunner return, per image, exactly the
+    single-lane result (no cross-lane state: the library keeps none, each lane has its own buffers and graph)."""
+    from frcnn_b200.engine import LanePool, StreamRunner
+    H, W = 96, 128
+    eng = _engine(params, "bf16x3")
+    plan = eng.plan(H, W)
+    imgs = [torch.from_numpy(orc.make_image(H, W, seed=40 + i)[0]).pin_memory() for i in range(7)]
+    dev = [im.cuda() for im in imgs]
+    want = []
+    for im in dev:
+        p, b, c = plan.forward(im)
+        torch.cuda.synchronize()
+        want.append((p.cpu().clone(), b.cpu().clone(), int(c.item())))
+    pool = LanePool(plan, lanes=3)
+    assert len(pool) == 3 and pool.plans[0] is plan
+    for rnd in range(0, 7, 3):                       # one round = one image per lane, then read the lanes back
+        pool.fork()
+        used = [(i, pool.submit(i, dev[i])) for i in range(rnd, min(rnd + 3, 7))]
+        pool.join()
+        torch.cuda.synchronize()
+        for i, pl in used:
+            assert int(pl.prop.count.item()) == want[i][2]
+            assert torch.equal(pl.prob.cpu(), want[i][0]) and torch.equal(pl.boxes.cpu(), want[i][1])
+    got = []
+    runner = StreamRunner(pool, depth=4)
+    counts = runner.run(imgs, on_result=lambda i, r: got.append((i, r["prob"].clone(), r["boxes"].clone())))
+    assert counts == [w[2] for w in want] and [g[0] for g in got] == list(range(7))
+    for (i, p, b), (wp, wb, wc) in zip(got, want):
+        assert torch.equal(p, wp) and torch.equal(b, wb)
+
+
 def test_bf16_fast_mode_runs_and_is_close(params):
     """Single-pass bf16: same graph, lo planes absent.  Not the parity mode -- only sanity-checked."""
     H, W = 96, 128
