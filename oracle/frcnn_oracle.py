@@ -15,7 +15,9 @@ Parity status
 * PINNED against the reference itself (tests/golden, made by
   tests/golden/make_golden.py which imports the reference's own modules and its
   compiled cpu_nms.pyx): generate_anchors, _generate_all_bbox,
-  bbox_transform_inv, clip_boxes, filter_boxes, cpu_nms, ProposalLayer.__call__.
+  bbox_transform_inv, clip_boxes, filter_boxes, cpu_nms, ProposalLayer.__call__,
+  and (training path) bbox_overlaps (compiled bbox.pyx), keep_inside, bbox_transform,
+  AnchorTargetLayer.__call__ (same np.random seed -> identical labels / targets).
 * UNPINNED ("parity unpinned", no reference test or golden vector exists and
   Chainer cannot be installed): conv / linear / max-pool / softmax / roi-pool.
   Those follow the published Chainer-v1 / Caffe semantics and are cross-checked
@@ -203,6 +205,139 @@ def bbox_overlaps(boxes, query):
     _lib().orc_bbox_overlaps(b.ctypes.data_as(dp), b.shape[0], q.ctypes.data_as(dp), q.shape[0],
                              out.ctypes.data_as(dp))
     return out
+
+
+# --------------------------------------------------------------------------- AnchorTargetLayer + RPN losses (training, "next")
+RPN_NEGATIVE_OVERLAP, RPN_POSITIVE_OVERLAP = 0.3, 0.7      # models/anchor_target_layer.py:44-45
+RPN_FG_FRACTION, RPN_BATCHSIZE = 0.5, 256                  # :46-47
+
+
+def all_anchor_boxes_f64(feat_h, feat_w, feat_stride, anchors):
+    """ProposalLayer._generate_all_bbox (models/proposal_layer.py:207-221) WITHOUT the float32 cast: that is what
+    AnchorTargetLayer uses (anchor_target_layer.py:108) -- the whole target computation runs in float64."""
+    A = len(anchors)
+    sx = np.arange(feat_w, dtype=np.int64) * feat_stride
+    sy = np.arange(feat_h, dtype=np.int64) * feat_stride
+    gx, gy = np.meshgrid(sx, sy)
+    shifts = np.stack([gx.ravel(), gy.ravel(), gx.ravel(), gy.ravel()], axis=1)
+    return (np.asarray(anchors, np.float64).reshape(1, A, 4) + shifts.reshape(-1, 1, 4)).reshape(-1, 4)
+
+
+def bbox_transform(ex_rois, gt_rois):
+    """models/bbox_transform.py:18-38 (dtype follows the inputs: float64 anchors x float32 gt -> float64)."""
+    ex_w = ex_rois[:, 2] - ex_rois[:, 0] + 1.0
+    ex_h = ex_rois[:, 3] - ex_rois[:, 1] + 1.0
+    ex_cx = ex_rois[:, 0] + 0.5 * ex_w
+    ex_cy = ex_rois[:, 1] + 0.5 * ex_h
+    gt_w = gt_rois[:, 2] - gt_rois[:, 0] + 1.0
+    gt_h = gt_rois[:, 3] - gt_rois[:, 1] + 1.0
+    gt_cx = gt_rois[:, 0] + 0.5 * gt_w
+    gt_cy = gt_rois[:, 1] + 0.5 * gt_h
+    return np.vstack(((gt_cx - ex_cx) / ex_w, (gt_cy - ex_cy) / ex_h, np.log(gt_w / ex_w), np.log(gt_h / ex_h))).transpose()
+
+
+def anchor_target_layer(feat_h, feat_w, gt_boxes, img_info, anchors=None, feat_stride=16, choice=None):
+    """AnchorTargetLayer.__call__ (models/anchor_target_layer.py:66-120) with _create_bbox_labels (:122-173) and
+    _calc_overlaps (:175-198).  gt_boxes (1,G,5) float32, img_info (1,2) int [h, w].
+
+    choice(inds, size) picks the indices to disable; default = the reference's own np.random.choice(..., replace=False)
+    on the global NumPy RNG (:153-156,164-167), so `np.random.seed(s)` before the call reproduces the reference run.
+    Returns a dict: labels int32 [n_inside], targets float32 [n_inside,4], inds_inside, n_all, and the intermediate
+    values the device path is checked against (labels_before_subsample, max_overlaps, argmax, fg_disable, bg_disable)."""
+    if anchors is None:
+        anchors = generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+    if choice is None:
+        choice = lambda inds, size: np.random.choice(inds, size=size, replace=False)     # noqa: E731
+    gt = np.asarray(gt_boxes)[0]
+    info = np.asarray(img_info)[0]
+    all_bbox = all_anchor_boxes_f64(feat_h, feat_w, feat_stride, anchors)                # :108
+    inds_inside, inside = keep_inside(all_bbox, info)                                    # :109
+    overlaps = bbox_overlaps(inside, gt[:, :4])                                          # :181-185 (float64)
+    argmax = overlaps.argmax(axis=1)                                                     # :189
+    gt_argmax = overlaps.argmax(axis=0)                                                  # :190
+    max_ov = overlaps[np.arange(len(inds_inside)), argmax]                               # :192-193
+    gt_max = overlaps[gt_argmax, np.arange(overlaps.shape[1])]                           # :194-195
+    gt_argmax_rows = np.where(overlaps == gt_max)[0]                                     # :196 (every tie; all rows if 0)
+    labels = np.ones((len(inds_inside),), dtype=np.int32) * -1                           # :131
+    labels[max_ov < RPN_NEGATIVE_OVERLAP] = 0                                            # :137
+    labels[gt_argmax_rows] = 1                                                           # :140
+    labels[max_ov >= RPN_POSITIVE_OVERLAP] = 1                                           # :143
+    labels[max_ov < RPN_NEGATIVE_OVERLAP] = 0                                            # :146 (bg clobbers positives)
+    before = labels.copy()
+    num_fg = int(RPN_FG_FRACTION * RPN_BATCHSIZE)                                        # :149
+    fg_inds = np.where(labels == 1)[0]
+    fg_disable = np.zeros((0,), np.int64)
+    if len(fg_inds) > num_fg:                                                            # :151-157
+        fg_disable = np.asarray(choice(fg_inds, int(len(fg_inds) - num_fg)), dtype=np.int64)
+        labels[fg_disable] = -1
+    num_bg = RPN_BATCHSIZE - np.sum(labels == 1)                                         # :160
+    bg_inds = np.where(labels == 0)[0]
+    bg_disable = np.zeros((0,), np.int64)
+    if len(bg_inds) > num_bg:                                                            # :162-168
+        bg_disable = np.asarray(choice(bg_inds, int(len(bg_inds) - num_bg)), dtype=np.int64)
+        labels[bg_disable] = -1
+    targets = bbox_transform(inside, gt[argmax]).astype(f32)                             # :115-117
+    return dict(labels=labels, targets=targets, inds_inside=inds_inside, n_all=len(all_bbox),
+                labels_before_subsample=before, max_overlaps=max_ov, argmax=argmax,
+                fg_disable=fg_disable, bg_disable=bg_disable)
+
+
+def rpn_labels_mapped(labels, inds_inside, n_all, A, feat_h, feat_w):
+    """RegionProposalNetwork._calc_rpn_loss_cls, the label map-up (models/region_proposal_network.py:163-172):
+    -> int32 (1, A, H, W), -1 for anchors outside the image."""
+    m = np.ones((n_all,), dtype=np.int32) * -1
+    m[inds_inside] = labels
+    return m.reshape(1, feat_h, feat_w, A).transpose(0, 3, 1, 2)
+
+
+def rpn_loss_cls(rpn_cls_score, labels, inds_inside, n_all, A):
+    """models/region_proposal_network.py:160-181.  F.softmax_cross_entropy over the score reshaped to (1,2,A,H,W) -- a
+    2-way softmax between channel a (bg) and A+a (fg) -- with ignore_label -1, normalised by the number of non-ignored
+    labels (Chainer v1 default normalize=True: coeff = 1/max(count,1)); F.accuracy with ignore_label -1.
+    UNPINNED (Chainer absent): restated from Chainer v1's published semantics, cross-checked against
+    torch.nn.functional.cross_entropy(ignore_index=-1) in the tests.  Returns (loss f32, accuracy f32, dscore f32)."""
+    x = np.asarray(rpn_cls_score, dtype=f32)
+    _, _, H, W = x.shape
+    t = rpn_labels_mapped(labels, inds_inside, n_all, A, H, W)                    # (1,A,H,W)
+    z = x.reshape(1, 2, A, H, W)
+    m = z.max(axis=1, keepdims=True)
+    e = expf(z - m)
+    lse = np.log(e.sum(axis=1, keepdims=True, dtype=f32)).astype(f32) + m
+    logp = (z - lse).astype(f32)                                                  # log_softmax, float32
+    valid = t != -1
+    count = max(int(valid.sum()), 1)
+    tt = np.where(valid, t, 0)
+    picked = np.take_along_axis(logp, tt[:, None], axis=1)[:, 0]
+    loss = f32(-(picked[valid].astype(np.float64).sum()) / count)
+    pred = z.argmax(axis=1)
+    acc = f32((pred[valid] == t[valid]).sum() / count) if valid.any() else f32(0)
+    # d loss / d score = (softmax - onehot) / count on valid anchors, 0 elsewhere
+    p = np.exp(logp.astype(np.float64))
+    g = p.copy()
+    onehot = np.zeros_like(g)
+    np.put_along_axis(onehot, tt[:, None], 1.0, axis=1)
+    g = (g - onehot) * valid[:, None] / count
+    return loss, acc, g.reshape(x.shape).astype(f32)
+
+
+def rpn_loss_bbox(rpn_bbox_pred, targets, inds_inside, A, delta=3.0):
+    """models/region_proposal_network.py:183-204.  NOTE the channel convention of this reshape: (4, A, K) -> channel
+    c = j*A + a holds coordinate j of anchor a (the ProposalLayer reads c = a*4 + j, proposal_layer.py:139) -- restated
+    as written.  F.huber_loss(x, t, delta): 0.5 d^2 if |d| < delta else delta (|d| - 0.5 delta), summed; / n_bbox
+    (ALL anchors, not the inside count).  UNPINNED (Chainer absent).  Returns (loss f32, dpred f32 same shape)."""
+    x = np.asarray(rpn_bbox_pred, dtype=f32)
+    K = x.shape[2] * x.shape[3]
+    p = x.reshape(4, A, K).transpose(2, 1, 0).reshape(-1, 4)                       # (K*A, 4)
+    n_bbox = p.shape[0]
+    d = (p[inds_inside].astype(np.float64) - np.asarray(targets, np.float64))
+    a = np.abs(d)
+    per = np.where(a < delta, 0.5 * d * d, delta * (a - 0.5 * delta))
+    loss = f32(per.sum() / n_bbox)
+    gd = np.where(a < delta, d, delta * np.sign(d)) / n_bbox
+    gp = np.zeros((n_bbox, 4), np.float64)
+    gp[inds_inside] = gd
+    g = gp.reshape(K, A, 4).transpose(2, 1, 0).reshape(x.shape)
+    return loss, g.astype(f32)
 
 
 # --------------------------------------------------------------------------- ProposalLayer

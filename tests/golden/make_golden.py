@@ -140,6 +140,51 @@ def main():
         out[name + "_all_bbox_sum"] = np.float64(layer._generate_all_bbox(prob.shape[2], prob.shape[3]).sum())
         print(name, "rois", rois.shape, "probs", probs.shape)
     np.savez(os.path.join(HERE, "proposal_layer.npz"), **out)
+
+    # ---- 5. training path: bbox_overlaps (compiled bbox.pyx), keep_inside, bbox_transform, AnchorTargetLayer.__call__
+    ref_bbox = build_ref.load_bbox()
+    assert ref_bbox is not None, "reference bbox.pyx could not be built"
+    sys.modules["models.bbox"] = ref_bbox
+    from models import anchor_target_layer as atl
+    out = {}
+    boxes, _ = gi.box_transform_case(500, 1, 21)
+    query, _ = gi.box_transform_case(17, 1, 22)
+    out["overlaps_500x17"] = ref_bbox.bbox_overlaps(np.ascontiguousarray(boxes, dtype=np.float64),
+                                                    np.ascontiguousarray(query, dtype=np.float64))
+    out["overlaps_checksum"] = gi.checksum(boxes, query)
+    ex, _ = gi.box_transform_case(300, 1, 23)
+    gt_, _ = gi.box_transform_case(300, 1, 24)
+    out["bbox_transform_f64xf32"] = bt.bbox_transform(ex.astype(np.float64), gt_)       # the dtype mix AnchorTargetLayer uses
+    out["bbox_transform_checksum"] = gi.checksum(ex, gt_)
+    real_choice = np.random.choice
+    for name in gi.ANCHOR_TARGET_CASES:
+        fh, fw, gt, info, seed = gi.anchor_target_case(name)
+        calls = []
+
+        def recording_choice(a, size=None, replace=True, p=None):
+            r = real_choice(a, size=size, replace=replace, p=p)
+            calls.append((np.asarray(a).copy(), np.asarray(r).copy()))
+            return r
+        np.random.choice = recording_choice
+        try:
+            np.random.seed(seed)
+            layer = atl.AnchorTargetLayer()
+            labels, targets, inds_inside, n_all = layer(fh, fw, Variable(gt), Variable(info))
+        finally:
+            np.random.choice = real_choice
+        out[name + "_labels"] = labels
+        out[name + "_targets"] = targets
+        out[name + "_inds_inside"] = inds_inside
+        out[name + "_n_all"] = np.int64(n_all)
+        # the subsampling draws, in call order: [pool, chosen] (fg first if it happened, then bg)
+        out[name + "_n_choice_calls"] = np.int64(len(calls))
+        for ci, (pool, chosen) in enumerate(calls):
+            out[name + "_choice%d_pool" % ci] = pool
+            out[name + "_choice%d_chosen" % ci] = chosen
+        out[name + "_checksum"] = gi.checksum(gt, info)
+        print(name, "labels", labels.shape, "fg", int((labels == 1).sum()), "bg", int((labels == 0).sum()),
+              "choice calls", len(calls), targets.dtype)
+    np.savez_compressed(os.path.join(HERE, "anchor_target_layer.npz"), **out)
     print("golden vectors written to", HERE)
 
 

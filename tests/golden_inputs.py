@@ -140,3 +140,48 @@ def proposal_case(name, A=9):
     prob[0, A:] = fg.reshape(A, fh, fw)
     assert np.unique(prob[0, A:]).size == n
     return prob, pred, np.array([info], dtype=np.int32), train
+
+
+# --------------------------------------------------------------------------- AnchorTargetLayer (training path)
+ANCHOR_TARGET_CASES = {
+    # name: (feat_h, feat_w, (img_h, img_w), n_gt, kind, seed)
+    "t14_ref_test": (14, 14, (224, 224), 3, "reference_test", 0),   # tests/test_anchor_target_layer.py:18-30
+    "c1_g1": (38, 63, (600, 1000), 1, "random", 1),
+    "c1_g8": (38, 63, (600, 1000), 8, "random", 2),
+    "c1_g40_manyfg": (38, 63, (600, 1000), 40, "anchor_like", 3),   # > 128 positives: fg subsampling runs
+    "c1_g3_outside": (38, 63, (600, 1000), 3, "one_outside", 4),    # a gt no inside anchor overlaps (gt_max == 0 quirk)
+    "c0_g5_square_info": (38, 50, (600, 600), 5, "random", 5),      # img_info (H, H) as forward.py passes it (Q7)
+    "t10_small": (10, 12, (160, 192), 2, "random", 6),               # few inside anchors; bg <= 256: no bg subsampling
+}
+
+
+def anchor_target_case(name):
+    """-> feat_h, feat_w, gt_boxes float32 (1, G, 5) [x1,y1,x2,y2,cls], img_info int32 (1, 2) [h, w], numpy seed."""
+    fh, fw, (ih, iw), g, kind, seed = ANCHOR_TARGET_CASES[name]
+    rng = np.random.default_rng(2000 + seed)
+    if kind == "reference_test":
+        gt = np.array([[10, 10, 60, 200, 0], [50, 100, 210, 210, 1], [160, 40, 200, 70, 2]], dtype=f32)
+    else:
+        if kind == "anchor_like":
+            # boxes shaped like the anchors themselves (128/256/512 px, ratios 0.5/1/2) so many anchors reach IoU 0.7
+            size = rng.choice([128.0, 256.0], size=g)
+            ratio = rng.choice([0.5, 1.0, 2.0], size=g)
+            w = size / np.sqrt(ratio)
+            h = size * np.sqrt(ratio)
+            cx = rng.uniform(w / 2, iw - w / 2)
+            cy = rng.uniform(np.minimum(h / 2, ih / 2), np.maximum(ih - h / 2, ih / 2))
+        else:
+            w = rng.uniform(20, iw * 0.6, size=g)
+            h = rng.uniform(20, ih * 0.6, size=g)
+            cx = rng.uniform(w / 2, iw - w / 2)
+            cy = rng.uniform(h / 2, ih - h / 2)
+        x1 = np.clip(np.floor(cx - w / 2), 0, iw - 2)
+        y1 = np.clip(np.floor(cy - h / 2), 0, ih - 2)
+        x2 = np.clip(np.floor(cx + w / 2), x1 + 1, iw - 1)
+        y2 = np.clip(np.floor(cy + h / 2), y1 + 1, ih - 1)
+        cls = rng.integers(0, 20, size=g)
+        gt = np.stack([x1, y1, x2, y2, cls], axis=1).astype(f32)
+        if kind == "one_outside":
+            gt[1, :4] = [iw + 50, ih + 50, iw + 90, ih + 120]       # beyond every inside anchor
+    info = np.array([[ih, iw]], dtype=np.int32)
+    return fh, fw, gt[None], info, 7000 + seed
