@@ -52,6 +52,15 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     "frcnn_bbox_decode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
+    "frcnn_bbox_overlaps": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "frcnn_anchor_targets_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "frcnn_anchor_targets": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_double,
+                                     c_double, c_int, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_rpn_loss_workspace_bytes": (c_size_t, [c_int]),
+    "frcnn_rpn_loss": (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),

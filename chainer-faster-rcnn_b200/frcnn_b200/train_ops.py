@@ -1,0 +1,110 @@
+"""torch-tensor front end of the RPN-training entry points of the C ABI (include/frcnn_b200.h:
+frcnn_bbox_overlaps, frcnn_anchor_targets, frcnn_rpn_loss).  Like ops.py: device pointers + the current
+stream in, tensors out, no CPU path.
+
+Replaces models/bbox.pyx:16-56, models/anchor_target_layer.py:66-198 and the two loss functions of
+models/region_proposal_network.py:160-204 (all under /root/reference).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import FrcnnError, check
+from .ops import _need_cuda, _p, _stream
+
+RPN_NEGATIVE_OVERLAP, RPN_POSITIVE_OVERLAP = 0.3, 0.7       # models/anchor_target_layer.py:44-45
+RPN_FG_FRACTION, RPN_BATCHSIZE = 0.5, 256                   # :46-47
+SUBSAMPLE_NONE, SUBSAMPLE_DEVICE, SUBSAMPLE_LIST = 0, 1, 2
+
+
+def bbox_overlaps(boxes, query):
+    """boxes [N,4], query [K,4] float64 CUDA tensors -> overlaps [N,K] float64 (bbox.pyx:16-56)."""
+    _need_cuda(boxes, query)
+    b = boxes.contiguous().double()
+    q = query.contiguous().double()
+    if b.ndim != 2 or q.ndim != 2 or b.shape[1] != 4 or q.shape[1] != 4:
+        raise FrcnnError("bbox_overlaps: expected (N,4) and (K,4), got %s and %s" % (tuple(b.shape), tuple(q.shape)))
+    out = torch.zeros((b.shape[0], q.shape[0]), dtype=torch.float64, device=b.device)
+    check(_lib.load().frcnn_bbox_overlaps(_p(b), b.shape[0], _p(q), q.shape[0], _p(out), _stream()), "frcnn_bbox_overlaps")
+    return out
+
+
+class AnchorTargets(object):
+    """Device buffers of one feature-map shape: labels_full [n_all] int32, targets_full [n_all,4] float32,
+    inds_inside [n_all] int32 (first counts[0] valid), counts int32 [8]."""
+
+    def __init__(self, A, H, W, device, max_gt=256):
+        self.shape = (A, H, W)
+        self.n_all = n = A * H * W
+        self.labels_full = torch.empty((n,), dtype=torch.int32, device=device)
+        self.targets_full = torch.empty((n, 4), dtype=torch.float32, device=device)
+        self.inds_inside = torch.empty((n,), dtype=torch.int32, device=device)
+        self.counts = torch.zeros((8,), dtype=torch.int32, device=device)
+        self.max_gt = max_gt
+        lib = _lib.load()
+        self.ws = torch.empty((lib.frcnn_anchor_targets_workspace_bytes(n, max_gt),), dtype=torch.uint8, device=device)
+        self.loss_ws = torch.empty((lib.frcnn_rpn_loss_workspace_bytes(n),), dtype=torch.uint8, device=device)
+        self.losses = torch.zeros((4,), dtype=torch.float32, device=device)
+
+    def compact(self):
+        """The reference's return values (anchor_target_layer.py:120): labels [n_inside], targets [n_inside,4],
+        inds_inside [n_inside], n_all.  One D2H read of the inside count."""
+        n = int(self.counts[0].item())
+        idx = self.inds_inside[:n].long()
+        return self.labels_full[idx], self.targets_full[idx], idx, self.n_all
+
+
+def anchor_targets(anchors, A, H, W, feat_stride, gt_boxes, im_h, im_w, mode=SUBSAMPLE_DEVICE, seed=0, disable_pos=None,
+                   work=None, neg_thr=RPN_NEGATIVE_OVERLAP, pos_thr=RPN_POSITIVE_OVERLAP, batch=RPN_BATCHSIZE,
+                   num_fg=int(RPN_FG_FRACTION * RPN_BATCHSIZE)):
+    """frcnn_anchor_targets.  anchors [A,4] float64 CUDA; gt_boxes [G,5] float32 CUDA.  Returns the AnchorTargets."""
+    _need_cuda(anchors, gt_boxes)
+    gt = gt_boxes.contiguous().float()
+    if gt.ndim != 2 or gt.shape[1] != 5 or gt.shape[0] < 1:
+        raise FrcnnError("anchor_targets: gt_boxes must be (G>=1, 5), got %s" % (tuple(gt.shape),))
+    G = gt.shape[0]
+    if work is None or work.shape != (A, H, W) or work.max_gt < G:
+        work = AnchorTargets(A, H, W, gt.device, max_gt=max(256, G))
+    dp, nd = None, 0
+    if mode == SUBSAMPLE_LIST:
+        dp = (disable_pos if disable_pos is not None else torch.zeros((0,), dtype=torch.int32, device=gt.device))
+        dp = dp.to(device=gt.device, dtype=torch.int32).contiguous()
+        nd = dp.numel()
+    check(_lib.load().frcnn_anchor_targets(
+        _p(anchors), A, H, W, int(feat_stride), _p(gt), G, int(im_h), int(im_w), float(neg_thr), float(pos_thr),
+        int(batch), int(num_fg), int(mode), ctypes.c_ulonglong(int(seed) & (2 ** 64 - 1)), _p(dp) if nd else None, nd,
+        _p(work.labels_full), _p(work.targets_full), _p(work.inds_inside), _p(work.counts), _p(work.ws), work.ws.numel(),
+        _stream()), "frcnn_anchor_targets")
+    return work
+
+
+def rpn_loss(score, bbox, anchors, A, H, W, feat_stride, im_h, im_w, work, delta=3.0, loss_lambda=1.0, grad_scale=1.0,
+             layout="nchw", ld=0, want_grads=True):
+    """frcnn_rpn_loss.  layout "nchw": score (2A,H,W), bbox (4A,H,W) planar float32 (the reference's);
+    layout "nhwc": ONE float32 matrix [H*W, ld] (score in columns [0,2A), bbox in [2A,6A)) passed as `score`.
+    Returns (losses float32[4] = cls, bbox, accuracy, total; dscore; dbbox) -- gradients in the inputs' layout
+    (for "nhwc" a single [H*W, ld] matrix, returned as dscore, dbbox None)."""
+    _need_cuda(score, bbox)
+    if layout == "nchw":
+        score = score.contiguous().float()
+        bbox = bbox.contiguous().float()
+        cs, ps, bcs, bps = H * W, 1, H * W, 1
+        bbox_ptr = _p(bbox)
+        ds = torch.empty_like(score) if want_grads else None
+        db = torch.empty_like(bbox) if want_grads else None
+        ds_ptr, db_ptr = _p(ds), _p(db)
+    else:
+        if score.dtype != torch.float32 or not score.is_contiguous() or score.shape != (H * W, ld):
+            raise FrcnnError("rpn_loss: nhwc layout needs a contiguous float32 [H*W, ld] matrix")
+        cs, ps, bcs, bps = 1, ld, 1, ld
+        bbox_ptr = ctypes.c_void_p(score.data_ptr() + 4 * 2 * A)
+        ds = torch.zeros_like(score) if want_grads else None           # pad columns stay zero
+        db = None
+        ds_ptr = _p(ds)
+        db_ptr = ctypes.c_void_p(ds.data_ptr() + 4 * 2 * A) if want_grads else None
+    check(_lib.load().frcnn_rpn_loss(_p(score), cs, ps, bbox_ptr, bcs, bps, _p(anchors), A, H, W, int(feat_stride),
+                                     int(im_h), int(im_w), _p(work.labels_full), _p(work.targets_full), _p(work.counts),
+                                     float(delta), float(loss_lambda), float(grad_scale), _p(work.losses), ds_ptr, db_ptr,
+                                     _p(work.loss_ws), work.loss_ws.numel(), _stream()), "frcnn_rpn_loss")
+    return work.losses, ds, db

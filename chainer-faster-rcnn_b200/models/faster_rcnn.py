@@ -6,8 +6,9 @@ signature as /root/reference models/faster_rcnn.py:19-178, inference branch (:92
 The whole graph (trunk -> RPN -> ProposalLayer -> RoI pool -> fc6/fc7 -> cls/bbox -> softmax/decode/
 clip) is frcnn_b200.engine: hand-written sm_100a kernels behind the C ABI, replayed as ONE CUDA graph
 per image shape.  Link names / parameter paths are the reference's, so `serializers.load_npz` of a
-reference checkpoint (forward.py:29) fills this model.  The RCNN / RPN training branches
-(:115-116,136-173) are "next" rows and raise NotImplementedError.
+reference checkpoint (forward.py:29) fills this model.  RPN training mode (:114-116) returns rpn_loss computed on the
+device (targets + losses + head gradient, models/region_proposal_network.py); the RCNN training branch (:136-173) is a
+later "next" row and raises NotImplementedError.
 """
 import os
 
@@ -94,8 +95,13 @@ class FasterRCNN(links.Link):
         from chainer import Variable
         if self.type_check_enable:
             self._check_data_type_forward(x, img_info, gt_boxes)
-        if gt_boxes is not None and (self.rpn_train or self.rcnn_train):
-            raise NotImplementedError("training branches (models/faster_rcnn.py:115-116,136-173) are outside the forward path")
+        if self.rpn_train and gt_boxes is not None:
+            # RPN training mode (:114-116): trunk features -> RPN -> AnchorTargetLayer -> rpn_loss (a Variable); the
+            # gradient w.r.t. the RPN head outputs is left in self.RPN.head_grad.  The backward pass through the convs
+            # and the optimizer step are the remaining part of this "next" row.
+            return self.RPN(self.trunk(x), img_info, gt_boxes)
+        if gt_boxes is not None and self.rcnn_train:
+            raise NotImplementedError("RCNN training branch (models/faster_rcnn.py:136-173) is outside the forward path")
         fam = arrays.family(x)
         t = arrays.to_device(x)
         hw = arrays.to_host_ints(img_info)

@@ -179,6 +179,54 @@ int frcnn_bbox_decode(const float* boxes, const float* trans, int N, int K, int 
 int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_cap, int num_classes,
                  double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * RPN training targets and losses (the train_rpn.py step).  Box arithmetic is
+ * float64 in the reference's operation order: labels and indices are bit-identical to the reference.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* models/bbox.pyx:16-56 bbox_overlaps.  boxes [n,4], query [k,4], out [n,k], all float64 device
+ * memory.  (The reference runs this on the host even in GPU mode, anchor_target_layer.py:179-187.) */
+int frcnn_bbox_overlaps(const double* boxes, int n, const double* query, int k, double* out, void* stream);
+
+/* AnchorTargetLayer.__call__ (models/anchor_target_layer.py:66-198).
+ *   anchors [A,4] float64 base anchors; all anchors = base + (w,h,w,h)*feat_stride, row (h*W+w)*A+a,
+ *   kept in float64 (:108); gt_boxes [n_gt,5] float32 (x1,y1,x2,y2,cls), n_gt >= 1.
+ *   neg_thr / pos_thr / batch / num_fg: RPN_NEGATIVE_OVERLAP 0.3, RPN_POSITIVE_OVERLAP 0.7,
+ *   RPN_BATCHSIZE 256, int(RPN_FG_FRACTION*RPN_BATCHSIZE) = 128 (:44-47,149).
+ *   subsample_mode 0: labels BEFORE subsampling (:131-146);
+ *                  1: device subsampling (:148-168) by a counter hash of (seed, anchor index) -- the
+ *                     reference draws from NumPy's global RNG on the host, which cannot be matched
+ *                     bit-for-bit without that host state; no host sync;
+ *                  2: disable_pos[n_disable] = positions in the inside-compact arrays to set to -1
+ *                     (exactly what the reference's np.random.choice calls return).
+ * Outputs (device): labels_full int32 [n_all] in {-1,0,1}, -1 for anchors outside the image
+ *   (= bbox_labels_mapped of region_proposal_network.py:164-165); targets_full float32 [n_all,4]
+ *   (16-byte aligned; zeros outside); inds_inside int32 [n_all capacity] (ascending);
+ *   counts int32 [8] = {n_inside, n_fg, n_bg, n_fg before subsampling, n_bg before, n_all, 0, 0}.
+ * The reference's compact outputs are labels_full[inds_inside], targets_full[inds_inside]. */
+size_t frcnn_anchor_targets_workspace_bytes(int n_all, int n_gt);
+int frcnn_anchor_targets(const double* anchors, int A, int feat_h, int feat_w, int feat_stride, const float* gt_boxes,
+                         int n_gt, int im_h, int im_w, double neg_thr, double pos_thr, int batch, int num_fg,
+                         int subsample_mode, unsigned long long seed, const int* disable_pos, int n_disable,
+                         int* labels_full, float* targets_full, int* inds_inside, int* counts, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* RegionProposalNetwork._calc_rpn_loss_cls / _calc_rpn_loss_bbox (models/region_proposal_network.py
+ * :160-204) and, in the same pass, d(rpn_loss)/d(score) and d(rpn_loss)/d(bbox_pred).
+ *   score: channel c of pixel k at score[c*score_cs + k*score_ps] (2A channels; 2-way softmax between
+ *   channel a and A+a, ignore label -1, normalised by max(#valid,1)); bbox likewise (4A channels;
+ *   channel j*A+a = coordinate j of anchor a, :186-191; Huber `delta`, summed over every INSIDE anchor,
+ *   divided by the number of ALL anchors).  labels_full / targets_full / counts from
+ *   frcnn_anchor_targets.  losses float32 [4] = {rpn_loss_cls, rpn_loss_bbox, rpn_cls_accuracy,
+ *   rpn_loss = cls + loss_lambda*bbox}.  dscore / dbbox (optional, same addressing as score / bbox)
+ *   receive grad_scale * d(rpn_loss)/d(.), zeros where no loss term applies. */
+size_t frcnn_rpn_loss_workspace_bytes(int n_all);
+int frcnn_rpn_loss(const float* score, long score_cs, long score_ps, const float* bbox, long bbox_cs, long bbox_ps,
+                   const double* anchors, int A, int feat_h, int feat_w, int feat_stride, int im_h, int im_w,
+                   const int* labels_full, const float* targets_full, const int* counts, double delta, double loss_lambda,
+                   double grad_scale, float* losses, float* dscore, float* dbbox, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
 /* Profiling hook (not part of the drop-in surface): a device buffer of 8 int64 that receives the
  * per-phase clock64() stamps of subsequent top-k sort launches; NULL disables. */
 void frcnn_debug_sort_clocks(long long* dev_buf);

@@ -312,8 +312,9 @@ def rpn_loss_cls(rpn_cls_score, labels, inds_inside, n_all, A):
     pred = z.argmax(axis=1)
     acc = f32((pred[valid] == t[valid]).sum() / count) if valid.any() else f32(0)
     # d loss / d score = (softmax - onehot) / count on valid anchors, 0 elsewhere
-    p = np.exp(logp.astype(np.float64))
-    g = p.copy()
+    z64 = z.astype(np.float64)                                                    # gradient in float64 (no p-1 cancellation)
+    e64 = np.exp(z64 - z64.max(axis=1, keepdims=True))
+    g = e64 / e64.sum(axis=1, keepdims=True)
     onehot = np.zeros_like(g)
     np.put_along_axis(onehot, tt[:, None], 1.0, axis=1)
     g = (g - onehot) * valid[:, None] / count

@@ -1,0 +1,296 @@
+"""GPU parity tests of the RPN-training row: frcnn_bbox_overlaps, frcnn_anchor_targets,
+frcnn_rpn_loss through the C ABI, against the oracle (itself pinned to the reference's anchor_target_layer.py and compiled
+bbox.pyx, tests/test_oracle_cpu.py) and against the committed golden vectors of the reference run.
+
+Bar: labels / indices / counts bit-exact; float64 IoU bit-exact; regression targets: float64 arithmetic with CUDA's log()
+instead of NumPy's, cast to float32 -> at most 1 float32 ulp apart (asserted, exact fraction printed); losses 1e-6 relative
+(double accumulation on both sides, different summation order), gradients 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import frcnn_oracle as orc
+import golden_inputs as gi
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+ANCHORS = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+
+
+@pytest.fixture(scope="module")
+def tops():
+    from frcnn_b200 import train_ops
+    return train_ops
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "anchor_target_layer.npz"))
+
+
+def _ulp_diff_f32(a, b):
+    ia = np.ascontiguousarray(a, f32).view(np.int32).astype(np.int64)
+    ib = np.ascontiguousarray(b, f32).view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return np.abs(ia - ib)
+
+
+def test_bbox_overlaps_bit_exact(tops):
+    g = _golden()
+    boxes, _ = gi.box_transform_case(500, 1, 21)
+    query, _ = gi.box_transform_case(17, 1, 22)
+    got = tops.bbox_overlaps(_dev(boxes.astype(np.float64)), _dev(query.astype(np.float64))).cpu().numpy()
+    assert np.array_equal(got, g["overlaps_500x17"])                       # the reference's compiled bbox.pyx output
+    rng = np.random.default_rng(0)                                         # integer grid: exact ties, zero overlaps, identical boxes
+    b = rng.integers(0, 30, (700, 2)).astype(np.float64)
+    b = np.hstack([b, b + rng.integers(0, 25, (700, 2))])
+    q = np.vstack([b[:40], b[100:110] + 0.5])
+    assert np.array_equal(tops.bbox_overlaps(_dev(b), _dev(q)).cpu().numpy(), orc.bbox_overlaps(b, q))
+    assert tops.bbox_overlaps(_dev(np.zeros((0, 4))), _dev(q)).shape == (0, 50)
+
+
+def _run_targets(tops, name, mode, **kw):
+    fh, fw, gt, info, seed = gi.anchor_target_case(name)
+    w = tops.anchor_targets(_dev(ANCHORS.astype(np.float64)), 9, fh, fw, 16, _dev(gt[0]), int(info[0, 0]), int(info[0, 1]),
+                            mode=mode, **kw)
+    torch.cuda.synchronize()
+    return w, (fh, fw, gt, info, seed)
+
+
+@pytest.mark.parametrize("name", list(gi.ANCHOR_TARGET_CASES))
+def test_anchor_targets_before_subsampling(tops, name):
+    w, (fh, fw, gt, info, seed) = _run_targets(tops, name, tops.SUBSAMPLE_NONE)
+    np.random.seed(seed)
+    r = orc.anchor_target_layer(fh, fw, gt, info)
+    counts = w.counts.cpu().numpy()
+    n_in = int(counts[0])
+    assert n_in == len(r["inds_inside"]) and int(counts[5]) == r["n_all"] == w.n_all
+    inds = w.inds_inside[:n_in].cpu().numpy()
+    assert np.array_equal(inds, r["inds_inside"])                                            # ascending np.where order
+    lab_full = w.labels_full.cpu().numpy()
+    before = r["labels_before_subsample"]
+    assert np.array_equal(lab_full[inds], before)                                            # bit-exact labelling rules
+    outside = np.ones(w.n_all, bool)
+    outside[inds] = False
+    assert (lab_full[outside] == -1).all()
+    assert int(counts[1]) == int(counts[3]) == int((before == 1).sum())
+    assert int(counts[2]) == int(counts[4]) == int((before == 0).sum())
+    tg = w.targets_full.cpu().numpy()
+    assert (tg[outside] == 0).all()
+    ulp = _ulp_diff_f32(tg[inds], r["targets"])
+    print("%s: targets exact %.4f%%, max ulp %d" % (name, 100.0 * (ulp == 0).mean(), ulp.max()))
+    assert ulp.max() <= 1 and (ulp == 0).mean() > 0.999
+    lab_c, tg_c, idx_c, n_all = w.compact()                                                  # the reference's return tuple
+    assert n_all == r["n_all"] and np.array_equal(idx_c.cpu().numpy(), r["inds_inside"])
+    assert np.array_equal(lab_c.cpu().numpy(), before) and np.array_equal(tg_c.cpu().numpy(), tg[inds])
+
+
+@pytest.mark.parametrize("name", list(gi.ANCHOR_TARGET_CASES))
+def test_anchor_targets_replay_reference_draws(tops, name):
+    """Mode 2 with the index sets the reference's own np.random.choice calls returned (recorded in the golden file)
+    reproduces the reference's final labels exactly."""
+    g = _golden()
+    ncall = int(g[name + "_n_choice_calls"])
+    chosen = [g[name + "_choice%d_chosen" % i] for i in range(ncall)]
+    dis = np.concatenate(chosen).astype(np.int32) if chosen else np.zeros((0,), np.int32)
+    w, _ = _run_targets(tops, name, tops.SUBSAMPLE_LIST, disable_pos=_dev(dis) if dis.size else None)
+    n_in = int(w.counts[0].item())
+    inds = w.inds_inside[:n_in].cpu().numpy()
+    assert np.array_equal(inds, g[name + "_inds_inside"])
+    lab = w.labels_full.cpu().numpy()[inds]
+    assert np.array_equal(lab, g[name + "_labels"])
+    c = w.counts.cpu().numpy()
+    assert int(c[1]) == int((lab == 1).sum()) and int(c[2]) == int((lab == 0).sum())
+    ulp = _ulp_diff_f32(w.targets_full.cpu().numpy()[inds], g[name + "_targets"])
+    assert ulp.max() <= 1
+
+
+@pytest.mark.parametrize("name", ["c1_g8", "c1_g40_manyfg", "c1_g3_outside", "c1_g1", "t10_small"])
+def test_anchor_targets_device_subsampling_properties(tops, name):
+    """Mode 1 cannot match NumPy's Mersenne stream; it must satisfy what the reference's subsampling guarantees
+    (anchor_target_layer.py:148-168) and be a deterministic function of the seed."""
+    w0, _ = _run_targets(tops, name, tops.SUBSAMPLE_NONE)
+    before = w0.labels_full.cpu().numpy().copy()
+    w1, _ = _run_targets(tops, name, tops.SUBSAMPLE_DEVICE, seed=1234)
+    a = w1.labels_full.cpu().numpy().copy()
+    c = w1.counts.cpu().numpy().copy()
+    fg_b, bg_b = int((before == 1).sum()), int((before == 0).sum())
+    fg_a, bg_a = int((a == 1).sum()), int((a == 0).sum())
+    assert (int(c[1]), int(c[2]), int(c[3]), int(c[4])) == (fg_a, bg_a, fg_b, bg_b)
+    assert fg_a == min(fg_b, 128) and bg_a == min(bg_b, 256 - fg_a)
+    changed = a != before
+    assert (a[changed] == -1).all() and (before[changed] >= 0).all()                        # only disables, never relabels
+    w2, _ = _run_targets(tops, name, tops.SUBSAMPLE_DEVICE, seed=1234)
+    assert np.array_equal(w2.labels_full.cpu().numpy(), a)                                   # deterministic
+    if changed.any():
+        w3, _ = _run_targets(tops, name, tops.SUBSAMPLE_DEVICE, seed=99)
+        assert not np.array_equal(w3.labels_full.cpu().numpy(), a)                           # seed matters
+
+
+def test_anchor_targets_many_gt_boxes(tops):
+    """n_gt beyond one shared-memory chunk (256) and a ResNet-sized map."""
+    rng = np.random.default_rng(11)
+    G, fh, fw, ih, iw = 300, 50, 84, 800, 1333
+    w_ = rng.uniform(16, 500, G)
+    h_ = rng.uniform(16, 400, G)
+    x1 = np.floor(rng.uniform(0, iw - w_))
+    y1 = np.floor(rng.uniform(0, ih - h_))
+    gt = np.stack([x1, y1, np.floor(x1 + w_ - 1), np.floor(y1 + h_ - 1), rng.integers(0, 20, G)], 1).astype(f32)[None]
+    info = np.array([[ih, iw]], np.int32)
+    w = tops.anchor_targets(_dev(ANCHORS.astype(np.float64)), 9, fh, fw, 16, _dev(gt[0]), ih, iw, mode=tops.SUBSAMPLE_NONE)
+    r = orc.anchor_target_layer(fh, fw, gt, info, choice=lambda inds, size: inds[:size])
+    n_in = int(w.counts[0].item())
+    inds = w.inds_inside[:n_in].cpu().numpy()
+    assert np.array_equal(inds, r["inds_inside"])
+    assert np.array_equal(w.labels_full.cpu().numpy()[inds], r["labels_before_subsample"])
+    assert _ulp_diff_f32(w.targets_full.cpu().numpy()[inds], r["targets"]).max() <= 1
+
+
+def test_anchor_targets_argument_errors(tops):
+    from frcnn_b200._lib import FrcnnError
+    with pytest.raises(FrcnnError):
+        tops.anchor_targets(_dev(ANCHORS.astype(np.float64)), 9, 14, 14, 16, torch.zeros((0, 5), device="cuda"), 224, 224)
+    with pytest.raises(FrcnnError):
+        tops.anchor_targets(_dev(ANCHORS.astype(np.float64)), 9, 14, 14, 16, torch.zeros((3, 4), device="cuda"), 224, 224)
+
+
+@pytest.mark.parametrize("name,layout", [("c1_g8", "nchw"), ("c1_g8", "nhwc"), ("t14_ref_test", "nchw"),
+                                         ("c1_g3_outside", "nhwc"), ("t10_small", "nchw")])
+def test_rpn_loss_and_gradients(tops, name, layout):
+    g = _golden()
+    ncall = int(g[name + "_n_choice_calls"])
+    chosen = [g[name + "_choice%d_chosen" % i] for i in range(ncall)]
+    dis = np.concatenate(chosen).astype(np.int32) if chosen else np.zeros((0,), np.int32)
+    w, (fh, fw, gt, info, seed) = _run_targets(tops, name, tops.SUBSAMPLE_LIST, disable_pos=_dev(dis) if dis.size else None)
+    labels, targets, inds = g[name + "_labels"], g[name + "_targets"], g[name + "_inds_inside"]
+    A, n_all = 9, 9 * fh * fw
+    rng = np.random.default_rng(5)
+    score = (rng.standard_normal((1, 2 * A, fh, fw)) * 2).astype(f32)
+    pred = (rng.standard_normal((1, 4 * A, fh, fw)) * 2.5).astype(f32)
+    lam, delta = 1.5, 3.0
+    lc, acc, dsc = orc.rpn_loss_cls(score, labels, inds, n_all, A)
+    lb, dpr = orc.rpn_loss_bbox(pred, targets, inds, A, delta=delta)
+    anchors = _dev(ANCHORS.astype(np.float64))
+    if layout == "nchw":
+        losses, ds, db = tops.rpn_loss(_dev(score[0]), _dev(pred[0]), anchors, A, fh, fw, 16, int(info[0, 0]), int(info[0, 1]), w,
+                                       delta=delta, loss_lambda=lam)
+        ds, db = ds.cpu().numpy()[None], db.cpu().numpy()[None]
+    else:
+        ld = 64
+        m = np.zeros((fh * fw, ld), f32)
+        m[:, :2 * A] = score[0].reshape(2 * A, -1).T
+        m[:, 2 * A:6 * A] = pred[0].reshape(4 * A, -1).T
+        losses, dm, _ = tops.rpn_loss(_dev(m), None, anchors, A, fh, fw, 16, int(info[0, 0]), int(info[0, 1]), w,
+                                      delta=delta, loss_lambda=lam, layout="nhwc", ld=ld)
+        dm = dm.cpu().numpy()
+        assert (dm[:, 6 * A:] == 0).all()
+        ds = dm[:, :2 * A].T.reshape(1, 2 * A, fh, fw)
+        db = dm[:, 2 * A:6 * A].T.reshape(1, 4 * A, fh, fw)
+    L = losses.cpu().numpy()
+    want_total = float(lc) + lam * float(lb)
+    print(name, layout, "losses", L, "oracle", float(lc), float(lb), float(acc), want_total)
+    assert abs(L[0] - float(lc)) <= 1e-6 * max(1.0, abs(float(lc)))
+    assert abs(L[1] - float(lb)) <= 1e-6 * max(1e-3, abs(float(lb)))
+    assert abs(L[2] - float(acc)) <= 1e-6
+    assert abs(L[3] - want_total) <= 2e-6 * max(1.0, abs(want_total))
+    np.testing.assert_allclose(ds, dsc, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(db, dpr * lam, rtol=1e-5, atol=1e-10)
+    # the training step's gradient of the summed loss: grad_scale is a plain multiplier
+    if layout == "nchw":
+        _, ds2, db2 = tops.rpn_loss(_dev(score[0]), _dev(pred[0]), anchors, A, fh, fw, 16, int(info[0, 0]), int(info[0, 1]), w,
+                                    delta=delta, loss_lambda=lam, grad_scale=0.5)
+        np.testing.assert_allclose(ds2.cpu().numpy()[None], 0.5 * ds, rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(db2.cpu().numpy()[None], 0.5 * db, rtol=1e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------ the drop-in classes (reference call statements)
+@pytest.fixture(scope="module")
+def dropin_installed():
+    from frcnn_b200 import dropin
+    dropin.install()
+
+
+@pytest.mark.parametrize("name", list(gi.ANCHOR_TARGET_CASES))
+def test_anchor_target_layer_class_same_numpy_seed_same_labels_as_reference(dropin_installed, name):
+    """tests/test_anchor_target_layer.py:62-66 call statement.  In the default 'numpy' mode the drop-in draws from NumPy's
+    global RNG exactly like the reference (same pools, same call order), so the SAME np.random.seed gives the reference's
+    own labels -- compared with the golden vectors of the reference run, bit for bit."""
+    from chainer import Variable
+    from models.anchor_target_layer import AnchorTargetLayer
+    g = _golden()
+    fh, fw, gt, info, seed = gi.anchor_target_case(name)
+    layer = AnchorTargetLayer(16, [0.5, 1, 2], [8, 16, 32])
+    np.random.seed(seed)
+    bbox_labels, bbox_reg_targets, inds_inside, n_all_bbox = layer(fh, fw, Variable(gt), Variable(info))
+    assert isinstance(bbox_labels, np.ndarray) and bbox_labels.dtype == np.int32
+    assert n_all_bbox == int(g[name + "_n_all"])
+    assert np.array_equal(inds_inside, g[name + "_inds_inside"])
+    assert np.array_equal(bbox_labels, g[name + "_labels"])
+    assert bbox_reg_targets.dtype == np.float32 and _ulp_diff_f32(bbox_reg_targets, g[name + "_targets"]).max() <= 1
+    assert len(bbox_labels) == len(inds_inside) == len(bbox_reg_targets)           # test_anchor_target_layer.py:76-77
+    # device arrays in -> device arrays out (the reference's test_time GPU leg, :49-58)
+    import chainer
+    cp = chainer.cuda.cupy
+    np.random.seed(seed)
+    lab_d, tg_d, inds_d, _ = layer(fh, fw, Variable(cp.asarray(gt)), Variable(info))
+    assert isinstance(lab_d, cp.ndarray) and np.array_equal(cp.asnumpy(lab_d), g[name + "_labels"])
+    # "device" subsampling mode: same guarantees, no host RNG
+    layer.subsample = "device"
+    lab2, _, _, _ = layer(fh, fw, Variable(gt), Variable(info))
+    assert (lab2 == 1).sum() <= 128 and (lab2 >= 0).sum() <= 256
+    assert (lab2 == 1).sum() == (g[name + "_labels"] == 1).sum() and (lab2 == 0).sum() == (g[name + "_labels"] == 0).sum()
+
+
+def test_bbox_overlaps_module_surface(dropin_installed):
+    from models.bbox import bbox_overlaps
+    boxes, _ = gi.box_transform_case(500, 1, 21)
+    query, _ = gi.box_transform_case(17, 1, 22)
+    got = bbox_overlaps(np.ascontiguousarray(boxes, dtype=np.float64), np.ascontiguousarray(query, dtype=np.float64))
+    assert isinstance(got, np.ndarray) and np.array_equal(got, _golden()["overlaps_500x17"])
+
+
+def test_rpn_training_branch_like_reference(dropin_installed):
+    """RegionProposalNetwork.__call__ with train=True and gt_boxes (region_proposal_network.py:126-156): returns rpn_loss;
+    compared with the oracle's losses on the device's own head outputs, with the reference-faithful NumPy subsampling."""
+    from chainer import Variable
+    from models.region_proposal_network import RegionProposalNetwork
+    name = "c1_g8"
+    fh, fw, gt, info, seed = gi.anchor_target_case(name)
+    rng = np.random.default_rng(8)
+    rpn = RegionProposalNetwork(loss_lambda=1., delta=3)
+    for _, p in rpn.namedparams():                      # non-degenerate weights (the default N(0, 0.01) is fine too)
+        if p.data.ndim == 4:
+            p.data[...] = (rng.standard_normal(p.data.shape) * 0.02).astype(f32)
+    rpn._params_changed()
+    x = (np.maximum(rng.standard_normal((1, 512, fh, fw)), 0) * 1.0).astype(f32)
+    rpn.train = True
+    np.random.seed(seed)
+    loss = rpn(Variable(x), Variable(info), Variable(gt))
+    assert isinstance(loss, Variable) and loss.name == "rpn_loss" and loss.data.shape == ()
+    y = rpn.head_out.cpu().numpy()                                          # [H*W, ld] fp32: the device's own logits/deltas
+    score = y[:, :18].T.reshape(1, 18, fh, fw)
+    pred = y[:, 18:54].T.reshape(1, 36, fh, fw)
+    np.random.seed(seed)
+    r = orc.anchor_target_layer(fh, fw, gt, info)
+    lc, acc, dsc = orc.rpn_loss_cls(score, r["labels"], r["inds_inside"], r["n_all"], 9)
+    lb, dpr = orc.rpn_loss_bbox(pred, r["targets"], r["inds_inside"], 9, delta=3.0)
+    print("rpn_loss", float(loss.data), "cls", float(rpn.rpn_loss_cls.data), "bbox", float(rpn.rpn_loss_bbox.data),
+          "acc", float(rpn.rpn_cls_accuracy.data), "| oracle", float(lc), float(lb), float(acc))
+    assert abs(float(rpn.rpn_loss_cls.data) - float(lc)) <= 1e-6 * max(1.0, float(lc))
+    assert abs(float(rpn.rpn_loss_bbox.data) - float(lb)) <= 1e-5 * max(1e-3, float(lb))
+    assert abs(float(rpn.rpn_cls_accuracy.data) - float(acc)) <= 1e-6
+    assert abs(float(loss.data) - (float(lc) + float(lb))) <= 2e-6 * max(1.0, float(lc) + float(lb))
+    gmat = rpn.head_grad.cpu().numpy()
+    np.testing.assert_allclose(gmat[:, :18].T.reshape(1, 18, fh, fw), dsc, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(gmat[:, 18:54].T.reshape(1, 36, fh, fw), dpr, rtol=2e-5, atol=1e-10)
+    # the head outputs themselves follow the fp32 oracle convs within the forward path's tolerance
+    params = {"RPN/" + k.lstrip("/"): p.data for k, p in rpn.namedparams()}
+    h = orc.relu(orc.conv2d(x, params["RPN/rpn_conv_3x3/W"], params["RPN/rpn_conv_3x3/b"], 1))
+    want_score = orc.conv2d(h, params["RPN/rpn_cls_score/W"], params["RPN/rpn_cls_score/b"], 0)
+    assert np.abs(score - want_score).max() <= 1e-4 * max(1.0, np.abs(want_score).max())
