@@ -48,6 +48,13 @@ struct ConvParams {
     float* y_f32;
     const float* bias;
     const int* m_valid;
+    // split-K GEMM mode (frcnn_gemm_nt_splitk, per-tap path only): the tile space is n_parts x tiles_per_part,
+    // part = group * splits + split; a split covers k-blocks [split*kb_per_split, ...) of kb_total; group g shifts
+    // the B operand's K coordinate by (g/3-1)*g_row_stride and reads plane g%3 of B (the 3x3 taps of a padded pixel
+    // axis: a TMA box must start 16-B aligned, so the +-1 column shifts are three pre-shifted planes); every part
+    // writes its own fp32 slab y_f32 + part*part_stride.  n_parts == 1: an ordinary convolution.
+    int n_parts, tiles_per_part, splits, kb_per_split, kb_total, g_row_stride;
+    long part_stride;
 };
 
 constexpr int kNumThreads = 192;
@@ -74,6 +81,23 @@ struct Cfg {
 // CG = 1: one CTA per tile (M = 128).  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256-pixel tile --
 // each CTA feeds its own 128 pixel rows of A and HALF of the weight tile, which halves the shared-memory
 // operand traffic per MMA (the 1-CTA kernel is smem-bandwidth bound at N = 128).
+// split-K GEMM mode helpers (ConvParams::n_parts > 1); an ordinary convolution has one part covering everything
+__device__ __forceinline__ int part_k0(const ConvParams& p, int part) {
+    return p.n_parts > 1 ? (part % p.splits) * p.kb_per_split : 0;
+}
+__device__ __forceinline__ int part_kblocks(const ConvParams& p, int part, int num_kb) {
+    if (p.n_parts <= 1) return num_kb;
+    const int k0 = (part % p.splits) * p.kb_per_split;
+    return min(p.kb_per_split, p.kb_total - k0);
+}
+__device__ __forceinline__ int part_b_shift(const ConvParams& p, int part) {
+    if (p.n_parts <= 1 || p.g_row_stride == 0) return 0;
+    return ((part / p.splits) / 3 - 1) * p.g_row_stride;       // multiple of 8 elements: TMA box starts stay 16-B aligned
+}
+__device__ __forceinline__ int part_b_plane(const ConvParams& p, int part) {
+    return (p.n_parts > 1 && p.g_row_stride != 0) ? (part / p.splits) % 3 : -1;
+}
+
 template <int CG>
 __device__ __forceinline__ void tma_ld(void* s, const void* d, uint64_t* bar, int c0, int c1, int c2) {
     if constexpr (CG == 2) ptx::tma_load_3d_2sm(s, d, bar, c0, c1, c2); else ptx::tma_load_3d(s, d, bar, c0, c1, c2);
@@ -192,8 +216,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             uint32_t aphase = 0;
             (void)as; (void)aphase;
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-                const int nt = tile % p.n_tiles;
-                const int mt = (tile / p.n_tiles) * CG + (int)rank;      // an out-of-range tile of an odd pair loads zeros, stores nothing
+                const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
+                const int nt = t2 % p.n_tiles;
+                const int mt = (t2 / p.n_tiles) * CG + (int)rank;      // an out-of-range tile of an odd pair loads zeros, stores nothing
                 const int h0 = (mt / p.tiles_w) * p.TH;
                 const int w0 = (mt % p.tiles_w) * p.TW;
                 const int n0 = nt * BN + (int)rank * (BN / CG);        // this CTA's half of the weight tile
@@ -216,19 +241,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     }
                     continue;
                 }
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int nkb = part_kblocks(p, part, num_kb);
+                const int ka = part_k0(p, part) * BK, kboff = ka + part_b_shift(p, part);
+                const int bplane = part_b_plane(p, part);
+                for (int kb = 0; kb < nkb; ++kb) {
                     const int tap = kb / p.cin_blocks;
+                    const int btap = bplane >= 0 ? bplane : tap;
                     const int cb = kb - tap * p.cin_blocks;
                     const int r = tap / p.ksize, s = tap - r * p.ksize;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = ring + (size_t)stage * stage_bytes;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * CG));
-                    tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
-                    tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], cb * BK, n0, tap);
+                    tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], ka + cb * BK, w0 + s - pad, h0 + r - pad);
+                    tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], kboff + cb * BK, n0, btap);
                     if (p.x3) {
                         uint8_t* st2 = st + C::A_BYTES + C::B_BYTES;
-                        tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], cb * BK, w0 + s - pad, h0 + r - pad);
-                        tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], cb * BK, n0, tap);
+                        tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], ka + cb * BK, w0 + s - pad, h0 + r - pad);
+                        tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], kboff + cb * BK, n0, btap);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -285,7 +314,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int nkb = part_kblocks(p, tile / p.tiles_per_part, num_kb);
+            for (int kb = 0; kb < nkb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
@@ -306,7 +336,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         for (int k = 0; k < BK / 16; ++k) mma_ss<CG>(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
                     }
                     mma_cm<CG>(&empty_bar[stage]);            // frees the smem slot when the MMAs retire
-                    if (kb == num_kb - 1) mma_cm<CG>(&tfull_bar[acc]);   // accumulator complete
+                    if (kb == nkb - 1) mma_cm<CG>(&tfull_bar[acc]);   // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == S) { stage = 0; phase ^= 1; }
@@ -323,8 +353,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         uint32_t acc_phase = 0;
         uint32_t chunk_i = 0;                    // running chunk counter -> staging buffer parity
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-            const int nt = tile % p.n_tiles;
-            const int mt = (tile / p.n_tiles) * CG + (int)rank;
+            const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
+            const int nt = t2 % p.n_tiles;
+            const int mt = (t2 / p.n_tiles) * CG + (int)rank;
             const int h0 = (mt / p.tiles_w) * p.TH, w0 = (mt % p.tiles_w) * p.TW;
             const int h = h0 + row / p.TW;
             const int w = w0 + row % p.TW;
@@ -373,7 +404,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     for (int j = 0; j < 32; ++j) v[j] = 0.0f;
                 }
                 if (in_img && p.y_f32 != nullptr && n < p.ld_f32) {
-                    float4* dst = reinterpret_cast<float4*>(p.y_f32 + pix * p.ld_f32 + n);
+                    float4* dst = reinterpret_cast<float4*>(p.y_f32 + (long)part * p.part_stride + pix * p.ld_f32 + n);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
@@ -570,9 +601,17 @@ extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
     g_force_tw = tile_w;
 }
 
-extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
-                            const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
-                            void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
+namespace {
+struct GemmExtra {          // split-K GEMM mode of the same kernel (frcnn_gemm_nt_splitk)
+    int groups, row_stride, splits;
+    long part_stride;
+};
+}  // namespace
+
+static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
+                       const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
+                       void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_,
+                       const GemmExtra* ge) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(x_hi && w_hi && bias, "frcnn_conv2d: x_hi, w_hi and bias are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
@@ -646,6 +685,21 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     if (g_force_cg == 2 && BK == 64) CG = 2;
     FRCNN_REQUIRE(m_tiles * p.n_tiles < (1l << 30), "frcnn_conv2d: too many tiles");
     p.num_tiles = (int)(cdiv((int)m_tiles, CG) * p.n_tiles);     // tiles (CG = 1) or pair-tiles (CG = 2)
+    p.tiles_per_part = p.num_tiles;
+    p.n_parts = 1; p.splits = 1; p.kb_per_split = p.kb_total = p.taps * p.cin_blocks; p.g_row_stride = 0; p.part_stride = 0;
+    if (ge != nullptr) {
+        FRCNN_REQUIRE(ksize == 1 && BK == 64 && Cin % 64 == 0 && y_f32 && !y_hi && !m_valid, "gemm_nt_splitk: bad configuration");
+        p.kb_total = p.cin_blocks;
+        p.kb_per_split = cdiv(p.kb_total, ge->splits);
+        p.splits = cdiv(p.kb_total, p.kb_per_split);             // every split non-empty
+        p.n_parts = ge->groups * p.splits;
+        p.g_row_stride = ge->groups == 9 ? ge->row_stride : 0;
+        FRCNN_REQUIRE(ge->groups == 1 || (ge->row_stride > 0 && ge->row_stride % 8 == 0),
+                      "gemm_nt_splitk: row_stride must be a positive multiple of 8 (16-byte aligned TMA box starts)");
+        p.part_stride = ge->part_stride;
+        FRCNN_REQUIRE((long)p.num_tiles * p.n_parts < (1l << 30), "gemm_nt_splitk: too many tiles");
+        p.num_tiles *= p.n_parts;
+    }
     p.num_stages = 0;
     p.x3 = x_lo != nullptr;
     p.relu = relu;
@@ -663,10 +717,11 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
     int rc;
     const int abw = halo ? kHaloW : TW, abh = halo ? kHaloH : TH;     // A box: the tile, or the tile + 1-pixel halo
     if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
-    if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, p.taps, BK, BN / CG, 1)) != FRCNN_OK) return rc;
+    const int b_planes = (ge != nullptr && ge->groups == 9) ? 3 : p.taps;
+    if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, b_planes, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     if (p.x3) {
         if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
-        if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, p.taps, BK, BN / CG, 1)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, b_planes, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     } else {
         tm[1] = tm[0];
         tm[3] = tm[2];
@@ -707,4 +762,26 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
 #undef FRCNN_DISPATCH
     set_error("frcnn_conv2d: no kernel for BN=%d BK=%d", BN, BK);
     return FRCNN_ERR_ARG;
+}
+
+extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
+                            const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
+                            void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
+    return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, fuse_pool2x2, y_hi, y_lo, y_f32, ld_f32,
+                       m_valid, stream_, nullptr);
+}
+
+extern "C" int frcnn_gemm_nt_splitk_splits(int K, int splits) {
+    const int kb = cdiv(K, 64), per = cdiv(kb, splits < 1 ? 1 : splits);
+    return cdiv(kb, per);
+}
+
+extern "C" int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, int K, const void* b_hi, const void* b_lo,
+                                    int N, int groups, int row_stride, int splits, const float* zero_bias, float* parts,
+                                    int ld, void* stream_) {
+    FRCNN_REQUIRE(groups == 1 || groups == 9, "gemm_nt_splitk: groups must be 1 or 9 (got %d)", groups);
+    FRCNN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "gemm_nt_splitk: bad shape M=%d N=%d K=%d (K %% 64 == 0)", M, N, K);
+    FRCNN_REQUIRE(splits >= 1 && parts && zero_bias, "gemm_nt_splitk: splits >= 1, parts and a zero bias vector of ld floats are required");
+    GemmExtra ge{groups, row_stride, splits, (long)M * ld};
+    return conv2d_impl(a_hi, a_lo, 1, M, K, b_hi, b_lo, zero_bias, N, 1, 0, 0, nullptr, nullptr, parts, ld, nullptr, stream_, &ge);
 }

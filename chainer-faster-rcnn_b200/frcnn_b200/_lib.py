@@ -61,6 +61,9 @@ SIGNATURES = {
     "frcnn_rpn_loss": (c_int, [c_void_p, c_long, c_long, c_void_p, c_long, c_long, c_void_p, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_gemm_nt_splitk_splits": (c_int, [c_int, c_int]),
+    "frcnn_gemm_nt_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p]),
     "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),

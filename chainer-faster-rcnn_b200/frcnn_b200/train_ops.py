@@ -108,3 +108,29 @@ def rpn_loss(score, bbox, anchors, A, H, W, feat_stride, im_h, im_w, work, delta
                                      float(delta), float(loss_lambda), float(grad_scale), _p(work.losses), ds_ptr, db_ptr,
                                      _p(work.loss_ws), work.loss_ws.numel(), _stream()), "frcnn_rpn_loss")
     return work.losses, ds, db
+
+
+def split_bf16(x):
+    """float32 CUDA tensor -> (hi, lo) bf16 planes with x ~= hi + lo (the kernels' "bf16x3" operand format)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
+    """frcnn_gemm_nt_splitk: A [M,K]; B [N,K] (groups=1) or [3,N,K] pre-shifted planes (groups=9); bf16 planes (lo may
+    be None for both) -> parts [groups, S, M, ld] fp32, ld = N rounded up to 32.  See include/frcnn_b200.h."""
+    _need_cuda(a_hi, b_hi)
+    M, K = a_hi.shape
+    N = b_hi.shape[-2]
+    want_b = (3, N, K) if groups == 9 else (N, K)
+    if tuple(b_hi.shape) != want_b or K % 64:
+        raise FrcnnError("gemm_nt_splitk: A [M,K], B %s with K %% 64 == 0 (got %s, %s)" % (want_b, tuple(a_hi.shape), tuple(b_hi.shape)))
+    lib = _lib.load()
+    S = lib.frcnn_gemm_nt_splitk_splits(K, int(splits))
+    ld = (N + 31) // 32 * 32
+    parts = torch.empty((groups, S, M, ld), dtype=torch.float32, device=a_hi.device)
+    zero = torch.zeros((max(ld, 256),), dtype=torch.float32, device=a_hi.device)
+    check(lib.frcnn_gemm_nt_splitk(_p(a_hi), _p(a_lo), M, K, _p(b_hi), _p(b_lo), N, int(groups), int(row_stride), int(splits),
+                                   _p(zero), _p(parts), ld, _stream()), "frcnn_gemm_nt_splitk")
+    return parts

@@ -227,6 +227,22 @@ int frcnn_rpn_loss(const float* score, long score_cs, long score_ps, const float
                    double grad_scale, float* losses, float* dscore, float* dbbox, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* Split-K "NT" GEMM on the tensor-core kernel of frcnn_conv2d (same bf16 hi/lo operand planes), the engine of the
+ * weight-gradient pass (conv backward-filter as a GEMM over the pixel axis):
+ *     parts[g][s][m][n] = sum over k in split s of  A[m][k] * B_g[n][k + off(g)]        (fp32, row stride ld)
+ *   A [M][K], B [N][K]: bf16 hi (+ lo, both or neither) planes, K contiguous, K % 64 == 0; reads outside [0,K) are 0.
+ *   groups = 1: B_g = B, off = 0.  groups = 9 (the 3x3 taps when K is a zero-padded pixel axis of row pitch
+ *   row_stride, row_stride % 8 == 0): B is THREE planes [3][N][K] holding the operand pre-shifted by -1 / 0 / +1
+ *   pixel (plane j at k = the unshifted operand at k + j - 1; a TMA box must start 16-byte aligned, so the column
+ *   shift cannot be a coordinate), B_g = plane g%3 and off(g) = (g/3 - 1)*row_stride.
+ *   splits: requested K splits (the effective number is frcnn_gemm_nt_splitk_splits(K, splits)); parts holds
+ *   groups*effective_splits slabs of M*ld floats, ld % 32 == 0, ld >= N.  zero_bias: ld zeros in device memory (the
+ *   kernel's bias input).  The caller reduces over s. */
+int frcnn_gemm_nt_splitk_splits(int K, int splits);
+int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, int K, const void* b_hi, const void* b_lo, int N,
+                         int groups, int row_stride, int splits, const float* zero_bias, float* parts, int ld,
+                         void* stream);
+
 /* Profiling hook (not part of the drop-in surface): a device buffer of 8 int64 that receives the
  * per-phase clock64() stamps of subsequent top-k sort launches; NULL disables. */
 void frcnn_debug_sort_clocks(long long* dev_buf);

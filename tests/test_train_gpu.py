@@ -294,3 +294,61 @@ def test_rpn_training_branch_like_reference(dropin_installed):
     h = orc.relu(orc.conv2d(x, params["RPN/rpn_conv_3x3/W"], params["RPN/rpn_conv_3x3/b"], 1))
     want_score = orc.conv2d(h, params["RPN/rpn_cls_score/W"], params["RPN/rpn_cls_score/b"], 0)
     assert np.abs(score - want_score).max() <= 1e-4 * max(1.0, np.abs(want_score).max())
+
+
+# ------------------------------------------------------------------ split-K NT GEMM (the weight-gradient engine)
+def _ref_gemm_parts(A, B, groups, row_stride, S_eff, K):
+    """float64 reference of parts[g][s] on the exact operand values (B: [N,K], or [3,N,K] when groups == 9)."""
+    kb = K // 64
+    per = -(-kb // S_eff)
+    out = []
+    for g in range(groups):
+        off = (g // 3 - 1) * row_stride if groups == 9 else 0
+        Bg = B[g % 3] if groups == 9 else B
+        Bs = torch.zeros_like(Bg)
+        lo, hi = max(0, -off), min(K, K - off)
+        if hi > lo:
+            Bs[:, lo:hi] = Bg[:, lo + off:hi + off]
+        row = []
+        for s in range(S_eff):
+            k0, k1 = s * per * 64, min(K, (s + 1) * per * 64)
+            row.append(A[:, k0:k1] @ Bs[:, k0:k1].T)
+        out.append(torch.stack(row))
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("M,N,K,groups,splits,x3", [
+    (64, 64, 64 * 37, 9, 5, True),        # conv1_2-like: half-empty M tile, single-CTA path, ragged last split
+    (512, 512, 64 * 40, 9, 3, True),      # CTA pairs, wide N
+    (256, 128, 64 * 16, 1, 1, True),      # plain GEMM, no split
+    (128, 64, 64 * 9, 9, 9, False),       # single-pass bf16
+    (54, 512, 64 * 12, 1, 4, True),       # RPN heads: M not a multiple of anything
+])
+def test_gemm_nt_splitk_matches_float64(tops, M, N, K, groups, splits, x3):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    B = torch.randn(((3, N, K) if groups == 9 else (N, K)), device="cuda", generator=g)
+    row_stride = 40
+    if x3:
+        a_hi, a_lo = tops.split_bf16(A)
+        b_hi, b_lo = tops.split_bf16(B)
+        Ae, Be = a_hi.double() + a_lo.double(), b_hi.double() + b_lo.double()
+    else:
+        a_hi, b_hi, a_lo, b_lo = A.to(torch.bfloat16), B.to(torch.bfloat16), None, None
+        Ae, Be = a_hi.double(), b_hi.double()
+    parts = tops.gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=groups, row_stride=row_stride, splits=splits)
+    S_eff = parts.shape[1]
+    assert parts.shape == (groups, S_eff, M, (N + 31) // 32 * 32) and S_eff <= splits
+    want = _ref_gemm_parts(Ae, Be, groups, row_stride, S_eff, K)
+    got = parts[..., :N].double()
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    print("gemm M%d N%d K%d g%d s%d x3=%s: max err %.3g of scale %.3g" % (M, N, K, groups, S_eff, x3, err, scale))
+    # bf16x3 drops the lo*lo term (2^-18 relative per product) and accumulates in the tensor core's truncating fp32
+    assert err <= 2e-5 * scale
+    # exactly representable operands -> exact sums (small integers, K short enough for fp32)
+    Ai = torch.randint(-3, 4, (M, K), device="cuda", generator=g).float()
+    Bi = torch.randint(-3, 4, tuple(B.shape), device="cuda", generator=g).float()
+    pi = tops.gemm_nt_splitk(Ai.to(torch.bfloat16), None, Bi.to(torch.bfloat16), None, groups=groups, row_stride=row_stride,
+                             splits=splits)
+    assert torch.equal(pi[..., :N].double(), _ref_gemm_parts(Ai.double(), Bi.double(), groups, row_stride, pi.shape[1], K))
