@@ -64,6 +64,13 @@ SIGNATURES = {
     "frcnn_gemm_nt_splitk_splits": (c_int, [c_int, c_int]),
     "frcnn_gemm_nt_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_int, c_void_p]),
+    "frcnn_padded_pixels": (c_long, [c_int, c_int, c_void_p]),
+    "frcnn_grad_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "frcnn_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "frcnn_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_long, c_float, c_void_p, c_void_p]),
+    "frcnn_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_void_p]),
+    "frcnn_pack_conv_weights_dgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),

@@ -4,6 +4,11 @@ The reference hard-wires batch size 1 (models/faster_rcnn.py:77) and its forward
 cross-image state, so N GPUs run N independent replicas and there is NO data-path collective
 (SURVEY.md 8e).  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used only for the
 barrier around the timed region, the max-over-ranks of the elapsed time and gathering per-rank counts.
+
+The one real collective of the repository is on the TRAINING path (train_rpn.py:169-174, Chainer ParallelUpdater:
+every device back-propagates its own image, gradients are ADDED into the main model, one optimizer update): here a
+single all-reduce(SUM) of the flat float32 gradient bucket, `allreduce_sum_`, followed by the identical local update
+on every rank (weights stay replicated without a broadcast).
 """
 import os
 
@@ -50,3 +55,10 @@ def aggregate_throughput(items_per_rank, seconds_this_rank, device=None):
     """Whole-job throughput: all ranks' items divided by the SLOWEST rank's time."""
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     return world * items_per_rank / max_over_ranks(seconds_this_rank, device)
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place SUM over ranks of one flat gradient bucket (no-op for a single process).  Returns `flat`."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat

@@ -3,7 +3,9 @@ frcnn_bbox_overlaps, frcnn_anchor_targets, frcnn_rpn_loss).  Like ops.py: device
 stream in, tensors out, no CPU path.
 
 Replaces models/bbox.pyx:16-56, models/anchor_target_layer.py:66-198 and the two loss functions of
-models/region_proposal_network.py:160-204 (all under /root/reference).
+models/region_proposal_network.py:160-204 (all under /root/reference); the second half wraps the conv-backward entry
+points (frcnn_gemm_nt_splitk, frcnn_grad_prepare, frcnn_wgrad_reduce, frcnn_bias_grad, frcnn_sgd_momentum,
+frcnn_pack_conv_weights_dgrad) used by train_engine.py.
 """
 import ctypes
 
@@ -134,3 +136,64 @@ def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
     check(lib.frcnn_gemm_nt_splitk(_p(a_hi), _p(a_lo), M, K, _p(b_hi), _p(b_lo), N, int(groups), int(row_stride), int(splits),
                                    _p(zero), _p(parts), ld, _stream()), "frcnn_gemm_nt_splitk")
     return parts
+
+
+def padded_pixels(H, W):
+    """(Kp, Wp) of the transposed padded layout of an H x W map (include/frcnn_b200.h)."""
+    wp = ctypes.c_int(0)
+    kp = _lib.load().frcnn_padded_pixels(int(H), int(W), ctypes.byref(wp))
+    return int(kp), int(wp.value)
+
+
+class TBuf(object):
+    """Transposed padded planes [planes, C, Kp] bf16 hi (+ lo), zeroed once (the kernels write the interior only)."""
+
+    def __init__(self, planes, C, H, W, device, x3=True):
+        self.Kp, self.Wp = padded_pixels(H, W)
+        self.planes, self.C, self.H, self.W = planes, C, H, W
+        self.hi = torch.zeros((planes, C, self.Kp), dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros_like(self.hi) if x3 else None
+
+
+def grad_prepare(H, W, C, g=None, g_f32=None, y=None, p=None, out=None, tbuf=None):
+    """frcnn_grad_prepare.  g: ops.Act source (NHWC, or pooled size when p is given) or g_f32 [H*W, ld] fp32;
+    y / p: forward activation / its pooled map (ops.Act) for the ReLU mask / max-pool routing;
+    out: ops.Act [H,W,C] to receive the NHWC result (optional); tbuf: TBuf to receive the transposed planes (optional)."""
+    ld = int(g_f32.shape[1]) if g_f32 is not None else 0
+    check(_lib.load().frcnn_grad_prepare(
+        _p(g.hi) if g is not None else None, _p(g.lo) if g is not None else None, _p(g_f32), ld,
+        _p(y.hi) if y is not None else None, _p(y.lo) if y is not None else None,
+        _p(p.hi) if p is not None else None, _p(p.lo) if p is not None else None, int(H), int(W), int(C),
+        _p(out.hi) if out is not None else None, _p(out.lo) if out is not None else None,
+        _p(tbuf.hi) if tbuf is not None else None, _p(tbuf.lo) if tbuf is not None else None,
+        tbuf.planes if tbuf is not None else 1, _stream()), "frcnn_grad_prepare")
+
+
+def wgrad_reduce(parts, M, N, dw, scale=1.0):
+    """parts [groups, S, M_parts, ld] -> dw (flat fp32 view of M*N*groups elements, OIHW order)."""
+    groups, S, Mp, ld = parts.shape
+    check(_lib.load().frcnn_wgrad_reduce(_p(parts), groups, S, Mp, int(M), ld, int(N), float(scale), _p(dw), _stream()),
+          "frcnn_wgrad_reduce")
+
+
+def bias_grad(tbuf, C, db, scale=1.0):
+    check(_lib.load().frcnn_bias_grad(_p(tbuf.hi), _p(tbuf.lo), int(C), tbuf.Kp, float(scale), _p(db), _stream()), "frcnn_bias_grad")
+
+
+def sgd_momentum(w, v, g, lr, momentum, weight_decay):
+    check(_lib.load().frcnn_sgd_momentum(_p(w), _p(v), _p(g), w.numel(), float(lr), float(momentum), float(weight_decay),
+                                         _stream()), "frcnn_sgd_momentum")
+
+
+def pack_conv_weights_dgrad(w, cout_pad=None, x3=True):
+    """OIHW float32 CUDA weights -> ([taps, Cin, cout_pad] bf16 hi, lo or None): the filter of the data-gradient conv."""
+    w = w.contiguous().float()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    Cout, Cin, kh, kw = w.shape
+    cout_pad = cout_pad or (Cout + 7) // 8 * 8
+    hi = torch.empty((kh * kw, Cin, cout_pad), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if x3 else None
+    check(_lib.load().frcnn_pack_conv_weights_dgrad(_p(w), Cout, Cin, kh, kw, cout_pad, _p(hi), _p(lo), _stream()),
+          "frcnn_pack_conv_weights_dgrad")
+    return hi, lo

@@ -243,6 +243,41 @@ int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, int K, const
                          int groups, int row_stride, int splits, const float* zero_bias, float* parts, int ld,
                          void* stream);
 
+/* ---- conv backward, memory-bound parts (train_backward.cu).  The "transposed padded" layout used by the weight-
+ * gradient GEMM: a [C][Kp] bf16 plane per hi/lo where pixel (h,w) of an H x W map sits at k = (h+1)*Wp + (w+1),
+ * Wp = W+2 rounded up to 8, Kp = (H+2)*Wp rounded up to 64, everything else zero (the buffer must be zeroed once; the
+ * kernels only write the interior).  frcnn_padded_pixels returns Kp and the row pitch Wp. */
+long frcnn_padded_pixels(int H, int W, int* row_pitch);
+
+/* Gradient / activation re-layout with the element-wise backward ops fused:
+ *   source  : bf16 hi(/lo) NHWC planes g [H][W][C] -- or [ceil(H/2)][ceil(W/2)][C] when p_hi is given -- or fp32 [H*W][ld_f32]
+ *   y (opt) : the forward post-ReLU activation [H][W][C]: value *= (y > 0)                 (F.relu backward)
+ *   p (opt) : the 2x2/2 ceil-mode max-pooled y: the source is routed to the FIRST maximum of each window in scan order
+ *             (F.max_pooling_2d backward), zero elsewhere
+ *   outputs : o (opt) NHWC hi/lo [H][W][C]; t (opt) transposed padded planes [planes][C][Kp], planes = 1 (at k) or 3
+ *             (plane j at k holds pixel k + j - 1: the pre-shifted B operand of frcnn_gemm_nt_splitk groups = 9).
+ * With y = p = NULL and planes = 3 this is the plain activation transposer. */
+int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, int ld_f32, const void* y_hi, const void* y_lo,
+                       const void* p_hi, const void* p_lo, int H, int W, int C, void* o_hi, void* o_lo, void* t_hi, void* t_lo,
+                       int planes, void* stream);
+
+/* dw[m][n][g] (the reference's OIHW float32, g = r*3+s or 1) = scale * sum over splits of parts[g][s][m][n], m < M;
+ * parts slabs have M_parts >= M rows of ld floats. */
+int frcnn_wgrad_reduce(const float* parts, int groups, int splits, int M_parts, int M, int ld, int N, float scale, float* dw,
+                       void* stream);
+
+/* db[c] = scale * sum over k of (t_hi + t_lo)[c][k] -- the bias gradient from the transposed dY. */
+int frcnn_bias_grad(const void* t_hi, const void* t_lo, int C, long Kp, float scale, float* db, void* stream);
+
+/* chainer.optimizer.WeightDecay(rate) hook + optimizers.MomentumSGD(lr, momentum) (train_rpn.py:165-167) on float32
+ * master weights: g' = g + rate*w; v = momentum*v - lr*g'; w += v. */
+int frcnn_sgd_momentum(float* w, float* v, const float* g, long n, float lr, float momentum, float weight_decay, void* stream);
+
+/* Weights of the data-gradient convolution: out[t][ci][co] = W[co][ci][kh-1-r][kw-1-s] (t = r*kw+s), bf16 hi/lo, co
+ * zero-padded to Cout_pad -- feed to frcnn_conv2d with Cin := Cout_pad, Cout := Cin. */
+int frcnn_pack_conv_weights_dgrad(const float* w_oihw, int Cout, int Cin, int kh, int kw, int Cout_pad, void* w_hi, void* w_lo,
+                                  void* stream);
+
 /* Profiling hook (not part of the drop-in surface): a device buffer of 8 int64 that receives the
  * per-phase clock64() stamps of subsequent top-k sort launches; NULL disables. */
 void frcnn_debug_sort_clocks(long long* dev_buf);

@@ -341,6 +341,54 @@ def rpn_loss_bbox(rpn_bbox_pred, targets, inds_inside, A, delta=3.0):
     return loss, g.astype(f32)
 
 
+def rpn_train_step(params, x, labels, targets, inds_inside, lr=0.001, momentum=0.9, weight_decay=0.0005, velocity=None,
+                   loss_lambda=1.0, delta=3.0, A=9, dtype="float64"):
+    """One train_rpn.py update in RPN mode (train_rpn.py:165-174; models/faster_rcnn.py:114-116;
+    models/region_proposal_network.py:117-156), restated with torch-CPU autograd standing in for Chainer's backward
+    (UNPINNED: Chainer is absent; conv / ReLU / ceil-mode max-pool / softmax-CE / Huber gradients are the textbook ones,
+    max-pool routes to the first maximum).  labels / targets / inds_inside: an AnchorTargetLayer result (pinned).
+    dtype "float64" gives a rounding-free reference for the device's tolerance; "float32" is what Chainer computes in.
+    Returns dict(losses=(cls, bbox, acc, total), grads={name: ndarray}, params={...}, velocity={...}) for the trainable
+    parameters (trunk/*, RPN/*).  Update rule: g += weight_decay*w (WeightDecay hook); v = momentum*v - lr*g; w += v."""
+    import torch
+    import torch.nn.functional as F
+    td = torch.float64 if dtype == "float64" else torch.float32
+    names = [k for k in params if k.startswith("trunk/") or k.startswith("RPN/")]
+    P = {k: torch.tensor(np.asarray(params[k]), dtype=td, requires_grad=True) for k in names}
+    h = torch.tensor(np.asarray(x), dtype=td)
+    for item in VGG16_LAYERS:
+        if item == "pool":
+            h = F.max_pool2d(h, 2, 2, ceil_mode=True)
+        else:
+            h = F.relu(F.conv2d(h, P["trunk/%s/W" % item[0]], P["trunk/%s/b" % item[0]], padding=1))
+    mid = F.relu(F.conv2d(h, P["RPN/rpn_conv_3x3/W"], P["RPN/rpn_conv_3x3/b"], padding=1))
+    score = F.conv2d(mid, P["RPN/rpn_cls_score/W"], P["RPN/rpn_cls_score/b"])
+    pred = F.conv2d(mid, P["RPN/rpn_bbox_pred/W"], P["RPN/rpn_bbox_pred/b"])
+    _, _, fh, fw = score.shape
+    n_all = A * fh * fw
+    t = torch.from_numpy(rpn_labels_mapped(labels, inds_inside, n_all, A, fh, fw)).long()
+    z = score.reshape(1, 2, A, fh, fw)
+    valid = t != -1
+    loss_cls = F.cross_entropy(z, t, ignore_index=-1) if bool(valid.any()) else z.sum() * 0
+    acc = float((z.argmax(1)[valid] == t[valid]).double().mean()) if bool(valid.any()) else 0.0
+    p4 = pred.reshape(4, A, -1).permute(2, 1, 0).reshape(-1, 4)
+    sel = p4[torch.from_numpy(np.asarray(inds_inside, dtype=np.int64))]
+    loss_bbox = F.huber_loss(sel, torch.tensor(np.asarray(targets), dtype=td), reduction="sum", delta=float(delta)) / p4.shape[0]
+    loss = loss_cls + loss_lambda * loss_bbox
+    loss.backward()
+    grads = {k: P[k].grad.detach().numpy().astype(np.float64) for k in names}
+    vel = {k: (np.zeros_like(grads[k]) if velocity is None else np.asarray(velocity[k], np.float64)) for k in names}
+    new_p, new_v = {}, {}
+    for k in names:
+        w = np.asarray(params[k], np.float64)
+        g = grads[k] + weight_decay * w
+        v = momentum * vel[k] - lr * g
+        new_v[k] = v
+        new_p[k] = w + v
+    return dict(losses=(float(loss_cls.detach()), float(loss_bbox.detach()), acc, float(loss.detach())), grads=grads,
+                params=new_p, velocity=new_v)
+
+
 # --------------------------------------------------------------------------- ProposalLayer
 RPN_NMS_THRESH = 0.7                 # models/proposal_layer.py:51
 TRAIN_PRE, TRAIN_POST = 12000, 2000  # :52-53

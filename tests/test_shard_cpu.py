@@ -19,6 +19,10 @@ def _worker(rank, world, port, q):
         t = shard.max_over_ranks(1.0 + rank)                       # slowest rank decides
         counts = shard.gather_ints(100 + rank)
         thr = shard.aggregate_throughput(10, 1.0 + rank)
+        # the training path's one collective: SUM of the flat gradient bucket, identical on every rank afterwards
+        g = torch.arange(6, dtype=torch.float32) * (rank + 1)
+        shard.allreduce_sum_(g)
+        assert torch.equal(g, torch.arange(6, dtype=torch.float32) * 3)
         dist.barrier()
         q.put((rank, mine, t, counts, thr, shard.image_seed(rank, 3)))
     finally:
@@ -47,6 +51,8 @@ def test_single_process_fallbacks():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "chainer-faster-rcnn_b200"))
     from frcnn_b200 import shard
     assert shard.max_over_ranks(3.5) == 3.5 and shard.gather_ints(7) == [7]
+    g = torch.ones(3)
+    assert shard.allreduce_sum_(g) is g and torch.equal(g, torch.ones(3))
     assert shard.shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]
     with pytest.raises(ValueError):
         shard.shard_indices(5, 2, 2)

@@ -352,3 +352,153 @@ def test_gemm_nt_splitk_matches_float64(tops, M, N, K, groups, splits, x3):
     pi = tops.gemm_nt_splitk(Ai.to(torch.bfloat16), None, Bi.to(torch.bfloat16), None, groups=groups, row_stride=row_stride,
                              splits=splits)
     assert torch.equal(pi[..., :N].double(), _ref_gemm_parts(Ai.double(), Bi.double(), groups, row_stride, pi.shape[1], K))
+
+
+# ------------------------------------------------------------------ the whole train_rpn.py step
+def _train_case(H, W, seed):
+    rng = np.random.default_rng(seed)
+    params = orc.make_params(seed=77)
+    for k in ("RPN/rpn_cls_score/W", "RPN/rpn_bbox_pred/W"):       # livelier heads than N(0, 0.01): every gradient path is exercised
+        params[k] = (rng.standard_normal(params[k].shape) * 0.05).astype(f32)
+    for k in params:
+        if k.endswith("/b") and (k.startswith("trunk/") or k.startswith("RPN/")):
+            params[k] = (rng.standard_normal(params[k].shape) * 0.05).astype(f32)
+    x = orc.make_image(H, W, seed=seed)
+    fh, fw = -(-H // 16), -(-W // 16)
+    gt = np.array([[[20, 30, 150, 170, 3], [100, 20, 330, 240, 7], [200, 150, 300, 280, 1]]], f32)
+    gt[..., [0, 2]] = np.clip(gt[..., [0, 2]], 0, W - 1)
+    gt[..., [1, 3]] = np.clip(gt[..., [1, 3]], 0, H - 1)
+    info = np.array([[H, W]], np.int32)
+    return params, x, gt, info
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _route_reference(g_in, y, p):
+    """numpy restatement of frcnn_grad_prepare on the device's own tensors: max-pool routing to the first maximum of the
+    2x2 ceil-mode window (when p is given) and the ReLU mask.  All (C,H,W) float32."""
+    C, H, W = y.shape
+    if p is None:
+        v = g_in.copy()
+    else:
+        v = np.zeros_like(y)
+        taken = np.zeros(p.shape, bool)
+        for e in range(4):                                   # scan order (0,0),(0,1),(1,0),(1,1)
+            dh, dw = e >> 1, e & 1
+            ys = y[:, dh::2, dw::2]
+            hh, ww = ys.shape[1:]
+            hit = (ys == p[:, :hh, :ww]) & ~taken[:, :hh, :ww]
+            v[:, dh::2, dw::2] = np.where(hit, g_in[:, :hh, :ww], 0)
+            taken[:, :hh, :ww] |= hit
+    return np.where(y > 0, v, 0).astype(f32)
+
+
+def test_rpn_train_step_layerwise_and_end_to_end():
+    """The whole train_rpn.py step: forward + AnchorTargetLayer + losses + backward (15 convs: weight gradient, data
+    gradient, ReLU / max-pool backward) + WeightDecay + MomentumSGD.
+
+    ReLU and max-pool make the end-to-end gradient DISCONTINUOUS in the forward activations: one pre-activation whose
+    sign differs between two correct implementations changes every upstream gradient by ~1e-3 of its max-norm (the
+    float32 and float64 runs of the oracle itself differ by 4e-4 from conv3_3 down for exactly this reason).  So:
+      (1) layer by layer, on the DEVICE's own tensors: the masked/routed gradient is exactly the restated rule, and each
+          layer's dW / db / dX match float64 conv gradients of the same inputs within 5e-5 of max-norm (continuous
+          functions: bf16x3 precision only);
+      (2) end to end against the float64 autograd oracle: losses 1e-4, every gradient within 1e-2 of max-norm (flips),
+          and the optimizer update rule over two steps (momentum)."""
+    from frcnn_b200.train_engine import RpnTrainer
+    import torch.nn.grad as tg
+    H, W = 296, 392                        # ragged pooled sizes: 296->148->74->37->19, 392->196->98->49->25
+    params, x, gt, info = _train_case(H, W, 3)
+    tr = RpnTrainer(params, H, W, ANCHORS, precision="bf16x3", subsample="none")
+    losses = tr.forward(_dev(x[0]), _dev(gt[0]))
+    dbg = {}
+    tr.backward(debug=dbg)
+    torch.cuda.synchronize()
+    # ---- (1) layer-wise, float64 on the device's own activations / gradients
+    f64 = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    worst_w = worst_x = 0.0
+    for i, L in enumerate(tr.layers):
+        name = L["name"]
+        d = dbg[name]
+        y = L["y"].to_chw_f32().cpu().numpy()
+        p = L["p"].to_chw_f32().cpu().numpy() if L["pool"] else None
+        want_dy = _route_reference(d["g_in"].cpu().numpy(), y, p)
+        assert np.array_equal(d["dy"].cpu().numpy(), want_dy), name                       # exact: routing + mask
+        dy = f64(d["dy"].cpu().numpy())[None]
+        Wt = f64(params[name + "/W"])
+        if i == 0:
+            xin = f64(x)                                                                  # conv1_1 sees the image itself
+        else:
+            xin = f64(tr._input_of(L).to_chw_f32().cpu().numpy())[None]
+        dw_ref = tg.conv2d_weight(xin, Wt.shape, dy, padding=1).numpy()
+        e_w = _rel(tr.grads(name + "/W").cpu().numpy(), dw_ref)
+        e_b = _rel(tr.grads(name + "/b").cpu().numpy(), dy.sum((0, 2, 3)).numpy())
+        e_x = 0.0
+        if i > 0:
+            dx_ref = tg.conv2d_input(xin.shape, Wt, dy, padding=1).numpy()[0]
+            e_x = _rel(d["g_out"].cpu().numpy(), dx_ref)
+        print("  %-22s dW %.2e  db %.2e  dX %.2e" % (name, e_w, e_b, e_x))
+        worst_w, worst_x = max(worst_w, e_w, e_b), max(worst_x, e_x)
+    # twin heads (1x1): dY is the loss kernel's gradient itself
+    dyh = f64(dbg["heads"]["dy"].cpu().numpy())[None][:, :54]
+    mid = f64(tr.layers[13]["y"].to_chw_f32().cpu().numpy())[None]
+    Wh = f64(np.concatenate([params["RPN/rpn_cls_score/W"], params["RPN/rpn_bbox_pred/W"]], 0))
+    dwh = tg.conv2d_weight(mid, Wh.shape, dyh).numpy()
+    got_wh = np.concatenate([tr.grads("RPN/rpn_cls_score/W").cpu().numpy(), tr.grads("RPN/rpn_bbox_pred/W").cpu().numpy()], 0)
+    got_bh = np.concatenate([tr.grads("RPN/rpn_cls_score/b").cpu().numpy(), tr.grads("RPN/rpn_bbox_pred/b").cpu().numpy()], 0)
+    e_w, e_b = _rel(got_wh, dwh), _rel(got_bh, dyh.sum((0, 2, 3)).numpy())
+    e_x = _rel(dbg["heads"]["g_out"].cpu().numpy(), tg.conv2d_input(mid.shape, Wh, dyh).numpy()[0])
+    print("  %-22s dW %.2e  db %.2e  dX %.2e" % ("RPN heads", e_w, e_b, e_x))
+    worst_w, worst_x = max(worst_w, e_w, e_b), max(worst_x, e_x)
+    print("layer-wise worst: dW/db %.2e, dX %.2e" % (worst_w, worst_x))
+    assert worst_w <= 5e-5 and worst_x <= 5e-5
+    # ---- (2) end to end
+    n_in = int(tr.targets.counts[0].item())
+    inds = tr.targets.inds_inside[:n_in].cpu().numpy().astype(np.int64)
+    labels = tr.targets.labels_full.cpu().numpy()[inds]
+    targets = tr.targets.targets_full.cpu().numpy()[inds]
+    r = orc.anchor_target_layer(tr.fh, tr.fw, gt, info, choice=lambda a, n: a[:0])
+    assert np.array_equal(labels, r["labels_before_subsample"]) and np.array_equal(inds, r["inds_inside"])
+    want = orc.rpn_train_step(params, x, labels, targets, inds)
+    Lv = losses.cpu().numpy()
+    print("losses", Lv, "oracle", want["losses"])
+    assert abs(Lv[0] - want["losses"][0]) <= 1e-4 * max(1.0, want["losses"][0])
+    assert abs(Lv[1] - want["losses"][1]) <= 1e-4 * max(1e-2, want["losses"][1])
+    assert abs(Lv[3] - want["losses"][3]) <= 1e-4 * max(1.0, want["losses"][3])
+    worst = 0.0
+    for name in tr.index:
+        e = _rel(tr.grads(name).cpu().numpy(), want["grads"][name])
+        worst = max(worst, e)
+        assert np.abs(want["grads"][name]).max() > 0, name            # every trainable tensor receives a gradient
+    print("end-to-end worst gradient error (of max-norm): %.2e" % worst)
+    assert worst <= 1e-2
+    # optimizer: the update applied to the DEVICE's gradient is the reference rule, exactly (fp32 ops in the same order)
+    g_dev = {k: tr.grads(k).cpu().numpy().copy() for k in tr.index}
+    tr.update()
+    lr, mom, wd = f32(0.001), f32(0.9), f32(0.0005)
+    v1 = {}
+    for name in tr.index:
+        w0 = params[name].astype(f32)
+        gi = (wd * w0 + g_dev[name]).astype(f32)             # fma in the kernel: compare with a 1-ulp allowance below
+        v = (mom * f32(0) - lr * gi).astype(f32)
+        v1[name] = v
+        np.testing.assert_allclose(tr.weights(name).cpu().numpy(), (w0 + v).astype(f32), rtol=3e-7, atol=1e-10)
+        np.testing.assert_allclose(tr.view(tr.v_flat, name).cpu().numpy(), v, rtol=2e-6, atol=1e-12)
+    # second step: momentum buffer in play
+    p1 = {k: tr.weights(k).cpu().numpy().copy() for k in tr.index}
+    vd = {k: tr.view(tr.v_flat, k).cpu().numpy().copy() for k in tr.index}
+    tr.forward(_dev(x[0]), _dev(gt[0]))
+    tr.backward()
+    g2 = {k: tr.grads(k).cpu().numpy().copy() for k in tr.index}
+    tr.update()
+    for name in tr.index:
+        gi = (wd * p1[name] + g2[name]).astype(f32)
+        v = (mom * vd[name] - lr * gi).astype(f32)
+        np.testing.assert_allclose(tr.weights(name).cpu().numpy(), (p1[name] + v).astype(f32), rtol=3e-7, atol=1e-10)
+    # and the loss went down on the same image
+    l3 = tr.forward(_dev(x[0]), _dev(gt[0])).cpu().numpy()
+    print("loss after 0/2 updates: %.5f -> %.5f" % (Lv[3], l3[3]))
+    assert l3[3] < Lv[3]
