@@ -171,20 +171,63 @@ __device__ int block_sum(int v, int* s_warp) {           // all threads get the 
     return t;
 }
 
-// Disable (label := -1) the n_dis entries with label == which that have the smallest sample_key.
+// Disable (label := -1) the n_dis entries with label == which that have the smallest sample_key (hash, then index).
+// Every thread caches the 32-bit hashes of the (at most KEYS_PER_THREAD) anchors it owns in registers, so the threshold
+// search touches no memory: 32 steps on the hash, then -- only among hash ties at the threshold -- 32 steps on the index.
+constexpr int KEYS_PER_THREAD = 40;          // 1024 threads x 40 = 40,960 anchors (an 800x1333 map has 37,800)
+
+__device__ __forceinline__ uint32_t sample_hash(unsigned long long seed, int i) { return (uint32_t)(sample_key(seed, i) >> 32); }
+
 __device__ void disable_smallest(int* labels, int n_all, int which, int n_dis, unsigned long long seed, int* s_warp) {
     if (n_dis <= 0) return;
-    unsigned long long T = 0;                 // largest x with |{key < x}| <= n_dis  ==> exactly n_dis keys are < T (keys unique)
-    for (int bit = 63; bit >= 0; --bit) {
-        unsigned long long cand = T | (1ull << bit);
+    const bool cached = n_all <= KEYS_PER_THREAD * (int)blockDim.x;
+    uint32_t hs[KEYS_PER_THREAD];
+    unsigned long long valid = 0;             // bit j: owned element j is a candidate (label == which)
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < KEYS_PER_THREAD; ++j) {
+            const int i = threadIdx.x + j * blockDim.x;
+            const bool c = i < n_all && labels[i] == which;
+            hs[j] = c ? sample_hash(seed, i) : 0u;
+            valid |= (unsigned long long)(c ? 1 : 0) << j;
+        }
+    }
+    // T = largest x in [0, 2^32] with |{hash < x}| <= n_dis
+    unsigned long long T = 0;
+    for (int bit = 32; bit >= 0; --bit) {
+        const unsigned long long cand = T | (1ull << bit);
+        if (cand > 0x100000000ull) continue;
         int c = 0;
-        for (int i = threadIdx.x; i < n_all; i += blockDim.x)
-            c += (labels[i] == which && sample_key(seed, i) < cand) ? 1 : 0;
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < KEYS_PER_THREAD; ++j) c += (((valid >> j) & 1ull) != 0 && (unsigned long long)hs[j] < cand) ? 1 : 0;
+        } else {
+            for (int i = threadIdx.x; i < n_all; i += blockDim.x)
+                c += (labels[i] == which && (unsigned long long)sample_hash(seed, i) < cand) ? 1 : 0;
+        }
         if (block_sum(c, s_warp) <= n_dis) T = cand;
     }
-    __syncthreads();
+    // everything with hash < T goes; r more among hash == T (almost always a single element), lowest indices first
+    int c = 0;
     for (int i = threadIdx.x; i < n_all; i += blockDim.x)
-        if (labels[i] == which && sample_key(seed, i) < T) labels[i] = -1;
+        c += (labels[i] == which && (unsigned long long)sample_hash(seed, i) < T) ? 1 : 0;
+    const int r = n_dis - block_sum(c, s_warp);
+    unsigned long long Y = 0;                 // largest y with |{hash == T, index < y}| <= r
+    if (r > 0) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned long long cand = Y | (1ull << bit);
+            int e = 0;
+            for (int i = threadIdx.x; i < n_all; i += blockDim.x)
+                e += (labels[i] == which && (unsigned long long)sample_hash(seed, i) == T && (unsigned long long)i < cand) ? 1 : 0;
+            if (block_sum(e, s_warp) <= r) Y = cand;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+        if (labels[i] != which) continue;
+        const unsigned long long h = sample_hash(seed, i);
+        if (h < T || (h == T && (unsigned long long)i < Y)) labels[i] = -1;
+    }
     __syncthreads();
 }
 

@@ -142,17 +142,38 @@ __global__ void __launch_bounds__(256) grad_prepare_kernel(PrepArgs a) {
     }
     if (a.t_hi == nullptr) return;
     __syncthreads();
+    // transposed stores: a channel row of this tile is <= 64 consecutive k positions starting at q0 - shift; they are
+    // written as 16-byte vectors on the 8-element-aligned groups that lie fully inside the row, element-wise at the ends.
     const int warp = t >> 5, lane = t & 31;
     const long q0 = (long)(h + 1) * a.Wp + (w0 + 1);
+    const int n = min(TP, a.W - w0);                 // valid pixels of this tile
+    const int rsub = lane >> 3, gl = lane & 7;       // 4 channel rows per warp pass, 8 lanes per row
     for (int pl = 0; pl < a.planes; ++pl) {
         const int shift = a.planes == 3 ? pl - 1 : 0;                // plane pl at k holds the operand at k + pl - 1
-        for (int ch = warp; ch < TC; ch += 8) {
-            if (c0 + ch >= a.C) break;
+        const long d0 = q0 - shift;                                  // destination of pixel 0
+        const long g0 = d0 & ~7l;                                    // first aligned group
+        for (int ch = warp * 4 + rsub; ch < TC; ch += 32) {
+            if (c0 + ch >= a.C) continue;
             const long row = ((long)pl * a.C + c0 + ch) * a.Kp;
-            for (int px = lane; px < TP; px += 32) {
-                if (w0 + px < a.W) {
-                    a.t_hi[row + q0 + px - shift] = s_hi[ch][px];
-                    if (a.t_lo) a.t_lo[row + q0 + px - shift] = s_lo[ch][px];
+            for (int grp = gl; grp < 9; grp += 8) {
+                const long k0 = g0 + 8 * grp;
+                const int px0 = (int)(k0 - d0);                      // pixel of the group's first element (may be < 0)
+                if (px0 >= n || px0 + 8 <= 0) continue;
+                if (px0 >= 0 && px0 + 8 <= n) {
+                    __align__(16) __nv_bfloat16 vh[8];
+                    __align__(16) __nv_bfloat16 vl[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { vh[e] = s_hi[ch][px0 + e]; vl[e] = s_lo[ch][px0 + e]; }
+                    *reinterpret_cast<uint4*>(a.t_hi + row + k0) = *reinterpret_cast<const uint4*>(vh);
+                    if (a.t_lo) *reinterpret_cast<uint4*>(a.t_lo + row + k0) = *reinterpret_cast<const uint4*>(vl);
+                } else {
+                    for (int e = 0; e < 8; ++e) {
+                        const int px = px0 + e;
+                        if (px >= 0 && px < n) {
+                            a.t_hi[row + k0 + e] = s_hi[ch][px];
+                            if (a.t_lo) a.t_lo[row + k0 + e] = s_lo[ch][px];
+                        }
+                    }
                 }
             }
         }
