@@ -430,6 +430,71 @@ def run_b200_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_train_arm(args, rank, local_rank, world):
+    """Secondary workload (BASELINE config #5, a "next" row): one train_rpn.py step per image -- forward, AnchorTargetLayer,
+    RPN losses, backward through 15 convs, gradient all-reduce over the ranks, WeightDecay + MomentumSGD.  Not the headline."""
+    import torch
+    import frcnn_oracle as orc
+    from frcnn_b200 import shard
+    from frcnn_b200.train_engine import RpnTrainer
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+    params = orc.make_params(seed=1234)
+    tr = RpnTrainer(params, H_IMG, W_IMG, anchors, precision=args.precision, subsample="device")
+    imgs = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=shard.image_seed(rank, i))[0]).cuda() for i in range(4)]
+    gt = torch.tensor([[100, 120, 400, 380, 3], [500, 200, 900, 560, 7], [50, 50, 200, 180, 1], [600, 30, 780, 150, 5]],
+                      dtype=torch.float32).cuda()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for i in range(max(args.warmup, 3)):
+        tr.step(imgs[i % 4], gt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        tr.step(imgs[i % 4], gt)
+    e1.record()
+    barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    losses = [float(v) for v in tr.last_losses.cpu().numpy()]
+    if rank == 0:
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = pick_cpu_threads(torch)
+            x = orc.make_image(H_IMG, W_IMG, seed=0)
+            info = np.array([[H_IMG, W_IMG]], np.int32)
+            t0 = time.perf_counter()
+            r = orc.anchor_target_layer(38, 63, gt.cpu().numpy()[None], info, choice=lambda a, n: np.asarray(a)[:n])
+            orc.rpn_train_step(params, x, r["labels"], r["targets"], r["inds_inside"], dtype="float32")
+            tt = time.perf_counter() - t0
+            cpu_baseline = {"value": 1.0 / tt, "unit": "images/s", "cores": cores, "kind": "port",
+                            "sample": "1 step, 600x1000: AnchorTargetLayer restatement + torch-CPU fp32 autograd standing in for "
+                                      "Chainer's backward (%.1f s)" % tt}
+        print(json.dumps({
+            "metric": "images/sec through the train_rpn.py step (forward + AnchorTargetLayer + RPN loss + backward + MomentumSGD) @600x1000",
+            "value": world * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "train_rpn.py step, VGG16 trunk + RPN trainable, one 600x1000 image per GPU per step, "
+                                   "all-reduce(SUM) of the flat fp32 gradient bucket (config #5; secondary workload)",
+                       "last_losses_cls_bbox_acc_total": losses},
+            "clocks": clocks, "cpu_baseline": cpu_baseline}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,6 +504,8 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn"],
+                    help="forward = the headline metric (default); train_rpn = the secondary training-step workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -451,6 +518,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.workload == "train_rpn":
+        run_train_arm(args, rank, local_rank, world)
+        return
     run_b200_arm(args, rank, local_rank, world)
 
 
