@@ -203,6 +203,9 @@ def conv_layer_table(plan, torch, reps=3):
 
     def timed(x, w_hi, w_lo, bias, ksize, relu, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # a ~150 us spin kernel first: while the GPU spins, the host enqueues e0 + the conv launch + e1, so the interval
+        # between the events is the kernel's execution alone (no host launch latency inside it, even on a slow host)
+        torch.cuda._sleep(300000)
         e0.record()
         r = orig(x, w_hi, w_lo, bias, ksize, relu, **kw)
         e1.record()

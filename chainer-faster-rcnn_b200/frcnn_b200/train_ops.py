@@ -119,6 +119,16 @@ def split_bf16(x):
     return hi, lo
 
 
+_ZERO_BIAS = {}
+
+
+def _zero_bias(device, n):
+    z = _ZERO_BIAS.get(device)
+    if z is None or z.numel() < n:
+        z = _ZERO_BIAS[device] = torch.zeros((max(n, 1024),), dtype=torch.float32, device=device)
+    return z
+
+
 def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
     """frcnn_gemm_nt_splitk: A [M,K]; B [N,K] (groups=1) or [3,N,K] pre-shifted planes (groups=9); bf16 planes (lo may
     be None for both) -> parts [groups, S, M, ld] fp32, ld = N rounded up to 32.  See include/frcnn_b200.h."""
@@ -132,7 +142,7 @@ def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
     S = lib.frcnn_gemm_nt_splitk_splits(K, int(splits))
     ld = (N + 31) // 32 * 32
     parts = torch.empty((groups, S, M, ld), dtype=torch.float32, device=a_hi.device)
-    zero = torch.zeros((max(ld, 256),), dtype=torch.float32, device=a_hi.device)
+    zero = _zero_bias(a_hi.device, ld)
     check(lib.frcnn_gemm_nt_splitk(_p(a_hi), _p(a_lo), M, K, _p(b_hi), _p(b_lo), N, int(groups), int(row_stride), int(splits),
                                    _p(zero), _p(parts), ld, _stream()), "frcnn_gemm_nt_splitk")
     return parts
