@@ -43,11 +43,17 @@ struct ConvParams {
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
     int num_stages, a_stages, x3, relu, pool;
     int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
+    // long-K GEMMs (fc6: K = 25,088 .. 100,352): the tensor core's fp32 accumulator truncates on every add, an error that
+    // grows with the number of adds x the accumulator's magnitude.  The k-blocks rotate over `nacc` main accumulators
+    // (acc_chunk blocks each turn; accumulator a >= 1 sits behind the correction accumulator), summed once in the epilogue with
+    // round-to-nearest adds: nacc-fold smaller bias.  nacc == 1: the ordinary single accumulator.
+    int nacc, acc_chunk;
     int ld_f32, n_cover;
     int store_bf16, store_lo;            // bf16 outputs go through the staged TMA store
     float* y_f32;
     const float* bias;
     const int* m_valid;
+    const __nv_bfloat16 *res_hi, *res_lo;   // optional residual [H][W][Cout] (hi + lo) added before the ReLU (ResNet shortcut)
     // split-K GEMM mode (frcnn_gemm_nt_splitk, per-tap path only): the tile space is n_parts x tiles_per_part,
     // part = group * splits + split; a split covers k-blocks [split*kb_per_split, ...) of kb_total; group g shifts
     // the B operand's K coordinate by (g/3-1)*g_row_stride and reads plane g%3 of B (the 3x3 taps of a padded pixel
@@ -322,10 +328,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const uint32_t st = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
                     const uint64_t a_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
                     const uint64_t b_hi = ptx::make_smem_desc(st + C::A_BYTES, C::ROW_BYTES);
+                    const int turn = kb / p.acc_chunk, ai = turn % p.nacc;
+                    const uint32_t d_main = d_tmem + (uint32_t)(ai == 0 ? 0 : (ai + (p.x3 ? 1 : 0)) * BN);
+                    const bool fresh = turn < p.nacc && kb == turn * p.acc_chunk;     // first k-block into this accumulator
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle span: +2 in (addr>>4)
-                        mma_ss<CG>(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                        mma_ss<CG>(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, !(fresh && k == 0));
                     }
                     if (p.x3) {
                         const uint64_t a_lo = ptx::make_smem_desc(st + C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
@@ -386,6 +395,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
                 }
+                for (int a = 1; a < p.nacc; ++a) {            // rotated main accumulators of a long-K GEMM
+                    ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)((a + (p.x3 ? 1 : 0)) * BN), r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
                 const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -394,6 +409,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     v[4 * j + 1] += b.y;
                     v[4 * j + 2] += b.z;
                     v[4 * j + 3] += b.w;
+                }
+                if (p.res_hi != nullptr && in_img && n < p.Cout) {
+                    // residual add (h + shortcut) of a bottleneck block, fused ahead of the ReLU
+                    const long ro = pix * p.Cout + n;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + ro) + q);
+                        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&rh);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[8 * q + j] += __bfloat162float(hb[j]);
+                        if (p.res_lo != nullptr) {
+                            const uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_lo + ro) + q);
+                            const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&rl);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 * q + j] += __bfloat162float(lb[j]);
+                        }
+                    }
                 }
                 if (p.relu) {
 #pragma unroll
@@ -565,6 +597,18 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     p.a_stages = a_stages;
     const size_t smem = (size_t)stages * stage_bytes + a_bytes + fixed;
     p.acc_cols = p.x3 ? 2 * BN : BN;
+    // long K (>= 256 k-blocks of 64, not a split-K part, per-tap path): rotate over up to 3 main accumulators
+    p.nacc = 1;
+    p.acc_chunk = 1 << 30;
+    if (!HALO && p.n_parts == 1 && p.taps * p.cin_blocks >= 256) {
+        int nacc = 3;
+        while (nacc > 1 && (p.acc_cols + (nacc - 1) * BN > 512)) --nacc;
+        if (nacc > 1) {
+            p.nacc = nacc;
+            p.acc_chunk = 8;
+            p.acc_cols += (nacc - 1) * BN;
+        }
+    }
     p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_bufs * p.acc_cols) p.tmem_cols *= 2;
@@ -606,12 +650,15 @@ struct GemmExtra {          // split-K GEMM mode of the same kernel (frcnn_gemm_
     int groups, row_stride, splits;
     long part_stride;
 };
+struct ResExtra {           // residual input of frcnn_conv2d_res
+    const void *hi, *lo;
+};
 }  // namespace
 
 static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
                        const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
                        void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_,
-                       const GemmExtra* ge) {
+                       const GemmExtra* ge, const ResExtra* re = nullptr) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(x_hi && w_hi && bias, "frcnn_conv2d: x_hi, w_hi and bias are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
@@ -711,6 +758,9 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     p.y_f32 = y_f32;
     p.bias = bias;
     p.m_valid = m_valid;
+    p.res_hi = re ? (const __nv_bfloat16*)re->hi : nullptr;
+    p.res_lo = re ? (const __nv_bfloat16*)re->lo : nullptr;
+    FRCNN_REQUIRE(!re || (re->hi && !fuse_pool2x2 && Cout % 32 == 0), "frcnn_conv2d_res: residual needs res_hi, Cout %% 32 == 0 and no fused pool");
     p.acc_bufs = p.acc_cols = p.tmem_cols = 0;
 
     CUtensorMap tm[6];
@@ -769,6 +819,14 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
                             void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
     return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, fuse_pool2x2, y_hi, y_lo, y_f32, ld_f32,
                        m_valid, stream_, nullptr);
+}
+
+extern "C" int frcnn_conv2d_res(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                                const float* bias, int Cout, int ksize, int relu, const void* res_hi, const void* res_lo,
+                                void* y_hi, void* y_lo, void* stream_) {
+    ResExtra re{res_hi, res_lo};
+    return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, 0, y_hi, y_lo, nullptr, 0, nullptr, stream_,
+                       nullptr, &re);
 }
 
 extern "C" int frcnn_gemm_nt_splitk_splits(int K, int splits) {

@@ -52,18 +52,7 @@ class PackedWeights(object):
         self.num_classes, self.n_anchors = num_classes, n_anchors
         P = lambda k: _t(params[k], device)
         self.convs = {}
-        for item in VGG16_LAYERS:
-            if item == "pool":
-                continue
-            name, cin, cout = item
-            w = P("trunk/%s/W" % name)
-            if cin <= 3:
-                # first layer as a K=32 GEMM over the im2col-packed image (ops.pack_image_im2col)
-                hi, lo = ops.pack_conv_weights_im2col(w, precision=precision)
-                b = P("trunk/%s/b" % name)
-                self.convs[name] = (hi, lo, ops.pad_bias(b, b.numel()))
-            else:
-                self.convs[name] = self._pack(w, P("trunk/%s/b" % name), cin_pad=cin)
+        self._pack_trunk(params, P)
         self.rpn3 = self._pack(P("RPN/rpn_conv_3x3/W"), P("RPN/rpn_conv_3x3/b"))
         # twin 1x1 heads merged along Cout: rows [0,2A) = rpn_cls_score, [2A,6A) = rpn_bbox_pred
         wh = torch.cat([P("RPN/rpn_cls_score/W"), P("RPN/rpn_bbox_pred/W")], dim=0)
@@ -77,6 +66,21 @@ class PackedWeights(object):
         self.head_ld = ops.round_up(5 * num_classes, 32)
         self.head = self._pack(wc, bc, n_bias=self.head_ld)
         torch.cuda.synchronize(device)
+
+    def _pack_trunk(self, params, P):
+        """VGG16 (models/vgg16.py:38-69); subclasses pack another trunk (resnet_engine.ResNetPackedWeights)."""
+        for item in VGG16_LAYERS:
+            if item == "pool":
+                continue
+            name, cin, cout = item
+            w = P("trunk/%s/W" % name)
+            if cin <= 3:
+                # first layer as a K=32 GEMM over the im2col-packed image (ops.pack_image_im2col)
+                hi, lo = ops.pack_conv_weights_im2col(w, precision=self.precision)
+                b = P("trunk/%s/b" % name)
+                self.convs[name] = (hi, lo, ops.pad_bias(b, b.numel()))
+            else:
+                self.convs[name] = self._pack(w, P("trunk/%s/b" % name), cin_pad=cin)
 
     def _pack(self, w, b, cin_pad=None, perm_chw=None, n_bias=0):
         hi, lo = ops.pack_conv_weights(w, cin_pad=cin_pad, precision=self.precision, perm_chw=perm_chw)
@@ -108,6 +112,29 @@ class ForwardPlan(object):
 
         self.x_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)      # static input (C,H,W)
         self.img_info = torch.tensor([H, W], dtype=torch.int32, device=dev)      # clip bounds (h, w): static in the graph
+        self._act = act
+        self.fuse_pool = fuse_pool
+        h, w_ = self._alloc_trunk(H, W)
+        self.fh, self.fw = h, w_
+        self.rpn_mid = act(h, w_, weights.rpn3[0].shape[1])
+        self.rpn_out = torch.empty((h * w_, weights.rpn_ld), dtype=torch.float32, device=dev)
+        self.prop = ops.ProposalWorkspace(A, h, w_, pre_n, post_n, dev, debug=keep_rpn_debug)
+        C = self.acts[-1].hi.shape[2]
+        self.pool5 = act(1, post_n, 49 * C)
+        self.fc6 = act(1, post_n, 4096)
+        self.fc7 = act(1, post_n, 4096)
+        self.head_out = torch.empty((post_n, weights.head_ld), dtype=torch.float32, device=dev)
+        self.prob = torch.zeros((post_n, weights.num_classes), dtype=torch.float32, device=dev)
+        self.boxes = torch.zeros((post_n, 4 * weights.num_classes), dtype=torch.float32, device=dev)
+        self.det = None
+        self.graph = None
+        self.use_graph = use_graph
+        self.im_h, self.im_w = H, W
+        self.n_launches = 0
+
+    def _alloc_trunk(self, H, W):
+        """VGG16 activations; returns the feature-map size.  (resnet_engine.ResNetForwardPlan overrides both trunk hooks.)"""
+        act, fuse_pool = self._act, self.fuse_pool
         self.acts = [act(H, W, 32)]          # im2col-packed image: 27 taps*channels + 5 zeros per pixel
         h, w_ = H, W
         self.trunk_steps = []          # (layer name, fuse the following 2x2 pool into the conv epilogue)
@@ -126,28 +153,12 @@ class ForwardPlan(object):
                 if pooled:
                     h, w_ = (h + 1) // 2, (w_ + 1) // 2
                     self.acts.append(act(h, w_, item[2]))
-        self.fh, self.fw = h, w_
-        self.rpn_mid = act(h, w_, 512)
-        self.rpn_out = torch.empty((h * w_, weights.rpn_ld), dtype=torch.float32, device=dev)
-        self.prop = ops.ProposalWorkspace(A, h, w_, pre_n, post_n, dev, debug=keep_rpn_debug)
-        C = self.acts[-1].hi.shape[2]
-        self.pool5 = act(1, post_n, 49 * C)
-        self.fc6 = act(1, post_n, 4096)
-        self.fc7 = act(1, post_n, 4096)
-        self.head_out = torch.empty((post_n, weights.head_ld), dtype=torch.float32, device=dev)
-        self.prob = torch.zeros((post_n, weights.num_classes), dtype=torch.float32, device=dev)
-        self.boxes = torch.zeros((post_n, 4 * weights.num_classes), dtype=torch.float32, device=dev)
-        self.det = None
-        self.graph = None
-        self.use_graph = use_graph
-        self.im_h, self.im_w = H, W
-        self.n_launches = 0
+        return h, w_
 
-    # -- the launch sequence (static; safe to capture)
-    def _run(self):
+    def _run_trunk(self):
+        """Launches the trunk; returns (feature map Act, number of launches)."""
         w = self.w
         n = 0
-        lib = ops._lib.load()
         x = self.acts[0]
         ops.pack_image_im2col(self.x_in, out=x)
         n += 1
@@ -162,7 +173,13 @@ class ForwardPlan(object):
                 ops.maxpool2x2_ceil(self.acts[i], out=self.acts[i + 1])
                 n += 1
                 i += 1
-        feat = self.acts[-1]
+        return self.acts[-1], n
+
+    # -- the launch sequence (static; safe to capture)
+    def _run(self):
+        w = self.w
+        feat, n = self._run_trunk()
+        self.feat = feat
         hi, lo, b = w.rpn3
         ops.conv2d(feat, hi, lo, b, 3, True, out=self.rpn_mid)
         hi, lo, b = w.rpn_heads
@@ -190,7 +207,7 @@ class ForwardPlan(object):
 
     def clone(self):
         """A second set of buffers (and its own graph) over the SAME packed weights: lets another image be in flight."""
-        p = ForwardPlan(self.w, self.H, self.W, **self._ctor)
+        p = type(self)(self.w, self.H, self.W, **self._ctor)
         p.set_clip(self.im_h, self.im_w)
         return p
 

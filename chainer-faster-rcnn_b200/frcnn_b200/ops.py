@@ -140,6 +140,65 @@ def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=Non
     return y, y32
 
 
+def conv2d_res(x, w_hi, w_lo, bias, ksize, relu, res, out=None):
+    """frcnn_conv2d_res: y = act(conv(x) + bias + res); res an Act of the output shape (ResNet shortcut add)."""
+    H, W, Cin = x.hi.shape
+    taps, Cout, cin_w = w_hi.shape
+    if cin_w != Cin or taps != ksize * ksize or tuple(res.hi.shape) != (H, W, Cout):
+        raise FrcnnError("conv2d_res: shapes do not match (x %s, w %s, res %s)" % (tuple(x.hi.shape), tuple(w_hi.shape), tuple(res.hi.shape)))
+    if out is None:
+        yh = torch.empty((H, W, Cout), dtype=torch.bfloat16, device=x.hi.device)
+        out = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    check(_lib.load().frcnn_conv2d_res(_p(x.hi), _p(x.lo), H, W, Cin, _p(w_hi), _p(w_lo), _p(bias), Cout, ksize, 1 if relu else 0,
+                                       _p(res.hi), _p(res.lo), _p(out.hi), _p(out.lo), _stream()), "frcnn_conv2d_res")
+    return out
+
+
+def pack_image_im2col_general(x_chw, ksize, stride, pad, k_pad, precision="bf16x3", out=None):
+    """(C,H,W) float32 CUDA image -> Act [Ho,Wo,k_pad]: the zero-padded ksize x ksize x C neighbourhood of every
+    stride-th pixel (K index (r*ksize+s)*C + c)."""
+    _need_cuda(x_chw)
+    x = x_chw.contiguous().float()
+    C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    if out is None:
+        hi = torch.empty((Ho, Wo, k_pad), dtype=torch.bfloat16, device=x.device)
+        out = Act(hi, torch.empty_like(hi) if precision == "bf16x3" else None)
+    check(_lib.load().frcnn_pack_image_im2col(_p(x), C, H, W, ksize, stride, pad, k_pad, _p(out.hi), _p(out.lo), _stream()),
+          "frcnn_pack_image_im2col")
+    return out
+
+
+def pack_conv_weights_im2col_general(w, k_pad, precision="bf16x3"):
+    """OIHW float32 -> ([1, Cout, k_pad] bf16 hi, lo or None) in the K order of pack_image_im2col_general."""
+    w = w.contiguous().float()
+    Cout, Cin, kh, kw = w.shape
+    hi = torch.empty((1, Cout, k_pad), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if precision == "bf16x3" else None
+    check(_lib.load().frcnn_pack_conv_weights_im2col(_p(w), None, Cout, Cin, kh, k_pad, _p(hi), _p(lo), _stream()),
+          "frcnn_pack_conv_weights_im2col")
+    return hi, lo
+
+
+def maxpool3x3s2_ceil(x, out=None):
+    H, W, C = x.hi.shape
+    Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    if out is None:
+        yh = torch.empty((Ho, Wo, C), dtype=torch.bfloat16, device=x.hi.device)
+        out = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    check(_lib.load().frcnn_maxpool3x3s2_ceil(_p(x.hi), _p(x.lo), H, W, C, _p(out.hi), _p(out.lo), _stream()), "frcnn_maxpool3x3s2_ceil")
+    return out
+
+
+def subsample2x(x, out=None):
+    H, W, C = x.hi.shape
+    if out is None:
+        yh = torch.empty(((H + 1) // 2, (W + 1) // 2, C), dtype=torch.bfloat16, device=x.hi.device)
+        out = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    check(_lib.load().frcnn_subsample2x(_p(x.hi), _p(x.lo), H, W, C, _p(out.hi), _p(out.lo), _stream()), "frcnn_subsample2x")
+    return out
+
+
 def set_conv_tile(block_n=0, tile_h=0, tile_w=0):
     _lib.load().frcnn_conv2d_set_tile(block_n, tile_h, tile_w)
 

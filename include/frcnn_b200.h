@@ -180,6 +180,30 @@ int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_
                  double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ResNet trunk support (chainer ResNetLayers as used by models/resnet.py:11-45).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* frcnn_conv2d with a residual input: y = act(conv(x) + bias + (res_hi + res_lo)), res [H][W][Cout] bf16 planes
+ * (res_lo may be NULL) -- the "h + shortcut, then ReLU" tail of a bottleneck block in one epilogue.  bf16 output only. */
+int frcnn_conv2d_res(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                     const float* bias, int Cout, int ksize, int relu, const void* res_hi, const void* res_lo, void* y_hi,
+                     void* y_lo, void* stream);
+
+/* General first-layer im2col: (C,H,W) fp32 -> [Ho][Wo][K_pad] bf16 hi/lo, K index (r*ksize+s)*C + c, zero padding,
+ * Ho = (H + 2*pad - ksize)/stride + 1 (conv1 of ResNet: ksize 7, stride 2, pad 3, K = 147 -> K_pad 160), and the matching
+ * weight packing [1][Cout][K_pad] (scale: optional per-output-channel factor, e.g. a folded BatchNorm). */
+int frcnn_pack_image_im2col(const float* x_chw, int C, int H, int W, int ksize, int stride, int pad, int K_pad, void* y_hi,
+                            void* y_lo, void* stream);
+int frcnn_pack_conv_weights_im2col(const float* w_oihw, const float* scale, int Cout, int Cin, int ksize, int K_pad, void* w_hi,
+                                   void* w_lo, void* stream);
+
+/* F.max_pooling_2d(x, 3, stride=2), Chainer defaults pad=0 / cover_all=True: [H][W][C] -> [ceil((H-3)/2)+1][...][C]. */
+int frcnn_maxpool3x3s2_ceil(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo, void* stream);
+
+/* Pixels (2h, 2w) of an NHWC map: the input of a stride-2 1x1 convolution.  [H][W][C] -> [ceil(H/2)][ceil(W/2)][C]. */
+int frcnn_subsample2x(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * RPN training targets and losses (the train_rpn.py step).  Box arithmetic is
  * float64 in the reference's operation order: labels and indices are bit-identical to the reference.
  * ------------------------------------------------------------------------------------------------ */
