@@ -140,3 +140,39 @@ class ResNetEngine(Engine):
         if key not in self.plans:
             self.plans[key] = ResNetForwardPlan(self.weights, H, W, anchors=self.anchors, feat_stride=self.feat_stride, **kw)
         return self.plans[key]
+
+
+class TrunkOnly(object):
+    """The trunk alone (models.resnet.ResNet.__call__): packs only trunk/* and runs ResNetForwardPlan's trunk hooks."""
+
+    class _W(ResNetPackedWeights):
+        def __init__(self, params, n_layers, precision, device):        # no RPN / head parameters here
+            self.n_layers, self.precision, self.device = n_layers, precision, device
+            self.convs = {}
+            self._pack_trunk(params, None)
+
+    class _Plan(ResNetForwardPlan):
+        def __init__(self, weights, H, W):
+            self.w, self.H, self.W = weights, H, W
+            dev = weights.device
+            x3 = weights.precision == "bf16x3"
+
+            def act(h, w, c):
+                hi = torch.empty((h, w, c), dtype=torch.bfloat16, device=dev)
+                return ops.Act(hi, torch.empty_like(hi) if x3 else None)
+            self._act = act
+            self.x_in = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+            self._alloc_trunk(H, W)
+
+    def __init__(self, params, n_layers, precision, device):
+        self.weights = self._W(params, n_layers, precision, device)
+        self.plans = {}
+
+    def run(self, x_chw):
+        _, H, W = x_chw.shape
+        if (H, W) not in self.plans:
+            self.plans[(H, W)] = self._Plan(self.weights, H, W)
+        p = self.plans[(H, W)]
+        p.x_in.copy_(x_chw)
+        feat, _ = p._run_trunk()
+        return feat

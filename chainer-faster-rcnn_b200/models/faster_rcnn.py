@@ -83,9 +83,14 @@ class FasterRCNN(links.Link):
         eng, ver = self._engine
         if eng is None or ver != self._version:
             params = self.param_dict()
-            eng = Engine(params, precision=self.precision, anchors=self.RPN.proposal_layer._anchors,
-                         num_classes=self._num_classes, n_anchors=self.RPN.proposal_layer._num_anchors,
-                         feat_stride=self._feat_stride)
+            kw = dict(precision=self.precision, anchors=self.RPN.proposal_layer._anchors, num_classes=self._num_classes,
+                      n_anchors=self.RPN.proposal_layer._num_anchors, feat_stride=self._feat_stride)
+            n_layers = getattr(self.trunk, "n_layers", None)
+            if n_layers is not None:                    # models.resnet.ResNet trunk
+                from frcnn_b200.resnet_engine import ResNetEngine
+                eng = ResNetEngine(params, n_layers, **kw)
+            else:
+                eng = Engine(params, **kw)
             self.__dict__["_engine"] = (eng, self._version)
         return eng
 

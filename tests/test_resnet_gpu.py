@@ -149,3 +149,48 @@ def test_resnet_faster_rcnn_forward_stagewise(n_layers, shape):
     pg, bg, plan_g = eng_g(torch.from_numpy(x[0]).cuda())
     assert torch.equal(pg, prob) and torch.equal(bg, boxes)
     assert type(plan_g.clone()) is type(plan_g)
+
+
+def test_dropin_resnet_trunk_and_detector():
+    """models.resnet.ResNet (the reference's trunk class name) alone and inside FasterRCNN(trunk_class=..., rpn_in_ch=2048,
+    feat_stride=32): parameter paths are Chainer's (trunk/res4/b7/bn2/avg_var, ...), the forward equals the oracle's."""
+    import functools
+    from frcnn_b200 import dropin
+    dropin.install()
+    from chainer import Variable
+    from models.faster_rcnn import FasterRCNN
+    from models.resnet import ResNet
+    np.random.seed(3)
+    model = FasterRCNN(trunk_class=functools.partial(ResNet, 50), rpn_in_ch=2048, feat_stride=32)
+    model.rcnn_train = False
+    model.rpn_train = False
+    rng = np.random.default_rng(9)
+    for path, p in model.namedparams():
+        if path.endswith("/avg_var"):
+            p.data[...] = rng.uniform(0.8, 1.25, p.data.shape).astype(f32)
+        elif path.endswith("/avg_mean") or path.endswith("/beta"):
+            p.data[...] = (rng.standard_normal(p.data.shape) * 0.05).astype(f32)
+        elif path == "/trunk/conv1/W":
+            p.data[...] *= f32(1.0 / 64)
+        elif path == "/fc6/W":
+            p.data[...] *= f32(0.2)
+    model._params_changed()
+    params = model.param_dict()
+    assert "trunk/res4/b5/bn2/avg_var" in params and "trunk/res5/a/conv4/W" in params and params["fc6/W"].shape == (4096, 2048 * 49)
+    H, W = 160, 224
+    x = orc.make_image(H, W, seed=6)
+    feat = model.trunk(Variable(x)).data
+    want = orc.resnet_forward(x, params, 50)
+    assert feat.shape == want.shape == (1, 2048, 5, 7) and _rel(feat, want) < 1e-4
+    info = np.array([[H, W]], np.int32)
+    cls_prob, pred_boxes = model(Variable(x), Variable(info))
+    R = cls_prob.data.shape[0]
+    assert 0 < R <= 300 and cls_prob.data.shape == (R, 21) and pred_boxes.shape == (R, 84)
+    np.testing.assert_allclose(cls_prob.data.sum(1), 1.0, rtol=1e-5)
+    # the same proposals as the oracle's end-to-end run, matched by box (near-tie scores may reorder)
+    want_cls, want_boxes, aux = orc.faster_rcnn_resnet_forward(x, params, info, n_layers=50, pre_nms_top_n=6000, post_nms_top_n=300)
+    got_rois = model.rpn_proposals
+    d = np.abs(got_rois[:, None, :] - aux["proposals"][None, :, :]).max(-1)
+    matched = (d.min(1) < 0.05).mean()
+    print("ResNet-50 detector: R=%d (oracle %d), proposals matched %.3f" % (R, len(aux["proposals"]), matched))
+    assert matched > 0.95 and abs(R - len(aux["proposals"])) <= max(3, R // 20)
