@@ -498,6 +498,73 @@ def run_train_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_resnet_arm(args, rank, local_rank, world):
+    """Secondary workload (BASELINE config #4, a "next" row): ResNet-101 trunk Faster R-CNN forward, 800x1333, 1000 proposals,
+    one image per GPU.  Device-timed with inputs resident in HBM, args.in_flight images in flight.  Not the headline."""
+    import torch
+    import frcnn_oracle as orc
+    from frcnn_b200 import shard
+    from frcnn_b200.engine import LanePool
+    from frcnn_b200.resnet_engine import ResNetEngine
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    H, W = 800, 1333
+    anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+    params = orc.make_resnet_params(101, seed=4321)
+    eng = ResNetEngine(params, 101, precision=args.precision, anchors=anchors, use_graph=True, post_n=1000)
+    plan = eng.plan(H, W)
+    imgs = [torch.from_numpy(orc.make_image(H, W, seed=shard.image_seed(rank, i))[0]).cuda() for i in range(4)]
+    pool = LanePool(plan, lanes=args.in_flight)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    pool.fork()
+    for i in range(max(args.warmup, 3)):
+        pool.submit(i, imgs[i % 4])
+    pool.join()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    pool.fork()
+    for i in range(args.steps):
+        pool.submit(i, imgs[i % 4])
+    pool.join()
+    e1.record()
+    barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    R_last = int(plan.prop.count.item())
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        plan.forward(imgs[i % 4])
+    e1.record()
+    barrier()
+    ms1 = e0.elapsed_time(e1)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "images/sec end-to-end ResNet-101 Faster R-CNN forward @800x1333, 1000 proposals",
+            "value": world * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "ResNet-101 trunk Faster R-CNN forward, synthetic 800x1333, 1000 proposals, one image per GPU "
+                                   "(config #4; secondary workload)", "images_in_flight_per_gpu": len(pool),
+                       "proposals_last_step": R_last, "one_image_in_flight_ms": ms1 / args.steps,
+                       "launches_per_image": plan.n_launches},
+            "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -507,8 +574,8 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn"],
-                    help="forward = the headline metric (default); train_rpn = the secondary training-step workload")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "resnet101"],
+                    help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -523,6 +590,9 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.workload == "train_rpn":
         run_train_arm(args, rank, local_rank, world)
+        return
+    if args.workload == "resnet101":
+        run_resnet_arm(args, rank, local_rank, world)
         return
     run_b200_arm(args, rank, local_rank, world)
 
