@@ -1,0 +1,96 @@
+"""CPU tests of host-side logic that needs no GPU: pure-host C-ABI helpers (called through the real library), the ResNet
+graph description and BN folding, the oracle's training-step restatement against numerical differentiation."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import frcnn_oracle as orc
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from frcnn_b200 import _lib
+    return _lib.load()
+
+
+def test_padded_pixel_layout_helper(lib):
+    """frcnn_padded_pixels: Wp = W+2 rounded up to 8, Kp = (H+2)*Wp rounded up to 64 (include/frcnn_b200.h)."""
+    for H, W in [(600, 1000), (38, 63), (1, 1), (19, 25), (75, 125)]:
+        wp = ctypes.c_int(0)
+        kp = lib.frcnn_padded_pixels(H, W, ctypes.byref(wp))
+        assert wp.value % 8 == 0 and W + 2 <= wp.value < W + 2 + 8
+        assert kp % 64 == 0 and (H + 2) * wp.value <= kp < (H + 2) * wp.value + 64
+        # every tap offset of every interior pixel stays inside [0, Kp)
+        q_last = (H + 1) * wp.value + (W + 1)              # pixel (H-1, W-1) shifted by (+1, +1)
+        assert q_last < kp
+
+
+def test_splitk_effective_splits(lib):
+    f = lib.frcnn_gemm_nt_splitk_splits
+    assert f(64 * 37, 5) == 5 and f(64 * 37, 1) == 1 and f(64 * 4, 9) == 4 and f(64 * 40, 3) == 3
+    for K, s in [(64 * 37, 5), (64 * 100, 7), (64 * 9, 9), (64 * 3, 2)]:
+        eff = f(K, s)
+        per = -(-(K // 64) // eff)
+        assert (eff - 1) * per < K // 64 <= eff * per       # every split non-empty, all k-blocks covered
+
+
+def test_resnet_graph_description_and_bn_folding():
+    from frcnn_b200 import resnet_engine as re_
+    for n, blocks in [(50, 16), (101, 33), (152, 50)]:
+        bl = re_.block_list(n)
+        assert len(bl) == blocks == len(orc.resnet_block_names(n)) and bl == orc.resnet_block_names(n)
+        assert sum(3 + (1 if b[6] else 0) for b in bl) + 1 == {50: 53, 101: 104, 152: 155}[n]     # convolutions incl. conv1
+        assert [b[5] for b in bl if b[1] == "a"] == [1, 2, 2, 2] and bl[-1][4] == 2048
+    p = orc.make_resnet_params(50, seed=2)
+    for conv, bn, bias in [("trunk/conv1", "trunk/bn1", p["trunk/conv1/b"]), ("trunk/res4/b3/conv2", "trunk/res4/b3/bn2", None)]:
+        Wf, bf = re_.fold_batchnorm(p[conv + "/W"], p[bn + "/gamma"], p[bn + "/beta"], p[bn + "/avg_mean"], p[bn + "/avg_var"], bias)
+        Wo, bo = orc.fold_bn(p[conv + "/W"], p, bn, bias)
+        assert Wf.dtype == np.float32 and np.array_equal(Wf, Wo) and np.array_equal(bf, bo)
+        # the folded convolution reproduces conv -> BN on random data
+        import torch
+        x = torch.randn(1, Wf.shape[1], 9, 11, dtype=torch.float64)
+        y = torch.nn.functional.conv2d(x, torch.from_numpy(p[conv + "/W"]).double(), None if bias is None else torch.from_numpy(bias).double(),
+                                       padding=Wf.shape[2] // 2)
+        g, b_, m, v = (torch.from_numpy(p[bn + "/" + k]).double().view(1, -1, 1, 1) for k in ("gamma", "beta", "avg_mean", "avg_var"))
+        want = g * (y - m) / torch.sqrt(v + orc.BN_EPS) + b_
+        got = torch.nn.functional.conv2d(x, torch.from_numpy(Wf).double(), torch.from_numpy(bf).double(), padding=Wf.shape[2] // 2)
+        assert float((got - want).abs().max()) < 1e-5 * float(want.abs().max())
+
+
+def test_oracle_train_step_gradient_is_the_derivative_of_its_loss():
+    """The autograd restatement (oracle.rpn_train_step) against central differences of its own loss, on a tiny image."""
+    H, W = 64, 80
+    rng = np.random.default_rng(0)
+    params = orc.make_params(seed=5)
+    for k in ("RPN/rpn_cls_score/W", "RPN/rpn_bbox_pred/W"):
+        params[k] = (rng.standard_normal(params[k].shape) * 0.05).astype(f32)
+    x = orc.make_image(H, W, seed=1)
+    fh, fw = 4, 5
+    n_all = 9 * fh * fw
+    inds = np.arange(0, n_all, 3)
+    labels = rng.integers(-1, 2, len(inds)).astype(np.int32)
+    targets = rng.standard_normal((len(inds), 4)).astype(f32)
+    out = orc.rpn_train_step(params, x, labels, targets, inds)
+    for name, idx in [("RPN/rpn_bbox_pred/W", (3, 100, 0, 0)), ("RPN/rpn_conv_3x3/b", (7,)), ("trunk/conv5_3/W", (5, 9, 1, 2)),
+                      ("trunk/conv1_1/W", (2, 1, 0, 1))]:
+        eps = 1e-5 * max(float(params[name].std()), 1e-3)       # tiny against the tensor scale: stays between ReLU / max-pool kinks
+        vals = []
+        for sgn in (+1, -1):
+            p2 = dict(params)
+            w = params[name].astype(np.float64).copy()
+            w[idx] += sgn * eps
+            p2[name] = w
+            vals.append(orc.rpn_train_step(p2, x, labels, targets, inds)["losses"][3])
+        num = (vals[0] - vals[1]) / (2 * eps)
+        ana = out["grads"][name][idx]
+        assert abs(num - ana) <= 1e-3 * max(abs(ana), 1e-3) + 1e-7, (name, num, ana)
+    # update rule: g += wd*w; v = m*v - lr*g; w += v
+    k = "trunk/conv4_2/b"
+    g = out["grads"][k] + 0.0005 * params[k]
+    np.testing.assert_allclose(out["velocity"][k], -0.001 * g, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(out["params"][k], params[k] - 0.001 * g, rtol=1e-12, atol=0)
