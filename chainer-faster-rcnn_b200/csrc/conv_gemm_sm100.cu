@@ -705,6 +705,10 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     int BN = 0;
     if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) {
         BN = g_force_bn;
+    } else if (ge != nullptr) {
+        // split-K GEMM mode has tiles to spare (groups x splits): N = 128 halves the re-reads of A and is the measured
+        // optimum on every VGG weight-gradient shape (tests/gpu_wgrad_tune.py); N = 256 loses the accumulator double buffer
+        BN = cout_cover >= 128 ? 128 : 64;
     } else {
         const int sms = device_sm_count();
         double best = 0;

@@ -33,148 +33,174 @@ struct PrepArgs {
     int planes;                      // 1: plane at q; 3: planes shifted by -1/0/+1 pixel
 };
 
-constexpr int TP = 64;               // pixels per tile (along w)
-constexpr int TC = 64;               // channels per tile
-constexpr int PITCH = TP + 2;
+constexpr int PAD_LEFT = 8;          // zero columns left of pixel 0 in the transposed layout: every 8-pixel group starts 16-B aligned
 
-// value of the (masked / routed) gradient at (h, w, channel c8*8 + j), j < 8
-__device__ __forceinline__ void prep_values(const PrepArgs& a, int h, int w, int c8, float v[8]) {
-    const long off = ((long)h * a.W + w) * a.C + c8 * 8;
-    float yv[8];
-    bool has_y = a.y_hi != nullptr;
-    if (has_y) {
-        const uint4 yh = *reinterpret_cast<const uint4*>(a.y_hi + off);
-        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&yh);
-        uint4 yl = make_uint4(0, 0, 0, 0);
-        if (a.y_lo) yl = *reinterpret_cast<const uint4*>(a.y_lo + off);
-        const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&yl);
+// per-halfword mask (0xFFFF where equal) of VALUE equality hi+lo == hi'+lo' for two packed bf16 pairs.  The pooled map is a
+// re-split of the maximum's float value, and a re-split may move half an ulp between hi and lo (ties), so the bit patterns
+// of equal values can differ: the float sums (exact in fp32) are compared.
+__device__ __forceinline__ uint32_t eq_values(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+    const float a0 = __uint_as_float(ah << 16) + __uint_as_float(al << 16);
+    const float b0 = __uint_as_float(bh << 16) + __uint_as_float(bl << 16);
+    const float a1 = __uint_as_float(ah & 0xFFFF0000u) + __uint_as_float(al & 0xFFFF0000u);
+    const float b1 = __uint_as_float(bh & 0xFFFF0000u) + __uint_as_float(bl & 0xFFFF0000u);
+    return (a0 == b0 ? 0x0000FFFFu : 0u) | (a1 == b1 ? 0xFFFF0000u : 0u);
+}
+
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, long off, uint32_t w[4]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + off);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+
+// 8 floats -> 4 words of bf16 hi and 4 words of bf16 lo (element j in the low/high half of word j/2)
+__device__ __forceinline__ void pack8(const float v[8], uint32_t hw[4], uint32_t lw[4]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yv[j] = bf(hb[j]) + bf(lb[j]);
+    for (int m = 0; m < 4; ++m) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * m], h0, l0);
+        split_bf16(v[2 * m + 1], h1, l1);
+        hw[m] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[m] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
+}
+
+// The (masked / routed) gradient of 8 channels (chunk c8) at pixel (h, w) as packed bf16 words -- integer SIMD only:
+//   * a value is the pair (hi, lo) with hi = bf16(v), lo = bf16(v - hi): v > 0 iff hi > 0 (read as int16); equality of
+//     two values is tested on the exact float sums (eq_values);
+//   * F.max_pooling_2d backward: the incoming gradient goes to the FIRST element of the 2x2 ceil-mode window (scan order)
+//     whose value equals the pooled maximum;  F.relu backward: gy where y > 0.
+// Masked elements become +0 in both planes; kept elements keep the source's (hi, lo) words untouched.
+__device__ __forceinline__ void prep_words(const PrepArgs& a, int h, int w, int c8, uint32_t hw[4], uint32_t lw[4]) {
     if (a.g_f32 != nullptr) {
         const float* g = a.g_f32 + ((long)h * a.W + w) * a.ld_f32 + c8 * 8;
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (c8 * 8 + j < a.ld_f32) ? g[j] : 0.f;
-    } else if (a.p_hi == nullptr) {
-        const uint4 gh = *reinterpret_cast<const uint4*>(a.g_hi + off);
-        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&gh);
-        uint4 gl = make_uint4(0, 0, 0, 0);
-        if (a.g_lo) gl = *reinterpret_cast<const uint4*>(a.g_lo + off);
-        const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&gl);
+        pack8(v, hw, lw);
+        return;
+    }
+    const long off = ((long)h * a.W + w) * a.C + c8 * 8;
+    uint32_t keep[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    uint32_t yh[4], yl[4] = {0u, 0u, 0u, 0u};
+    if (a.y_hi != nullptr) {
+        ld4(a.y_hi, off, yh);
+        if (a.y_lo) ld4(a.y_lo, off, yl);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = bf(hb[j]) + bf(lb[j]);
-    } else {
-        // gradient at pooled resolution: route to the FIRST maximum of the 2x2 (ceil-mode) window in scan order
+        for (int m = 0; m < 4; ++m) keep[m] = __vcmpgts2(yh[m], 0u);          // y > 0
+    }
+    long goff = off;
+    if (a.p_hi != nullptr) {
         const int Wq = (a.W + 1) / 2;
         const int ph = h >> 1, pw = w >> 1;
-        const long poff = ((long)ph * Wq + pw) * a.C + c8 * 8;
-        const uint4 gh = *reinterpret_cast<const uint4*>(a.g_hi + poff);
-        const __nv_bfloat16* ghb = reinterpret_cast<const __nv_bfloat16*>(&gh);
-        uint4 gl = make_uint4(0, 0, 0, 0);
-        if (a.g_lo) gl = *reinterpret_cast<const uint4*>(a.g_lo + poff);
-        const __nv_bfloat16* glb = reinterpret_cast<const __nv_bfloat16*>(&gl);
-        const uint4 pmh = *reinterpret_cast<const uint4*>(a.p_hi + poff);
-        const __nv_bfloat16* pmhb = reinterpret_cast<const __nv_bfloat16*>(&pmh);
-        uint4 pml = make_uint4(0, 0, 0, 0);
-        if (a.p_lo) pml = *reinterpret_cast<const uint4*>(a.p_lo + poff);
-        const __nv_bfloat16* pmlb = reinterpret_cast<const __nv_bfloat16*>(&pml);
-        float pm[8];
+        goff = ((long)ph * Wq + pw) * a.C + c8 * 8;
+        uint32_t pmh[4], pml[4] = {0u, 0u, 0u, 0u};
+        ld4(a.p_hi, goff, pmh);
+        if (a.p_lo) ld4(a.p_lo, goff, pml);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pm[j] = bf(pmhb[j]) + bf(pmlb[j]);
-        // earlier window elements (scan order (0,0),(0,1),(1,0),(1,1)) that already equal the maximum take the gradient
-        bool earlier[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) earlier[j] = false;
+        for (int m = 0; m < 4; ++m) keep[m] &= eq_values(yh[m], yl[m], pmh[m], pml[m]);               // I am a maximum
         const int h0 = ph * 2, w0 = pw * 2;
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < 4; ++e) {                       // ... and no earlier window element is
             const int eh = h0 + (e >> 1), ew = w0 + (e & 1);
             if (eh == h && ew == w) break;
             if (eh >= a.H || ew >= a.W) continue;
             const long eo = ((long)eh * a.W + ew) * a.C + c8 * 8;
-            const uint4 eh4 = *reinterpret_cast<const uint4*>(a.y_hi + eo);
-            const __nv_bfloat16* ehb = reinterpret_cast<const __nv_bfloat16*>(&eh4);
-            uint4 el4 = make_uint4(0, 0, 0, 0);
-            if (a.y_lo) el4 = *reinterpret_cast<const uint4*>(a.y_lo + eo);
-            const __nv_bfloat16* elb = reinterpret_cast<const __nv_bfloat16*>(&el4);
+            uint32_t eh4[4], el4[4] = {0u, 0u, 0u, 0u};
+            ld4(a.y_hi, eo, eh4);
+            if (a.y_lo) ld4(a.y_lo, eo, el4);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) earlier[j] = earlier[j] || (bf(ehb[j]) + bf(elb[j]) == pm[j]);
+            for (int m = 0; m < 4; ++m) keep[m] &= ~eq_values(eh4[m], el4[m], pmh[m], pml[m]);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (!earlier[j] && yv[j] == pm[j]) ? bf(ghb[j]) + bf(glb[j]) : 0.f;
     }
-    if (has_y) {
+    ld4(a.g_hi, goff, hw);
+    if (a.g_lo) ld4(a.g_lo, goff, lw);
+    else { lw[0] = lw[1] = lw[2] = lw[3] = 0u; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = yv[j] > 0.f ? v[j] : 0.f;        // F.relu backward: gy * (y > 0)
-    }
+    for (int m = 0; m < 4; ++m) { hw[m] &= keep[m]; lw[m] &= keep[m]; }
 }
 
+// One block = 256 pixels x 64 channels of one image row, two phases with a 16-byte-granular exchange through shared memory:
+//   phase 1  thread = (pixel, 16-byte channel chunk): the 8 lanes of a pixel read its 8 chunks = one 128-B line (coalesced),
+//            evaluate prep_words, write the NHWC output (coalesced) and park the (hi, lo) vectors in smem, XOR-swizzled;
+//   phase 2  thread = (chunk = warp, 8-pixel group = lane): reads its 8 (+2) pixels' vectors back (conflict-free), transposes
+//            IN REGISTERS (byte_perm) -- per channel 8 consecutive pixels = one aligned 16-byte vector -- and stores: one
+//            instruction writes 32 x 16 B = 512 contiguous bytes of ONE channel row.
+// (Lane = chunk in both phases scatters every store over 8 rows 1.2 MB apart; lane = group in both phases makes every load
+// touch 32 lines: each ran at a third of the HBM rate.)
+constexpr int PREP_PX = 256;
+constexpr int PREP_SMEM = (PREP_PX + 2) * 128 * 2;        // rows -1 .. 256, 128 B per plane
+
+template <int PLANES>
 __global__ void __launch_bounds__(256) grad_prepare_kernel(PrepArgs a) {
-    __shared__ __nv_bfloat16 s_hi[TC][PITCH];
-    __shared__ __nv_bfloat16 s_lo[TC][PITCH];
-    const int wt = blockIdx.x, h = blockIdx.y, ct = blockIdx.z;
-    const int w0 = wt * TP, c0 = ct * TC;
-    const int t = threadIdx.x;
-    for (int it = 0; it < 2; ++it) {
-        const int px = (t >> 3) + it * 32, c8l = t & 7;
-        const int w = w0 + px, c8 = (c0 >> 3) + c8l;
-        float v[8];
-        const bool live = w < a.W && c8 * 8 < a.C;
-        if (live) {
-            prep_values(a, h, w, c8, v);
-        } else {
+    extern __shared__ uint4 prep_smem[];
+    uint4* s_hi = prep_smem;                                // [258][8] 16-byte units, unit column = c8 ^ ((row >> 3) & 7)
+    uint4* s_lo = prep_smem + (PREP_PX + 2) * 8;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int h = blockIdx.y, w0 = blockIdx.x * PREP_PX, c0 = blockIdx.z * 8;      // c0 in chunks
+    // ---- phase 1
+    {
+        const int c8l = t & 7, c8 = c0 + c8l;
+        const bool c_ok = c8 * 8 < a.C;
+        for (int it = 0; it < (PLANES == 3 ? 9 : 8); ++it) {
+            int row;                                        // smem row = pixel - w0 + 1
+            if (it < 8) row = 1 + it * 32 + (t >> 3);
+            else { if (t >= 16) break; row = (t >> 3) ? PREP_PX + 1 : 0; }         // the two halo pixels
+            const int w = w0 + row - 1;
+            uint32_t hw[4], lw[4];
+            const bool live = c_ok && w >= 0 && w < a.W;
+            if (live) {
+                prep_words(a, h, w, c8, hw, lw);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        }
-        __align__(16) __nv_bfloat16 hi[8];
-        __align__(16) __nv_bfloat16 lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
-        if (live && a.o_hi != nullptr) {
-            const long off = ((long)h * a.W + w) * a.C + c8 * 8;
-            *reinterpret_cast<uint4*>(a.o_hi + off) = *reinterpret_cast<const uint4*>(hi);
-            if (a.o_lo) *reinterpret_cast<uint4*>(a.o_lo + off) = *reinterpret_cast<const uint4*>(lo);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            s_hi[c8l * 8 + j][px] = hi[j];
-            s_lo[c8l * 8 + j][px] = lo[j];
+                for (int m = 0; m < 4; ++m) hw[m] = lw[m] = 0u;
+            }
+            if (live && it < 8 && a.o_hi != nullptr) {
+                const long off = ((long)h * a.W + w) * a.C + c8 * 8;
+                *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (a.o_lo) *reinterpret_cast<uint4*>(a.o_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            const int u = row * 8 + (c8l ^ ((row >> 3) & 7));
+            s_hi[u] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            s_lo[u] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
     }
     if (a.t_hi == nullptr) return;
     __syncthreads();
-    // transposed stores: a channel row of this tile is <= 64 consecutive k positions starting at q0 - shift; they are
-    // written as 16-byte vectors on the 8-element-aligned groups that lie fully inside the row, element-wise at the ends.
-    const int warp = t >> 5, lane = t & 31;
-    const long q0 = (long)(h + 1) * a.Wp + (w0 + 1);
-    const int n = min(TP, a.W - w0);                 // valid pixels of this tile
-    const int rsub = lane >> 3, gl = lane & 7;       // 4 channel rows per warp pass, 8 lanes per row
-    for (int pl = 0; pl < a.planes; ++pl) {
-        const int shift = a.planes == 3 ? pl - 1 : 0;                // plane pl at k holds the operand at k + pl - 1
-        const long d0 = q0 - shift;                                  // destination of pixel 0
-        const long g0 = d0 & ~7l;                                    // first aligned group
-        for (int ch = warp * 4 + rsub; ch < TC; ch += 32) {
-            if (c0 + ch >= a.C) continue;
-            const long row = ((long)pl * a.C + c0 + ch) * a.Kp;
-            for (int grp = gl; grp < 9; grp += 8) {
-                const long k0 = g0 + 8 * grp;
-                const int px0 = (int)(k0 - d0);                      // pixel of the group's first element (may be < 0)
-                if (px0 >= n || px0 + 8 <= 0) continue;
-                if (px0 >= 0 && px0 + 8 <= n) {
-                    __align__(16) __nv_bfloat16 vh[8];
-                    __align__(16) __nv_bfloat16 vl[8];
+    // ---- phase 2
+    constexpr int NPX = PLANES == 3 ? 10 : 8;
+    constexpr int FIRST = PLANES == 3 ? 0 : 1;              // first smem row relative to the group's row 8*lane
+    const int c8l = warp, c8 = c0 + c8l;
+    const int wg = w0 + lane * 8;
+    if (wg >= a.W || c8 * 8 >= a.C) return;
+    uint32_t hw[NPX][4], lw[NPX][4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { vh[e] = s_hi[ch][px0 + e]; vl[e] = s_lo[ch][px0 + e]; }
-                    *reinterpret_cast<uint4*>(a.t_hi + row + k0) = *reinterpret_cast<const uint4*>(vh);
-                    if (a.t_lo) *reinterpret_cast<uint4*>(a.t_lo + row + k0) = *reinterpret_cast<const uint4*>(vl);
-                } else {
-                    for (int e = 0; e < 8; ++e) {
-                        const int px = px0 + e;
-                        if (px >= 0 && px < n) {
-                            a.t_hi[row + k0 + e] = s_hi[ch][px];
-                            if (a.t_lo) a.t_lo[row + k0 + e] = s_lo[ch][px];
-                        }
-                    }
-                }
+    for (int i = 0; i < NPX; ++i) {
+        const int row = lane * 8 + FIRST + i;
+        const int u = row * 8 + (c8l ^ ((row >> 3) & 7));
+        const uint4 vh = s_hi[u], vl = s_lo[u];
+        hw[i][0] = vh.x; hw[i][1] = vh.y; hw[i][2] = vh.z; hw[i][3] = vh.w;
+        lw[i][0] = vl.x; lw[i][1] = vl.y; lw[i][2] = vl.z; lw[i][3] = vl.w;
+    }
+    const long k0 = (long)(h + 1) * a.Wp + PAD_LEFT + wg;          // multiple of 8
+#pragma unroll
+    for (int pl = 0; pl < PLANES; ++pl) {
+        // plane pl at k holds pixel k + pl - 1 (PLANES == 3) / pixel k (PLANES == 1): window starts at array index pl / 0
+        const int b0 = PLANES == 3 ? pl : 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+            const int m = j >> 1;
+            uint4 vh, vl;
+            vh.x = __byte_perm(hw[b0 + 0][m], hw[b0 + 1][m], sel);
+            vh.y = __byte_perm(hw[b0 + 2][m], hw[b0 + 3][m], sel);
+            vh.z = __byte_perm(hw[b0 + 4][m], hw[b0 + 5][m], sel);
+            vh.w = __byte_perm(hw[b0 + 6][m], hw[b0 + 7][m], sel);
+            const long row = ((long)pl * a.C + c8 * 8 + j) * a.Kp + k0;
+            *reinterpret_cast<uint4*>(a.t_hi + row) = vh;
+            if (a.t_lo) {
+                vl.x = __byte_perm(lw[b0 + 0][m], lw[b0 + 1][m], sel);
+                vl.y = __byte_perm(lw[b0 + 2][m], lw[b0 + 3][m], sel);
+                vl.z = __byte_perm(lw[b0 + 4][m], lw[b0 + 5][m], sel);
+                vl.w = __byte_perm(lw[b0 + 6][m], lw[b0 + 7][m], sel);
+                *reinterpret_cast<uint4*>(a.t_lo + row) = vl;
             }
         }
     }
@@ -257,7 +283,7 @@ __global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout,
 using namespace frcnn;
 
 static long padded_pixels(int H, int W, int* wp_out) {
-    const int Wp = (W + 2 + 7) / 8 * 8;
+    const int Wp = (W + PAD_LEFT + 1 + 7) / 8 * 8;        // 8 zero columns left (aligned groups), >= 1 right
     if (wp_out) *wp_out = Wp;
     const long raw = (long)(H + 2) * Wp;
     return (raw + 63) / 64 * 64;
@@ -284,9 +310,16 @@ int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, i
     a.Kp = padded_pixels(H, W, &a.Wp);
     a.o_hi = (__nv_bfloat16*)o_hi; a.o_lo = (__nv_bfloat16*)o_lo; a.t_hi = (__nv_bfloat16*)t_hi; a.t_lo = (__nv_bfloat16*)t_lo;
     a.planes = planes;
-    dim3 grid(cdiv(W, TP), H, cdiv(C, TC));
+    dim3 grid(cdiv(W, 256), H, cdiv(C, 64));
     FRCNN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grad_prepare: image too tall / too many channels for one launch");
-    grad_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FRCNN_CUDA_OK(cudaFuncSetAttribute(grad_prepare_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
+        FRCNN_CUDA_OK(cudaFuncSetAttribute(grad_prepare_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_SMEM));
+        attr_set = true;
+    }
+    if (planes == 3) grad_prepare_kernel<3><<<grid, 256, PREP_SMEM, (cudaStream_t)stream>>>(a);
+    else grad_prepare_kernel<1><<<grid, 256, PREP_SMEM, (cudaStream_t)stream>>>(a);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }

@@ -185,8 +185,10 @@ class RpnTrainer(object):
 
     # ---------------------------------------------------------------- backward
     def _splits(self, groups, M, N, kb_total):
+        # measured (tests/gpu_wgrad_tune.py): ~2 waves of 148 tiles, 4 when the M tile is half empty (64 output channels)
         tiles = groups * ((M + 127) // 128) * ((N + 127) // 128)
-        s = max(1, (2 * 148 + tiles - 1) // tiles)
+        target = (4 if M <= 64 else 2) * 148
+        s = max(1, (target + tiles - 1) // tiles)
         return int(min(s, max(1, kb_total // 8)))
 
     def _wgrad(self, dyT, xT, M, N, groups, dw, m_out=None):

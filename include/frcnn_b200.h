@@ -268,9 +268,10 @@ int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, int K, const
                          void* stream);
 
 /* ---- conv backward, memory-bound parts (train_backward.cu).  The "transposed padded" layout used by the weight-
- * gradient GEMM: a [C][Kp] bf16 plane per hi/lo where pixel (h,w) of an H x W map sits at k = (h+1)*Wp + (w+1),
- * Wp = W+2 rounded up to 8, Kp = (H+2)*Wp rounded up to 64, everything else zero (the buffer must be zeroed once; the
- * kernels only write the interior).  frcnn_padded_pixels returns Kp and the row pitch Wp. */
+ * gradient GEMM: a [C][Kp] bf16 plane per hi/lo where pixel (h,w) of an H x W map sits at k = (h+1)*Wp + 8 + w
+ * (8 zero columns on the left keep every 8-pixel group 16-byte aligned), Wp = W+9 rounded up to 8, Kp = (H+2)*Wp rounded up
+ * to 64, everything else zero (the buffer must be zeroed once; the kernels only write the interior and zeros into the
+ * padding).  frcnn_padded_pixels returns Kp and the row pitch Wp. */
 long frcnn_padded_pixels(int H, int W, int* row_pitch);
 
 /* Gradient / activation re-layout with the element-wise backward ops fused:

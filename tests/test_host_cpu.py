@@ -19,15 +19,16 @@ def lib():
 
 
 def test_padded_pixel_layout_helper(lib):
-    """frcnn_padded_pixels: Wp = W+2 rounded up to 8, Kp = (H+2)*Wp rounded up to 64 (include/frcnn_b200.h)."""
+    """frcnn_padded_pixels: Wp = W+9 rounded up to 8, Kp = (H+2)*Wp rounded up to 64 (include/frcnn_b200.h)."""
     for H, W in [(600, 1000), (38, 63), (1, 1), (19, 25), (75, 125)]:
         wp = ctypes.c_int(0)
         kp = lib.frcnn_padded_pixels(H, W, ctypes.byref(wp))
-        assert wp.value % 8 == 0 and W + 2 <= wp.value < W + 2 + 8
+        assert wp.value % 8 == 0 and W + 9 <= wp.value < W + 9 + 8
         assert kp % 64 == 0 and (H + 2) * wp.value <= kp < (H + 2) * wp.value + 64
-        # every tap offset of every interior pixel stays inside [0, Kp)
-        q_last = (H + 1) * wp.value + (W + 1)              # pixel (H-1, W-1) shifted by (+1, +1)
-        assert q_last < kp
+        # every tap offset of every interior pixel stays inside [0, Kp): pixel (h, w) sits at (h+1)*Wp + 8 + w
+        q_last = (H + 1) * wp.value + 8 + W                # pixel (H-1, W-1) shifted by (+1, +1)
+        q_first = 8 - 1                                    # pixel (0, 0) shifted by (-1, -1) lands in row 0
+        assert 0 <= q_first and q_last < kp
 
 
 def test_splitk_effective_splits(lib):
