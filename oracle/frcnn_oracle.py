@@ -389,6 +389,69 @@ def rpn_train_step(params, x, labels, targets, inds_inside, lr=0.001, momentum=0
                 params=new_p, velocity=new_v)
 
 
+# --------------------------------------------------------------------------- ProposalTargetLayer + RCNN losses (training, "next")
+FG_THRESH, BG_THRESH_HI, BG_THRESH_LO = 0.5, 0.5, 0.1        # models/proposal_target_layer.py:46-48
+ROIS_PER_IMAGE, FG_FRACTION = 128, 0.25                      # :49-50
+
+
+def proposal_target_layer(proposals, gt_boxes, num_classes=21, choice=None):
+    """ProposalTargetLayer.__call__ (models/proposal_target_layer.py:76-150).  proposals (N,4) float32, gt_boxes (1,G,5).
+    choice(inds, size): default = the reference's np.random.choice(..., replace=False) on the global RNG -- note it is
+    called whenever a candidate set is non-empty (:105-110,122-126), so the kept order is a random permutation.
+    Quirks restated as written: the class labels the loss uses are use_gt_boxes[:, 4] (faster_rcnn.py:154) -- the class of
+    the best-overlapping gt even for background RoIs (the clamp at :133 acts on a discarded array); rows whose gt class is
+    0 get no regression target (:143-147); float32 box arithmetic (both operands are float32)."""
+    if choice is None:
+        choice = lambda inds, size: np.random.choice(inds, size=size, replace=False)     # noqa: E731
+    proposals = np.asarray(proposals)
+    gt = np.asarray(gt_boxes)[0]
+    overlaps = bbox_overlaps(proposals, gt[:, :4])                                        # anchor_target_layer.py:181-185
+    argmax = overlaps.argmax(axis=1)
+    max_ov = overlaps[np.arange(len(proposals)), argmax]
+    n_fg_cap = int(FG_FRACTION * ROIS_PER_IMAGE)
+    fg_inds = np.where(max_ov >= FG_THRESH)[0]                                            # :99
+    n_fg = min(n_fg_cap, fg_inds.size)                                                    # :103
+    if fg_inds.size > 0:
+        fg_inds = np.asarray(choice(fg_inds, n_fg))                                       # :105-110
+    bg_inds = np.where((max_ov < BG_THRESH_HI) & (max_ov >= BG_THRESH_LO))[0]             # :113-114
+    n_bg = min(ROIS_PER_IMAGE - n_fg, bg_inds.size)                                       # :116-117
+    if bg_inds.size > 0:
+        bg_inds = np.asarray(choice(bg_inds, n_bg))                                       # :119-126
+    keep = np.concatenate([fg_inds, bg_inds]).astype(np.int32)                            # :129
+    use_gt = gt[argmax[keep]]                                                             # :138
+    reg = bbox_transform(proposals[keep], use_gt)                                         # :139 (float32 in, float32 out)
+    ext = np.zeros((len(keep), 4 * num_classes), dtype=f32)                               # :142-147
+    for ind in np.where(use_gt[:, 4] > 0)[0]:
+        c = int(4 * use_gt[ind, -1])
+        ext[ind, c:c + 4] = reg[ind]
+    return dict(use_gt_boxes=use_gt, bbox_reg_targets=ext, keep_inds=keep, max_overlaps=max_ov, argmax=argmax, n_fg=n_fg)
+
+
+def rcnn_losses(cls_score, bbox_pred, use_gt_boxes, bbox_reg_targets, keep_inds, delta=1.0):
+    """models/faster_rcnn.py:151-165.  cls_score (R,21), bbox_pred (R,84) float32 for ALL proposals; the kept rows enter a
+    21-way softmax cross entropy (mean over the kept rows) against use_gt_boxes[:, 4] and F.huber_loss(delta) whose per-row
+    sums are averaged over the rows.  UNPINNED (Chainer functions).  Returns (loss_cls, loss_bbox, accuracy, loss_rcnn,
+    dcls (R,21), dbbox (R,84)) -- gradients of loss_rcnn, zero on rows that were not kept (float64 arithmetic)."""
+    z = np.asarray(cls_score, np.float64)[keep_inds]
+    t = np.asarray(use_gt_boxes)[:, -1].astype(np.int32)
+    n = len(keep_inds)
+    m = z.max(1, keepdims=True)
+    lse = m + np.log(np.exp(z - m).sum(1, keepdims=True))
+    logp = z - lse
+    loss_cls = -logp[np.arange(n), t].mean()
+    acc = float((z.argmax(1) == t).mean())
+    p = np.exp(logp)
+    p[np.arange(n), t] -= 1.0
+    d = np.asarray(bbox_pred, np.float64)[keep_inds] - np.asarray(bbox_reg_targets, np.float64)
+    a = np.abs(d)
+    loss_bbox = np.where(a < delta, 0.5 * d * d, delta * (a - 0.5 * delta)).sum() / n
+    dcls = np.zeros(np.asarray(cls_score).shape, np.float64)
+    dbb = np.zeros(np.asarray(bbox_pred).shape, np.float64)
+    np.add.at(dcls, keep_inds, p / n)
+    np.add.at(dbb, keep_inds, np.where(a < delta, d, delta * np.sign(d)) / n)
+    return f32(loss_cls), f32(loss_bbox), f32(acc), f32(loss_cls + loss_bbox), dcls.astype(f32), dbb.astype(f32)
+
+
 # --------------------------------------------------------------------------- ProposalLayer
 RPN_NMS_THRESH = 0.7                 # models/proposal_layer.py:51
 TRAIN_PRE, TRAIN_POST = 12000, 2000  # :52-53

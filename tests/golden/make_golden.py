@@ -185,6 +185,35 @@ def main():
         print(name, "labels", labels.shape, "fg", int((labels == 1).sum()), "bg", int((labels == 0).sum()),
               "choice calls", len(calls), targets.dtype)
     np.savez_compressed(os.path.join(HERE, "anchor_target_layer.npz"), **out)
+
+    # ---- 6. ProposalTargetLayer.__call__ (RCNN training path)
+    from models import proposal_target_layer as ptl
+    out = {}
+    for name in gi.PROPOSAL_TARGET_CASES:
+        props, gt, seed = gi.proposal_target_case(name)
+        calls = []
+
+        def recording_choice2(a, size=None, replace=True, p=None):
+            r = real_choice(a, size=size, replace=replace, p=p)
+            calls.append((np.asarray(a).copy(), np.asarray(r).copy()))
+            return r
+        np.random.choice = recording_choice2
+        try:
+            np.random.seed(seed)
+            layer = ptl.ProposalTargetLayer()
+            use_gt, ext, keep = layer(props, Variable(gt))
+        finally:
+            np.random.choice = real_choice
+        out[name + "_use_gt_boxes"] = use_gt
+        out[name + "_bbox_reg_targets"] = ext
+        out[name + "_keep_inds"] = keep
+        out[name + "_n_choice_calls"] = np.int64(len(calls))
+        for ci, (pool, chosen) in enumerate(calls):
+            out[name + "_choice%d_pool" % ci] = pool
+            out[name + "_choice%d_chosen" % ci] = chosen
+        out[name + "_checksum"] = gi.checksum(props, gt)
+        print(name, "keep", keep.shape, keep.dtype, "targets", ext.shape, ext.dtype, "choice calls", len(calls))
+    np.savez_compressed(os.path.join(HERE, "proposal_target_layer.npz"), **out)
     print("golden vectors written to", HERE)
 
 

@@ -185,3 +185,31 @@ def anchor_target_case(name):
             gt[1, :4] = [iw + 50, ih + 50, iw + 90, ih + 120]       # beyond every inside anchor
     info = np.array([[ih, iw]], dtype=np.int32)
     return fh, fw, gt[None], info, 7000 + seed
+
+
+# --------------------------------------------------------------------------- ProposalTargetLayer (RCNN training path)
+PROPOSAL_TARGET_CASES = {
+    # name: (n_proposals, n_gt, kind, seed)
+    "ref_test": (300, 3, "reference_test", 0),        # tests/test_proposal_target_layer.py:20-33: gt + integer jitter
+    "few_fg": (300, 4, "random", 1),                  # random proposals: few reach IoU 0.5, many backgrounds
+    "n50": (50, 2, "jitter", 2),                      # fewer proposals than ROIS_PER_IMAGE
+    "class0": (200, 3, "class0", 3),                  # a gt of class 0: its rows get no regression targets
+}
+
+
+def proposal_target_case(name):
+    """-> proposals float32 (N,4), gt_boxes float32 (1,G,5), numpy seed."""
+    n, g, kind, seed = PROPOSAL_TARGET_CASES[name]
+    rng = np.random.default_rng(3000 + seed)
+    gt = np.array([[10, 10, 60, 200, 1], [50, 100, 210, 210, 2], [160, 40, 200, 70, 3], [20, 150, 120, 215, 7]], dtype=f32)[:g]
+    if kind == "class0":
+        gt[1, 4] = 0
+    if kind == "random":
+        xy = rng.uniform(0, 160, size=(n, 2))
+        wh = rng.uniform(10, 120, size=(n, 2))
+        props = np.hstack([xy, np.minimum(xy + wh, 223)]).astype(f32)
+        props[: n // 6] = (gt[rng.integers(0, g, n // 6), :4] + rng.integers(-8, 8, (n // 6, 4))).astype(f32)
+    else:
+        jitter = rng.integers(-10, 10, size=(n, 4))
+        props = (gt[rng.integers(0, g, size=n), :4] + jitter).astype(f32)
+    return props, gt[None], 9000 + seed
