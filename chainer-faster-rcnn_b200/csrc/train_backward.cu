@@ -31,6 +31,7 @@ struct PrepArgs {
     __nv_bfloat16 *o_hi, *o_lo;      // NHWC [H][W][C] out (optional)
     __nv_bfloat16 *t_hi, *t_lo;      // transposed [planes][C][Kp] out (optional)
     int planes;                      // 1: plane at q; 3: planes shifted by -1/0/+1 pixel
+    int times2;                      // multiply the result by 2 (the 1/(1-ratio) of a ratio-0.5 dropout): exponent + 1, exact
 };
 
 constexpr int PAD_LEFT = 8;          // zero columns left of pixel 0 in the transposed layout: every 8-pixel group starts 16-B aligned
@@ -115,6 +116,14 @@ __device__ __forceinline__ void prep_words(const PrepArgs& a, int h, int w, int 
     else { lw[0] = lw[1] = lw[2] = lw[3] = 0u; }
 #pragma unroll
     for (int m = 0; m < 4; ++m) { hw[m] &= keep[m]; lw[m] &= keep[m]; }
+    if (a.times2) {
+        // x2 on a bf16 = exponent field + 1 (halves with a zero exponent field -- zero / subnormal -- are left alone)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            hw[m] += 0x00800080u & __vcmpne2(hw[m] & 0x7F807F80u, 0u);
+            lw[m] += 0x00800080u & __vcmpne2(lw[m] & 0x7F807F80u, 0u);
+        }
+    }
 }
 
 // One block = 256 pixels x 64 channels of one image row, two phases with a 16-byte-granular exchange through shared memory:
@@ -295,7 +304,7 @@ long frcnn_padded_pixels(int H, int W, int* row_pitch) { return padded_pixels(H,
 
 int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, int ld_f32, const void* y_hi, const void* y_lo,
                        const void* p_hi, const void* p_lo, int H, int W, int C, void* o_hi, void* o_lo, void* t_hi, void* t_lo,
-                       int planes, void* stream) {
+                       int planes, int times2, void* stream) {
     FRCNN_REQUIRE(H > 0 && W > 0 && C > 0 && C % 8 == 0, "grad_prepare: bad shape H=%d W=%d C=%d (C %% 8 == 0)", H, W, C);
     FRCNN_REQUIRE((g_hi != nullptr) != (g_f32 != nullptr), "grad_prepare: give the source as bf16 planes OR fp32");
     FRCNN_REQUIRE(!g_f32 || (ld_f32 >= 1 && !p_hi), "grad_prepare: fp32 source needs ld_f32 and no pooling");
@@ -310,6 +319,8 @@ int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, i
     a.Kp = padded_pixels(H, W, &a.Wp);
     a.o_hi = (__nv_bfloat16*)o_hi; a.o_lo = (__nv_bfloat16*)o_lo; a.t_hi = (__nv_bfloat16*)t_hi; a.t_lo = (__nv_bfloat16*)t_lo;
     a.planes = planes;
+    a.times2 = times2 ? 1 : 0;
+    FRCNN_REQUIRE(!times2 || !g_f32, "grad_prepare: times2 is not available for an fp32 source");
     dim3 grid(cdiv(W, 256), H, cdiv(C, 64));
     FRCNN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "grad_prepare: image too tall / too many channels for one launch");
     static bool attr_set = false;

@@ -66,7 +66,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_int, c_void_p]),
     "frcnn_padded_pixels": (c_long, [c_int, c_int, c_void_p]),
     "frcnn_grad_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "frcnn_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "frcnn_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_long, c_float, c_void_p, c_void_p]),
     "frcnn_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_void_p]),
@@ -77,6 +77,14 @@ SIGNATURES = {
     "frcnn_pack_conv_weights_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_maxpool3x3s2_ceil": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_subsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_roi_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_roi_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "frcnn_rcnn_loss": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_double, c_void_p,
+                                c_void_p, c_void_p]),
+    "frcnn_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_void_p]),
+    "frcnn_roi_pool_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "frcnn_roi_pool_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),

@@ -129,7 +129,7 @@ def _zero_bias(device, n):
     return z
 
 
-def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
+def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1, out=None):
     """frcnn_gemm_nt_splitk: A [M,K]; B [N,K] (groups=1) or [3,N,K] pre-shifted planes (groups=9); bf16 planes (lo may
     be None for both) -> parts [groups, S, M, ld] fp32, ld = N rounded up to 32.  See include/frcnn_b200.h."""
     _need_cuda(a_hi, b_hi)
@@ -141,7 +141,12 @@ def gemm_nt_splitk(a_hi, a_lo, b_hi, b_lo, groups=1, row_stride=0, splits=1):
     lib = _lib.load()
     S = lib.frcnn_gemm_nt_splitk_splits(K, int(splits))
     ld = (N + 31) // 32 * 32
-    parts = torch.empty((groups, S, M, ld), dtype=torch.float32, device=a_hi.device)
+    if out is not None:          # groups == S == 1 and ld == N: the single slab IS the result (e.g. a weight gradient view)
+        if groups != 1 or S != 1 or ld != N or out.numel() != M * N or out.dtype != torch.float32 or not out.is_contiguous():
+            raise FrcnnError("gemm_nt_splitk: `out` needs groups = splits = 1, N %% 32 == 0 and a contiguous fp32 [M*N] target")
+        parts = out.view(1, 1, M, ld)
+    else:
+        parts = torch.empty((groups, S, M, ld), dtype=torch.float32, device=a_hi.device)
     zero = _zero_bias(a_hi.device, ld)
     check(lib.frcnn_gemm_nt_splitk(_p(a_hi), _p(a_lo), M, K, _p(b_hi), _p(b_lo), N, int(groups), int(row_stride), int(splits),
                                    _p(zero), _p(parts), ld, _stream()), "frcnn_gemm_nt_splitk")
@@ -165,7 +170,7 @@ class TBuf(object):
         self.lo = torch.zeros_like(self.hi) if x3 else None
 
 
-def grad_prepare(H, W, C, g=None, g_f32=None, y=None, p=None, out=None, tbuf=None):
+def grad_prepare(H, W, C, g=None, g_f32=None, y=None, p=None, out=None, tbuf=None, times2=False):
     """frcnn_grad_prepare.  g: ops.Act source (NHWC, or pooled size when p is given) or g_f32 [H*W, ld] fp32;
     y / p: forward activation / its pooled map (ops.Act) for the ReLU mask / max-pool routing;
     out: ops.Act [H,W,C] to receive the NHWC result (optional); tbuf: TBuf to receive the transposed planes (optional)."""
@@ -176,7 +181,7 @@ def grad_prepare(H, W, C, g=None, g_f32=None, y=None, p=None, out=None, tbuf=Non
         _p(p.hi) if p is not None else None, _p(p.lo) if p is not None else None, int(H), int(W), int(C),
         _p(out.hi) if out is not None else None, _p(out.lo) if out is not None else None,
         _p(tbuf.hi) if tbuf is not None else None, _p(tbuf.lo) if tbuf is not None else None,
-        tbuf.planes if tbuf is not None else 1, _stream()), "frcnn_grad_prepare")
+        tbuf.planes if tbuf is not None else 1, 1 if times2 else 0, _stream()), "frcnn_grad_prepare")
 
 
 def wgrad_reduce(parts, M, N, dw, scale=1.0):
@@ -207,3 +212,61 @@ def pack_conv_weights_dgrad(w, cout_pad=None, x3=True):
     check(_lib.load().frcnn_pack_conv_weights_dgrad(_p(w), Cout, Cin, kh, kw, cout_pad, _p(hi), _p(lo), _stream()),
           "frcnn_pack_conv_weights_dgrad")
     return hi, lo
+
+
+# ---------------------------------------------------------------------------------------------- RCNN-head training
+def roi_overlaps(rois, count, gt_boxes):
+    """frcnn_roi_overlaps: rois [R_cap,4] fp32, count int32[1] or None, gt [G,5] -> (max_overlaps float64 [R_cap], argmax int32)."""
+    R = rois.shape[0]
+    gt = gt_boxes.contiguous().float()
+    mo = torch.empty((R,), dtype=torch.float64, device=rois.device)
+    am = torch.empty((R,), dtype=torch.int32, device=rois.device)
+    check(_lib.load().frcnn_roi_overlaps(_p(rois), _p(count), R, _p(gt), gt.shape[0], _p(mo), _p(am), _stream()), "frcnn_roi_overlaps")
+    return mo, am
+
+
+def roi_targets(rois, gt_boxes, argmax, keep_inds, num_classes=21):
+    """frcnn_roi_targets -> (use_gt_boxes [n,5], bbox_reg_targets [n,4*num_classes], labels int32 [n])."""
+    n = keep_inds.numel()
+    gt = gt_boxes.contiguous().float()
+    keep = keep_inds.to(dtype=torch.int32).contiguous()
+    use_gt = torch.empty((n, 5), dtype=torch.float32, device=rois.device)
+    ext = torch.empty((n, 4 * num_classes), dtype=torch.float32, device=rois.device)
+    labels = torch.empty((n,), dtype=torch.int32, device=rois.device)
+    check(_lib.load().frcnn_roi_targets(_p(rois), _p(gt), _p(argmax), _p(keep), n, num_classes, _p(use_gt), _p(ext), _p(labels),
+                                        _stream()), "frcnn_roi_targets")
+    return use_gt, ext, labels
+
+
+def rcnn_loss(head_out, keep_inds, labels, bbox_reg_targets, num_classes=21, delta=1.0, grad_scale=1.0, want_grad=True):
+    """frcnn_rcnn_loss -> (losses float32[4] = cls, bbox, accuracy, total; dhead like head_out or None)."""
+    R, ld = head_out.shape
+    keep = keep_inds.to(dtype=torch.int32).contiguous()
+    losses = torch.empty((4,), dtype=torch.float32, device=head_out.device)
+    dh = torch.empty_like(head_out) if want_grad else None
+    check(_lib.load().frcnn_rcnn_loss(_p(head_out), ld, R, _p(keep), keep.numel(), _p(labels), _p(bbox_reg_targets), num_classes,
+                                      float(delta), float(grad_scale), _p(losses), _p(dh), _stream()), "frcnn_rcnn_loss")
+    return losses, dh
+
+
+def dropout_(act, mask, scale=2.0):
+    """In-place F.dropout with an explicit uint8 mask (same number of elements as the activation)."""
+    n = act.hi.numel()
+    if mask.numel() != n or mask.dtype != torch.uint8:
+        raise FrcnnError("dropout_: mask must be uint8 with %d elements" % n)
+    check(_lib.load().frcnn_dropout(_p(act.hi), _p(act.lo), _p(mask), n, float(scale), _stream()), "frcnn_dropout")
+    return act
+
+
+def roi_pool_backward(feat, rois, count, g, outh=7, outw=7, scale=1.0 / 16, out=None, ws=None):
+    """frcnn_roi_pool_backward: feat Act [H,W,C], g Act [1,R_cap,outh*outw*C] -> dfeat fp32 [H*W, C]."""
+    H, W, C = feat.hi.shape
+    R = rois.shape[0]
+    lib = _lib.load()
+    if ws is None:
+        ws = torch.empty((lib.frcnn_roi_pool_backward_workspace_bytes(H, W, C),), dtype=torch.uint8, device=feat.hi.device)
+    if out is None:
+        out = torch.empty((H * W, C), dtype=torch.float32, device=feat.hi.device)
+    check(lib.frcnn_roi_pool_backward(_p(feat.hi), _p(feat.lo), H, W, C, _p(rois), _p(count), R, outh, outw, float(scale),
+                                      _p(g.hi), _p(g.lo), _p(out), _p(ws), ws.numel(), _stream()), "frcnn_roi_pool_backward")
+    return out

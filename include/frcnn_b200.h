@@ -251,6 +251,34 @@ int frcnn_rpn_loss(const float* score, long score_cs, long score_ps, const float
                    double grad_scale, float* losses, float* dscore, float* dbbox, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* ---- RCNN-head training (rcnn_train.cu; train_rcnn.py, models/faster_rcnn.py:136-173) ---- */
+
+/* ProposalTargetLayer, part 1 (proposal_target_layer.py:91-96): best ground-truth overlap of every proposal, float64 in
+ * bbox.pyx order.  rois [R_cap,4] fp32 (*count valid, NULL = R_cap), gt_boxes [n_gt,5]; max_overlaps double [R_cap]
+ * (-1 for rows >= count), argmax int32 [R_cap].  The fg/bg sampling (:99-129) draws from NumPy's RNG on the host in the
+ * reference; the caller does the same (or any other rule) on these two small arrays and passes keep_inds to part 2. */
+int frcnn_roi_overlaps(const float* rois, const int* count, int R_cap, const float* gt_boxes, int n_gt, double* max_overlaps,
+                       int* argmax, void* stream);
+/* part 2 (:138-147): use_gt_boxes [n,5] = gt[argmax[keep]], labels int32 [n] = use_gt_boxes[:,4] (faster_rcnn.py:154),
+ * bbox_reg_targets [n, 4*num_classes] = float32 bbox_transform of the kept proposal scattered to its class's 4 columns
+ * (rows whose class is 0 stay zero). */
+int frcnn_roi_targets(const float* rois, const float* gt_boxes, const int* argmax, const int* keep_inds, int n, int num_classes,
+                      float* use_gt_boxes, float* bbox_reg_targets, int* labels, void* stream);
+/* faster_rcnn.py:151-165 on the merged head output head_out [R_cap][ld] (columns [0,num_classes) scores, then
+ * 4*num_classes deltas): losses float32 [4] = {loss_cls, loss_bbox, cls_accuracy, loss_rcnn}; dhead (optional, same shape)
+ * = grad_scale * d(loss_rcnn)/d(head_out), zero on rows not kept.  1 <= n <= 128. */
+int frcnn_rcnn_loss(const float* head_out, int ld, int R_cap, const int* keep_inds, int n, const int* labels,
+                    const float* bbox_reg_targets, int num_classes, double delta, double grad_scale, float* losses, float* dhead,
+                    void* stream);
+/* F.dropout with an explicit mask: x = mask ? x*scale : 0 in place on the bf16 hi(/lo) planes (scale = 1/(1-ratio)). */
+int frcnn_dropout(void* x_hi, void* x_lo, const unsigned char* mask, long n, float scale, void* stream);
+/* F.roi_pooling_2d backward: dfeat [H*W][C] fp32 = sum over (roi, bin) of the bin's gradient g [R_cap][outh*outw][C]
+ * (bf16 hi/lo) at the bin's first maximum of feat; order-independent 64-bit fixed-point accumulation (bit-reproducible). */
+size_t frcnn_roi_pool_backward_workspace_bytes(int H, int W, int C);
+int frcnn_roi_pool_backward(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois, const int* count,
+                            int R_cap, int outh, int outw, float scale, const void* g_hi, const void* g_lo, float* dfeat,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Split-K "NT" GEMM on the tensor-core kernel of frcnn_conv2d (same bf16 hi/lo operand planes), the engine of the
  * weight-gradient pass (conv backward-filter as a GEMM over the pixel axis):
  *     parts[g][s][m][n] = sum over k in split s of  A[m][k] * B_g[n][k + off(g)]        (fp32, row stride ld)
@@ -281,10 +309,11 @@ long frcnn_padded_pixels(int H, int W, int* row_pitch);
  *             (F.max_pooling_2d backward), zero elsewhere
  *   outputs : o (opt) NHWC hi/lo [H][W][C]; t (opt) transposed padded planes [planes][C][Kp], planes = 1 (at k) or 3
  *             (plane j at k holds pixel k + j - 1: the pre-shifted B operand of frcnn_gemm_nt_splitk groups = 9).
- * With y = p = NULL and planes = 3 this is the plain activation transposer. */
+ * With y = p = NULL and planes = 3 this is the plain activation transposer.  times2 != 0 doubles the result exactly
+ * (exponent + 1): the backward factor 1/(1-ratio) of a ratio-0.5 F.dropout whose kept set is {y > 0}. */
 int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, int ld_f32, const void* y_hi, const void* y_lo,
                        const void* p_hi, const void* p_lo, int H, int W, int C, void* o_hi, void* o_lo, void* t_hi, void* t_lo,
-                       int planes, void* stream);
+                       int planes, int times2, void* stream);
 
 /* dw[m][n][g] (the reference's OIHW float32, g = r*3+s or 1) = scale * sum over splits of parts[g][s][m][n], m < M;
  * parts slabs have M_parts >= M rows of ld floats. */

@@ -452,6 +452,48 @@ def rcnn_losses(cls_score, bbox_pred, use_gt_boxes, bbox_reg_targets, keep_inds,
     return f32(loss_cls), f32(loss_bbox), f32(acc), f32(loss_cls + loss_bbox), dcls.astype(f32), dbb.astype(f32)
 
 
+def rcnn_train_step(params, x, rois, keep_inds, labels, bbox_reg_targets, masks=None, delta=1.0, spatial_scale=1.0 / 16,
+                    dtype="float64"):
+    """The RCNN-mode forward/backward of train_rcnn.py (models/faster_rcnn.py:112-165 with rcnn_train=True), restated with
+    torch-CPU autograd (UNPINNED: Chainer absent).  rois (R,4): the proposals the (frozen, test-mode) RPN produced -- plain
+    arrays in the reference too, so no gradient reaches the RPN; keep_inds / labels / bbox_reg_targets: a ProposalTargetLayer
+    result; masks: the two F.dropout keep-masks (R,4096) (None = no dropout), applied as x*mask*2.
+    Returns dict(losses=(cls, bbox, acc, total), grads={trunk/*, fc6/*, fc7/*, cls_score/*, bbox_pred/*}, head=(R,105))."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    td = torch.float64 if dtype == "float64" else torch.float32
+    names = [k for k in params if k.startswith("trunk/") or k.split("/")[0] in ("fc6", "fc7", "cls_score", "bbox_pred")]
+    P = {k: torch.tensor(np.asarray(params[k]), dtype=td, requires_grad=True) for k in names}
+    h = torch.tensor(np.asarray(x), dtype=td)
+    for item in VGG16_LAYERS:
+        if item == "pool":
+            h = F.max_pool2d(h, 2, 2, ceil_mode=True)
+        else:
+            h = F.relu(F.conv2d(h, P["trunk/%s/W" % item[0]], P["trunk/%s/b" % item[0]], padding=1))
+    R = len(rois)
+    brois = torch.cat([torch.zeros((R, 1), dtype=td), torch.tensor(np.asarray(rois), dtype=td)], dim=1)
+    pool5 = torchvision.ops.roi_pool(h, brois, (7, 7), spatial_scale)
+    a6 = F.relu(F.linear(pool5.reshape(R, -1), P["fc6/W"], P["fc6/b"]))
+    if masks is not None:
+        a6 = a6 * torch.tensor(np.asarray(masks[0]), dtype=td) * 2.0
+    a7 = F.relu(F.linear(a6, P["fc7/W"], P["fc7/b"]))
+    if masks is not None:
+        a7 = a7 * torch.tensor(np.asarray(masks[1]), dtype=td) * 2.0
+    cls = F.linear(a7, P["cls_score/W"], P["cls_score/b"])
+    bb = F.linear(a7, P["bbox_pred/W"], P["bbox_pred/b"])
+    keep = torch.from_numpy(np.asarray(keep_inds, dtype=np.int64))
+    t = torch.from_numpy(np.asarray(labels, dtype=np.int64))
+    loss_cls = F.cross_entropy(cls[keep], t)
+    loss_bbox = F.huber_loss(bb[keep], torch.tensor(np.asarray(bbox_reg_targets), dtype=td), reduction="sum", delta=float(delta)) / len(keep)
+    loss = loss_cls + loss_bbox
+    loss.backward()
+    acc = float((cls[keep].argmax(1) == t).double().mean())
+    grads = {k: P[k].grad.detach().numpy().astype(np.float64) for k in names}
+    return dict(losses=(float(loss_cls.detach()), float(loss_bbox.detach()), acc, float(loss.detach())), grads=grads,
+                head=torch.cat([cls, bb], 1).detach().numpy())
+
+
 # --------------------------------------------------------------------------- ProposalLayer
 RPN_NMS_THRESH = 0.7                 # models/proposal_layer.py:51
 TRAIN_PRE, TRAIN_POST = 12000, 2000  # :52-53

@@ -502,3 +502,175 @@ def test_rpn_train_step_layerwise_and_end_to_end():
     l3 = tr.forward(_dev(x[0]), _dev(gt[0])).cpu().numpy()
     print("loss after 0/2 updates: %.5f -> %.5f" % (Lv[3], l3[3]))
     assert l3[3] < Lv[3]
+
+
+# ------------------------------------------------------------------ RCNN-head training (train_rcnn.py)
+def _golden_ptl():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "proposal_target_layer.npz"))
+
+
+@pytest.mark.parametrize("name", list(gi.PROPOSAL_TARGET_CASES))
+def test_proposal_target_layer_device(tops, name):
+    """frcnn_roi_overlaps + frcnn_roi_targets against the golden vectors of the reference's ProposalTargetLayer: best
+    overlaps / arg-max bit-exact (float64), and -- with the reference run's own kept indices -- its matched gt rows exactly
+    and its class-wise float32 targets (CUDA logf vs NumPy's float32 log: <= 2 ulp)."""
+    g = _golden_ptl()
+    props, gt, seed = gi.proposal_target_case(name)
+    rois = _dev(props)
+    mo, am = tops.roi_overlaps(rois, None, _dev(gt[0]))
+    np.random.seed(seed)
+    r = orc.proposal_target_layer(props, gt)
+    assert np.array_equal(mo.cpu().numpy(), r["max_overlaps"]) and np.array_equal(am.cpu().numpy(), r["argmax"].astype(np.int32))
+    keep = g[name + "_keep_inds"]
+    use_gt, ext, labels = tops.roi_targets(rois, _dev(gt[0]), am, _dev(keep), 21)
+    assert np.array_equal(use_gt.cpu().numpy(), g[name + "_use_gt_boxes"])
+    assert np.array_equal(labels.cpu().numpy(), g[name + "_use_gt_boxes"][:, 4].astype(np.int32))
+    want = g[name + "_bbox_reg_targets"]
+    got = ext.cpu().numpy()
+    assert np.array_equal(got == 0, want == 0)
+    ulp = _ulp_diff_f32(got, want)
+    print("%s: targets exact %.2f%%, max ulp %d" % (name, 100.0 * (ulp == 0).mean(), ulp.max()))
+    assert ulp.max() <= 2
+
+
+def test_rcnn_loss_and_gradient(tops):
+    props, gt, seed = gi.proposal_target_case("few_fg")
+    np.random.seed(seed)
+    r = orc.proposal_target_layer(props, gt)
+    rng = np.random.default_rng(4)
+    R, ld = len(props), 128
+    head = np.zeros((R, ld), f32)
+    head[:, :21] = rng.standard_normal((R, 21)) * 2
+    head[:, 21:105] = rng.standard_normal((R, 84)) * 0.8
+    lc, lb, acc, tot, dcls, dbb = orc.rcnn_losses(head[:, :21], head[:, 21:105], r["use_gt_boxes"], r["bbox_reg_targets"], r["keep_inds"])
+    losses, dh = tops.rcnn_loss(_dev(head), _dev(r["keep_inds"]), _dev(r["use_gt_boxes"][:, 4].astype(np.int32)),
+                                _dev(r["bbox_reg_targets"]), 21, 1.0)
+    L = losses.cpu().numpy()
+    assert abs(L[0] - float(lc)) < 2e-6 * max(1, float(lc)) and abs(L[1] - float(lb)) < 2e-6 * max(1, float(lb))
+    assert abs(L[2] - float(acc)) < 1e-6 and abs(L[3] - float(tot)) < 4e-6 * max(1, float(tot))
+    d = dh.cpu().numpy()
+    np.testing.assert_allclose(d[:, :21], dcls, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(d[:, 21:105], dbb, rtol=1e-5, atol=1e-9)
+    assert not d[:, 105:].any()
+
+
+def test_roi_pool_backward_matches_autograd_and_is_reproducible(tops):
+    import torchvision
+    from frcnn_b200 import ops
+    rng = np.random.default_rng(6)
+    H, W, C, R = 19, 25, 64, 40
+    feat = rng.standard_normal((C, H, W)).astype(f32)
+    t = torch.from_numpy(np.ascontiguousarray(feat.transpose(1, 2, 0))).cuda()
+    hi = t.to(torch.bfloat16)
+    fa = ops.Act(hi.contiguous(), (t - hi.float()).to(torch.bfloat16).contiguous())
+    fval = (fa.hi.float() + fa.lo.float()).cpu().numpy().transpose(2, 0, 1)
+    xy = rng.uniform(-10, 300, (R, 2))
+    wh = rng.uniform(5, 250, (R, 2))
+    rois = np.hstack([xy, xy + wh]).astype(f32)
+    g = rng.standard_normal((R, 49, C)).astype(f32)
+    gt_ = torch.from_numpy(g.reshape(1, R, 49 * C)).cuda()
+    ghi = gt_.to(torch.bfloat16)
+    ga = ops.Act(ghi.contiguous(), (gt_ - ghi.float()).to(torch.bfloat16).contiguous())
+    gval = (ga.hi.float() + ga.lo.float()).cpu().numpy().reshape(R, 7, 7, C)
+    count = torch.tensor([R - 3], dtype=torch.int32, device="cuda")          # the last 3 rows are beyond the valid count
+    d1 = tops.roi_pool_backward(fa, _dev(rois), count, ga).cpu().numpy()
+    d2 = tops.roi_pool_backward(fa, _dev(rois), count, ga).cpu().numpy()
+    assert np.array_equal(d1, d2)                                             # fixed-point accumulation: bit-reproducible
+    x = torch.from_numpy(fval).double()[None].requires_grad_(True)
+    br = torch.cat([torch.zeros((R - 3, 1), dtype=torch.float64), torch.from_numpy(rois[:R - 3]).double()], 1)
+    y = torchvision.ops.roi_pool(x, br, (7, 7), 1.0 / 16)
+    y.backward(torch.from_numpy(gval[:R - 3].transpose(0, 3, 1, 2)).double())
+    want = x.grad[0].numpy().transpose(1, 2, 0).reshape(H * W, C)
+    assert np.abs(d1 - want).max() <= 1e-6 * np.abs(want).max()
+
+
+def test_rcnn_train_step_layerwise_and_end_to_end():
+    """train_rcnn.py's update on the device (frcnn_b200.train_engine.RcnnTrainer) vs the autograd oracle, with the
+    proposals / kept set / dropout masks of the device run fed to the oracle.  As for the RPN step the end-to-end
+    gradient is discontinuous in the activations (ReLU, max-pool, RoI-pool arg-max), so the tight bars are local:
+    fc weight / data gradients vs float64 products of the device's own tensors (5e-5), exact ReLU+dropout masking,
+    RoI-pool backward vs autograd on the device's feature map; end to end: losses 2e-4, gradients 3e-2 of max-norm."""
+    from frcnn_b200.train_engine import RcnnTrainer
+    H, W = 296, 392
+    params, x, gt, info = _train_case(H, W, 5)
+    rng = np.random.default_rng(12)
+    for k in ("fc6/W", "fc7/W", "cls_score/W", "bbox_pred/W"):
+        params[k] = (rng.standard_normal(params[k].shape) * (0.002 if k == "fc6/W" else 0.01)).astype(f32)
+    gt[0, :, 4] = [3, 7, 1]
+    tr = RcnnTrainer(params, H, W, ANCHORS, post_n=100, sample="numpy")
+    np.random.seed(5)
+    losses = tr.forward(_dev(x[0]), _dev(gt[0]))
+    dbg = {}
+    tr.backward(debug=dbg)
+    torch.cuda.synchronize()
+    R = int(tr.prop.count.item())
+    keep = tr.keep.cpu().numpy()
+    rois = tr.prop.rois.cpu().numpy()[:R]
+    labels, ext = tr.labels.cpu().numpy(), tr.ext.cpu().numpy()
+    masks = [m.cpu().numpy()[:R] for m in tr.masks]
+    print("R=%d kept=%d fg-labels=%s" % (R, len(keep), np.bincount(labels)[:8]))
+    # the kept set is what the reference's ProposalTargetLayer draws from the same proposals under the same seed
+    np.random.seed(5)
+    ro = orc.proposal_target_layer(rois, gt)
+    assert np.array_equal(ro["keep_inds"], keep) and np.array_equal(ro["use_gt_boxes"], tr.use_gt.cpu().numpy())
+    assert _ulp_diff_f32(ext, ro["bbox_reg_targets"]).max() <= 2
+    # ---- local checks on the device's own tensors (float64 references)
+    f64 = lambda a: np.asarray(a, np.float64)
+    val = lambda a: (a.hi.float() + a.lo.float()).cpu().numpy()[0]             # [R_cap, C]
+    dyh = f64(tr.head_grad.cpu().numpy())                                      # [R_cap, ld]
+    fc7, fc6, pool5 = f64(val(tr.fc7)), f64(val(tr.fc6)), f64(val(tr.pool5))
+    Wh = f64(np.concatenate([params["cls_score/W"], params["bbox_pred/W"]], 0))
+    got_wh = np.concatenate([tr.grads("cls_score/W").cpu().numpy(), tr.grads("bbox_pred/W").cpu().numpy()], 0)
+    e = [_rel(got_wh, dyh[:, :105].T @ fc7)]
+    e.append(_rel(np.concatenate([tr.grads("cls_score/b").cpu().numpy(), tr.grads("bbox_pred/b").cpu().numpy()]), dyh[:, :105].sum(0)))
+    g7 = f64(dbg["fc7"]["g_in"].cpu().numpy().reshape(4096, -1).T)            # (C,1,R_cap) -> [R_cap, C]
+    e.append(_rel(g7, dyh[:, :105] @ Wh))
+    dy7 = f64(dbg["fc7"]["dy"].cpu().numpy().reshape(4096, -1).T)
+    assert np.array_equal(dy7, np.where(fc7 > 0, 2.0 * g7, 0.0))                # ReLU + dropout backward: exact
+    e.append(_rel(tr.grads("fc7/W").cpu().numpy(), dy7.T @ fc6))
+    e.append(_rel(tr.grads("fc7/b").cpu().numpy(), dy7.sum(0)))
+    g6 = f64(dbg["fc6"]["g_in"].cpu().numpy().reshape(4096, -1).T)
+    e.append(_rel(g6, dy7 @ f64(params["fc7/W"])))
+    dy6 = f64(dbg["fc6"]["dy"].cpu().numpy().reshape(4096, -1).T)
+    assert np.array_equal(dy6, np.where(fc6 > 0, 2.0 * g6, 0.0))
+    W6_hwc = f64(params["fc6/W"]).reshape(4096, 512, 49).transpose(0, 2, 1).reshape(4096, -1)
+    e.append(_rel(tr.grads("fc6/W").cpu().numpy(), dy6.T @ pool5))
+    e.append(_rel(tr.grads("fc6/b").cpu().numpy(), dy6.sum(0)))
+    dp5 = f64(dbg["roi"]["dpool5"].cpu().numpy().reshape(49 * 512, -1).T)
+    e.append(_rel(dp5, dy6 @ W6_hwc))
+    print("head local errors (dWh, dbh, dX7, dW7, db7, dX6, dW6, db6, dpool5):", ["%.1e" % v for v in e])
+    assert max(e) <= 5e-5
+    # RoI-pool backward on the device's feature map
+    import torchvision
+    feat = tr.feat.to_chw_f32().cpu().numpy()
+    xf = torch.from_numpy(feat).double()[None].requires_grad_(True)
+    br = torch.cat([torch.zeros((R, 1), dtype=torch.float64), torch.from_numpy(rois).double()], 1)
+    yp = torchvision.ops.roi_pool(xf, br, (7, 7), 1.0 / 16)
+    yp.backward(torch.from_numpy(dp5[:R].reshape(R, 7, 7, 512).transpose(0, 3, 1, 2)))
+    want_df = xf.grad[0].numpy().transpose(1, 2, 0).reshape(-1, 512)
+    assert np.abs(dbg["roi"]["dfeat"].cpu().numpy() - want_df).max() <= 1e-6 * np.abs(want_df).max()
+    # ---- end to end
+    want = orc.rcnn_train_step(params, x, rois, keep, labels, ext, masks)
+    Lv = losses.cpu().numpy()
+    print("losses", Lv, "oracle", want["losses"])
+    for i in (0, 1, 3):
+        assert abs(Lv[i] - want["losses"][i]) <= 2e-4 * max(1.0, want["losses"][i])
+    assert abs(Lv[2] - want["losses"][2]) <= 1.0 / len(keep) + 1e-6
+    exported = tr.export_params()
+    assert np.array_equal(exported["fc6/W"], params["fc6/W"])                   # (h,w,c) <-> (c,h,w) round trip
+    worst = 0.0
+    for name in tr.index:
+        gdev = tr.grads(name).cpu().numpy()
+        if name == "fc6/W":
+            gdev = gdev.reshape(4096, 49, 512).transpose(0, 2, 1).reshape(4096, -1)
+        e2e = _rel(gdev, want["grads"][name])
+        print("  e2e grad %-20s %.2e" % (name, e2e))
+        worst = max(worst, e2e)
+        assert np.abs(want["grads"][name]).max() > 0, name
+    print("end-to-end worst gradient error (of max-norm): %.2e" % worst)
+    assert worst <= 3e-2
+    # one update, then the loss on the same image / kept set / masks goes down
+    tr.update()
+    l2 = tr.forward(_dev(x[0]), _dev(gt[0]), keep_inds=tr.keep, masks=tr.masks).cpu().numpy()
+    print("loss_rcnn %.5f -> %.5f" % (Lv[3], l2[3]))
+    assert l2[3] < Lv[3]
