@@ -7,8 +7,8 @@ The whole graph (trunk -> RPN -> ProposalLayer -> RoI pool -> fc6/fc7 -> cls/bbo
 clip) is frcnn_b200.engine: hand-written sm_100a kernels behind the C ABI, replayed as ONE CUDA graph
 per image shape.  Link names / parameter paths are the reference's, so `serializers.load_npz` of a
 reference checkpoint (forward.py:29) fills this model.  RPN training mode (:114-116) returns rpn_loss computed on the
-device (targets + losses + head gradient, models/region_proposal_network.py); the RCNN training branch (:136-173) is a
-later "next" row and raises NotImplementedError.
+device (targets + losses + head gradient, models/region_proposal_network.py); RCNN training mode (:117-173) returns
+loss_rcnn from frcnn_b200.train_engine.RcnnTrainer (kept in `self.rcnn_trainer` for backward / update).
 """
 import os
 
@@ -106,7 +106,28 @@ class FasterRCNN(links.Link):
             # and the optimizer step are the remaining part of this "next" row.
             return self.RPN(self.trunk(x), img_info, gt_boxes)
         if gt_boxes is not None and self.rcnn_train:
-            raise NotImplementedError("RCNN training branch (models/faster_rcnn.py:136-173) is outside the forward path")
+            # RCNN training mode (:117-173): frozen test-mode RPN -> ProposalTargetLayer (NumPy-RNG sampling like the
+            # reference) -> RoI pool -> fc6/fc7 with dropout -> losses on the kept rows, all in frcnn_b200.train_engine.
+            # The trainer (weights, stored activations) is kept in self.rcnn_trainer: .backward() / .update() complete the
+            # train_rcnn.py step; loss_cls / cls_accuracy / loss_bbox are attributes like the reference's reports.
+            from frcnn_b200.train_engine import RcnnTrainer
+            fam = arrays.family(x)
+            t = arrays.to_device(x)
+            hw = arrays.to_host_ints(img_info)
+            pl = self.RPN.proposal_layer
+            tr = self.__dict__.get("rcnn_trainer")
+            key = (tuple(t.shape[2:]), self._version)
+            if tr is None or self.__dict__.get("_rcnn_trainer_key") != key:
+                tr = RcnnTrainer(self.param_dict(), int(t.shape[2]), int(t.shape[3]), pl._anchors, precision=self.precision,
+                                 feat_stride=self._feat_stride, num_classes=self._num_classes, delta=float(self._rcnn_delta),
+                                 post_n=pl._post_nms_top_n, pre_n=pl._pre_nms_top_n, nms_thresh=pl._nms_thresh,
+                                 min_size=pl._min_size, device=t.device)
+                self.__dict__["rcnn_trainer"], self.__dict__["_rcnn_trainer_key"] = tr, key
+            losses = tr.forward(t[0], arrays.to_device(gt_boxes)[0], im_info=(int(hw[0]), int(hw[1])))
+            vals = list(losses.cpu().numpy()) if fam == arrays.NUMPY else [arrays.from_device(losses[i].clone(), fam) for i in range(4)]
+            d = self.__dict__
+            d["loss_cls"], d["loss_bbox"], d["cls_accuracy"], d["loss_rcnn"] = [Variable(v) for v in vals]
+            return self.loss_rcnn
         fam = arrays.family(x)
         t = arrays.to_device(x)
         hw = arrays.to_host_ints(img_info)
