@@ -1,5 +1,9 @@
-"""One train_rpn.py step on the device: forward (trunk + RPN) -> AnchorTargetLayer -> rpn_loss -> backward through the
-RPN heads, the RPN 3x3 conv and the 13 trunk convs -> [gradient all-reduce] -> WeightDecay + MomentumSGD.
+"""The reference's two training steps on the device.
+
+RpnTrainer -- one train_rpn.py step: forward (trunk + RPN) -> AnchorTargetLayer -> rpn_loss -> backward through the RPN
+heads, the RPN 3x3 conv and the 13 trunk convs -> [gradient all-reduce] -> WeightDecay + MomentumSGD.
+RcnnTrainer -- one train_rcnn.py step: trunk -> frozen test-mode RPN -> ProposalTargetLayer -> RoI pool -> fc6/fc7 with
+dropout -> head losses -> backward through the head, the RoI pooling and the trunk -> the same optimizer.
 
 Mirrors /root/reference train_rpn.py:144-179 with `model.rpn_train = True`: FasterRCNN.__call__ takes the RPN training
 branch (models/faster_rcnn.py:114-116 -> models/region_proposal_network.py:117-156), the optimizer is
@@ -20,6 +24,8 @@ from . import ops, shard, train_ops
 from ._lib import FrcnnError
 from .engine import VGG16_LAYERS
 
+ROIS_PER_IMAGE, FG_FRACTION = 128, 0.25                          # models/proposal_target_layer.py:49-50
+FG_THRESH, BG_THRESH_HI, BG_THRESH_LO = 0.5, 0.5, 0.1            # :46-48
 TRUNK = [it for it in VGG16_LAYERS if it != "pool"]              # (name, cin, cout) x 13
 POOL_AFTER = {VGG16_LAYERS[i - 1][0] for i, it in enumerate(VGG16_LAYERS) if it == "pool"}
 
@@ -384,13 +390,13 @@ class RcnnTrainer(RpnTrainer):
     # ---------------------------------------------------------------- ProposalTargetLayer sampling (host, like the reference)
     def _sample(self, max_ov, R):
         mo = max_ov[:R].cpu().numpy()
-        n_fg_cap = int(train_ops_FG_FRACTION * train_ops_ROIS_PER_IMAGE)
-        fg = np.where(mo >= 0.5)[0]                                                          # :99
+        n_fg_cap = int(FG_FRACTION * ROIS_PER_IMAGE)
+        fg = np.where(mo >= FG_THRESH)[0]                                                    # :99
         n_fg = min(n_fg_cap, fg.size)
         if fg.size > 0:
             fg = np.random.choice(fg, size=n_fg, replace=False)                              # :105-110
-        bg = np.where((mo < 0.5) & (mo >= 0.1))[0]                                           # :113-114
-        n_bg = min(train_ops_ROIS_PER_IMAGE - n_fg, bg.size)
+        bg = np.where((mo < BG_THRESH_HI) & (mo >= BG_THRESH_LO))[0]                         # :113-114
+        n_bg = min(ROIS_PER_IMAGE - n_fg, bg.size)
         if bg.size > 0:
             bg = np.random.choice(bg, size=n_bg, replace=False)                              # :119-126
         return np.concatenate([fg, bg]).astype(np.int32)
@@ -501,5 +507,3 @@ class RcnnTrainer(RpnTrainer):
         self.update()
         return losses
 
-
-train_ops_ROIS_PER_IMAGE, train_ops_FG_FRACTION = 128, 0.25          # models/proposal_target_layer.py:49-50
