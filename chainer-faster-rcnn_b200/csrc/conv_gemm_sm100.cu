@@ -562,7 +562,7 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
     return FRCNN_OK;
 }
 
-static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0;
+static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0;
 
 static int device_sm_count() {
     static int sms = 0;
@@ -614,7 +614,9 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     while (p.tmem_cols < p.acc_bufs * p.acc_cols) p.tmem_cols *= 2;
     auto kern = conv_gemm_kernel<BN, BK, HALO, CG>;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int units = device_sm_count() / CG;            // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+    int ctas = device_sm_count();
+    if (g_max_ctas > 0 && g_max_ctas < ctas) ctas = g_max_ctas;      // several images in flight: each launch takes a share of the SMs
+    const int units = ctas / CG > 0 ? ctas / CG : 1;     // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
     const int grid = CG * (p.num_tiles < units ? p.num_tiles : units);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -638,6 +640,8 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
 using namespace frcnn;
 
 extern "C" void frcnn_conv2d_set_cta_group(int cta_group) { g_force_cg = cta_group; }
+
+extern "C" void frcnn_conv2d_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
 
 extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
     g_force_bn = block_n;

@@ -37,6 +37,7 @@ SIGNATURES = {
                              c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "frcnn_conv2d_set_tile": (None, [c_int, c_int, c_int]),
     "frcnn_conv2d_set_cta_group": (None, [c_int]),
+    "frcnn_conv2d_set_max_ctas": (None, [c_int]),
     "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "frcnn_pack_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

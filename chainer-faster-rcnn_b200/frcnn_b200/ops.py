@@ -208,6 +208,11 @@ def set_conv_cta_group(cta_group=0):
     _lib.load().frcnn_conv2d_set_cta_group(cta_group)
 
 
+def set_conv_max_ctas(max_ctas=0):
+    """Cap the persistent grid of later conv launches (0 = all SMs); baked into CUDA graphs at capture time."""
+    _lib.load().frcnn_conv2d_set_max_ctas(int(max_ctas))
+
+
 def maxpool2x2_ceil(x, out=None):
     H, W, C = x.hi.shape
     if out is None:

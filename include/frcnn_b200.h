@@ -115,6 +115,11 @@ void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w);
 /* 0 = automatic (CTA pairs / cta_group::2 for N tiles >= 128), 1 = force single-CTA MMAs, 2 = force pairs
  * where the tile allows it.  Process-wide; for tests and A/B timing. */
 void frcnn_conv2d_set_cta_group(int cta_group);
+/* Cap on the persistent grid of subsequent frcnn_conv2d launches (0 = all SMs).  With several independent images in
+ * flight on different streams, launches that each take a share of the SMs run side by side instead of queueing behind
+ * each other's 148-CTA grids, and a smaller grid quantises a layer's tile count into fuller waves.  The value is baked
+ * into a CUDA graph at capture time. */
+void frcnn_conv2d_set_max_ctas(int max_ctas);
 
 /* OIHW fp32 weights (Chainer layout, e.g. trunk/conv1_1/W) -> [kh*kw, Cout, Cin_pad] bf16 hi/lo.
  * For Linear weights (Cout, K) pass kh=kw=1.  `perm_chw_to_hwc` != 0 with (c,h,w) = (pc,ph,pw)
