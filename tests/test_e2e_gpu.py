@@ -227,3 +227,76 @@ def test_headline_config_600x1000(params):
     keep_idx, keep_count, conf_count = [t.cpu().numpy() for t in plan.det]
     for c, keep, dets in orc.detect(p, b, 0.3, 0.05):
         assert keep_idx[c - 1, :conf_count[c - 1]].tolist() == keep.tolist()
+
+
+# ------------------------------------------------------------------ edge cases of the whole graph and error paths
+def test_engine_zero_proposals_and_tiny_image(params):
+    """min_size larger than the image: the ProposalLayer keeps nothing; every later stage must cope with R == 0 (empty
+    outputs, zero buffers, a replayable graph).  And the smallest legal image: one feature-map cell."""
+    H, W = 96, 128
+    x = orc.make_image(H, W, seed=9)
+    for use_graph in (False, True):
+        eng = _engine(params, "bf16x3", use_graph=use_graph, with_detect=True, min_size=10000)
+        prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+        prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())               # second call: graph replay
+        assert prob.shape == (0, 21) and boxes.shape == (0, 84) and int(plan.prop.count.item()) == 0
+        assert not plan.prob.any().item() and not plan.boxes.any().item()
+        assert not plan.det[1].any().item()                                  # keep_count of every class is 0
+    want_rois, _ = orc.proposal_layer(np.full((1, 18, 6, 8), 1 / 18, f32), np.zeros((1, 36, 6, 8), f32), (H, W), min_size=10000)
+    assert len(want_rois) == 0
+    xs = orc.make_image(16, 16, seed=1)                                       # 16x16 -> a 1x1 feature map
+    eng = _engine(params, "bf16x3", use_graph=False)
+    prob, boxes, plan = eng(torch.from_numpy(xs[0]).cuda())
+    assert (plan.fh, plan.fw) == (1, 1)
+    feat_ref = orc.vgg16_forward(xs, params)
+    assert _rel(plan.acts[-1].to_chw_f32().cpu().numpy()[None], feat_ref) < 1e-4
+    rpn = plan.rpn_out.cpu().numpy()
+    want_rois, _ = orc.proposal_layer(orc.softmax_axis1(rpn[:, :18].T.reshape(1, 18, 1, 1)), rpn[:, 18:54].T.reshape(1, 36, 1, 1),
+                                      np.array([[16, 16]], np.int32))
+    R = prob.shape[0]
+    assert R == len(want_rois) and np.array_equal(plan.prop.rois.cpu().numpy()[:R], want_rois)
+
+
+def test_portrait_maximum_size_1000x600(params):
+    """The other orientation of the reference's size rule (forward.py:34-45: longest side capped at 1000): 1000 x 600."""
+    H, W = 1000, 600
+    x = orc.make_image(H, W, seed=3)
+    eng = _engine(params, "bf16x3", use_graph=True)
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    assert (plan.fh, plan.fw) == (63, 38) and 0 < prob.shape[0] <= 300
+    rpn = plan.rpn_out.cpu().numpy()
+    logits = rpn[:, :18].T.reshape(1, 18, 63, 38)
+    deltas = rpn[:, 18:54].T.reshape(1, 36, 63, 38)
+    want_rois, want_fg = orc.proposal_layer(orc.softmax_axis1(logits), deltas, np.array([[H, W]], np.int32))
+    R = prob.shape[0]
+    assert R == len(want_rois) and np.array_equal(plan.prop.rois.cpu().numpy()[:R], want_rois)      # bit-exact at full size
+    np.testing.assert_allclose(prob.sum(1).cpu().numpy(), 1.0, rtol=1e-5)
+    b = boxes.cpu().numpy()
+    assert (b[:, 0::4] >= 0).all() and (b[:, 2::4] <= W - 1).all() and (b[:, 1::4] >= 0).all() and (b[:, 3::4] <= H - 1).all()
+
+
+def test_argument_errors_raise_instead_of_crashing(params):
+    """The C ABI reports bad arguments through its status code + frcnn_last_error(); the Python layer raises FrcnnError."""
+    from frcnn_b200 import ops
+    from frcnn_b200._lib import FrcnnError
+    x = ops.Act(torch.zeros((8, 8, 64), dtype=torch.bfloat16, device="cuda"), torch.zeros((8, 8, 64), dtype=torch.bfloat16, device="cuda"))
+    w = torch.zeros((64, 64, 3, 3), device="cuda")
+    hi, lo = ops.pack_conv_weights(w, cin_pad=64)
+    b = ops.pad_bias(torch.zeros(64, device="cuda"), 64)
+    with pytest.raises(FrcnnError):
+        ops.conv2d(x, hi, lo, b, 1, True)                                     # 9 taps of weights for a 1x1 call
+    with pytest.raises(FrcnnError):
+        ops.conv2d(x, hi, None, b, 3, True)                                   # precision modes differ
+    with pytest.raises(FrcnnError):
+        ops.conv2d(x, hi, lo, torch.zeros(8, device="cuda"), 3, True)         # bias too short
+    x48 = ops.Act(torch.zeros((8, 8, 48), dtype=torch.bfloat16, device="cuda"), torch.zeros((8, 8, 48), dtype=torch.bfloat16, device="cuda"))
+    h48, l48 = ops.pack_conv_weights(torch.zeros((64, 48, 3, 3), device="cuda"), cin_pad=48)
+    with pytest.raises(FrcnnError, match="Cin"):
+        ops.conv2d(x48, h48, l48, b, 3, True)                                 # 32 < Cin < 64 is not a supported K tiling
+    with pytest.raises(FrcnnError):
+        ops.pack_image(torch.zeros((3, 8, 8)), c_pad=16)                      # host tensor: the library has no CPU path
+    with pytest.raises(FrcnnError):
+        ops.nms(torch.zeros((4, 5)), 0.7)
+    # the library is still usable afterwards
+    y, _ = ops.conv2d(x, hi, lo, b, 3, True)
+    assert y.hi.shape == (8, 8, 64)
