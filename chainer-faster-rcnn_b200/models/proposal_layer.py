@@ -1,7 +1,7 @@
 """models.proposal_layer.ProposalLayer -- same class, constants, `train` switch and call signature as
 /root/reference models/proposal_layer.py:30-221, with the whole body of __call__ (:126-198) replaced by
 ONE stream-ordered C-ABI call, frcnn_proposals: anchor grid from the index, decode, clip, min-size
-filter, fg-score slice, radix-select + bitonic top-N, bitmask NMS with a device-side scan, top-N.
+filter, fg-score slice, radix-select + chip-wide rank sort of the top-N, bitmask NMS with a device-side scan, top-N.
 The reference's three host<->device round trips (:161-163, :176-177, :195-196) are gone; the only
 synchronisation is reading the proposal count to size the returned arrays.
 """

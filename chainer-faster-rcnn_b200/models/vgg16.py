@@ -6,7 +6,7 @@ and conv4_3.  Link names are the reference's (conv1_1 ... conv5_3) so checkpoint
 `VGG16` in the reference derives from chainer's VGG16Layers and would download a caffemodel; here
 both classes start from random weights and differ only in name.
 
-__call__(x) runs on the GPU: frcnn_pack_image, 13x frcnn_conv2d (tcgen05), 4x frcnn_maxpool2x2_ceil.
+__call__(x) runs on the GPU: frcnn_pack_image_im2col3x3, 13x frcnn_conv2d (tcgen05) with the 4 ceil-mode pools fused into the epilogue.
 """
 import numpy as np
 import torch
