@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
                 cand &= ~di;
                 cand &= ~(1ull << i);
             }
+            __syncwarp();                    // every lane has read s_total (above) before lane 0 overwrites it
             if (lane == 0) { s_nk = nk; s_total = total; }
         }
         __syncthreads();
