@@ -256,14 +256,17 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---------------- device-timed value: inputs resident in HBM
     from frcnn_b200.engine import LanePool
     pool = LanePool(plan, lanes=args.in_flight)      # args.in_flight independent images in flight (one stream + graph each)
+    # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from the warm-up through the timed region and the
+    # one-image-in-flight repeat of it: the GPU is under the same load throughout, and a 25 ms timed region alone would
+    # yield a single sample
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     pool.fork()
     for i in range(max(args.warmup, 3)):
         pool.submit(i, imgs_dev[i % n_img])
     pool.join()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -274,7 +277,6 @@ def run_b200_arm(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     R_last = int(plan.prop.count.item())
     # the same K steps with ONE image in flight (no overlap between images): reported beside the headline
     barrier()
@@ -284,6 +286,7 @@ def run_b200_arm(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms_single = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
     # per-launch times of the tensor-core kernel, taken right here: same thermal / power state as the timed region above
     table = conv_layer_table(plan, torch) if rank == 0 else None
     from frcnn_b200 import shard
@@ -570,7 +573,7 @@ def run_resnet_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
