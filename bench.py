@@ -503,6 +503,60 @@ def run_train_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_train_rcnn_arm(args, rank, local_rank, world):
+    """Secondary workload: one train_rcnn.py step per image (frozen RPN -> ProposalTargetLayer -> RoI pool -> fc6/fc7 with
+    dropout -> losses -> backward through head, RoI pool and trunk -> MomentumSGD), device-side sampling disabled: the
+    reference-faithful NumPy sampling (one small D2H per step) is what is timed.  Not the headline."""
+    import torch
+    import frcnn_oracle as orc
+    from frcnn_b200 import shard
+    from frcnn_b200.train_engine import RcnnTrainer
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+    params = orc.make_params(seed=1234)
+    tr = RcnnTrainer(params, H_IMG, W_IMG, anchors, precision=args.precision, lr=1e-5)
+    imgs = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=shard.image_seed(rank, i))[0]).cuda() for i in range(4)]
+    gt = torch.tensor([[100, 120, 400, 380, 3], [500, 200, 900, 560, 7], [50, 50, 200, 180, 1], [600, 30, 780, 150, 5]],
+                      dtype=torch.float32).cuda()
+    np.random.seed(1234 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for i in range(max(args.warmup, 3)):
+        tr.step(imgs[i % 4], gt)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        tr.step(imgs[i % 4], gt)
+    e1.record()
+    barrier()
+    ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": "images/sec through the train_rcnn.py step @600x1000 (300 proposals, 128 RoIs per image)",
+            "value": world * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "train_rcnn.py step, trunk + fc6/fc7/cls_score/bbox_pred trainable, one 600x1000 image per GPU "
+                                   "per step (secondary workload)", "kept_rois_last_step": int(tr.keep.numel()),
+                       "last_losses_cls_bbox_acc_total": [float(v) for v in tr.last_losses.cpu().numpy()]},
+            "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_resnet_arm(args, rank, local_rank, world):
     """Secondary workload (BASELINE config #4, a "next" row): ResNet-101 trunk Faster R-CNN forward, 800x1333, 1000 proposals,
     one image per GPU.  Device-timed with inputs resident in HBM, args.in_flight images in flight.  Not the headline."""
@@ -579,7 +633,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "resnet101"],
+    ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -598,6 +652,9 @@ def main():
         return
     if args.workload == "resnet101":
         run_resnet_arm(args, rank, local_rank, world)
+        return
+    if args.workload == "train_rcnn":
+        run_train_rcnn_arm(args, rank, local_rank, world)
         return
     run_b200_arm(args, rank, local_rank, world)
 

@@ -202,8 +202,8 @@ def test_bf16_fast_mode_runs_and_is_close(params):
 
 
 def test_headline_config_600x1000(params):
-    """BASELINE config #2 at full size: 600x1000, 300 proposals.  Size-independent properties +
-    exact ProposalLayer parity on the device's own RPN outputs + detect vs the oracle."""
+    """BASELINE config #2 at full size: 600x1000, 300 proposals.  Size-independent properties, exact ProposalLayer
+    parity on the device's own RPN outputs, detect vs the oracle, and the float tolerances at this size."""
     H, W = 600, 1000
     x = orc.make_image(H, W, seed=0)
     info = np.array([[H, W]], np.int32)
@@ -227,6 +227,19 @@ def test_headline_config_600x1000(params):
     keep_idx, keep_count, conf_count = [t.cpu().numpy() for t in plan.det]
     for c, keep, dets in orc.detect(p, b, 0.3, 0.05):
         assert keep_idx[c - 1, :conf_count[c - 1]].tolist() == keep.tolist()
+    # float parity AT the headline size (the north star's 1e-4): trunk vs the fp32 oracle, head on the device's own
+    # feature map and RoIs (RoI pool exact), class probabilities and boxes
+    feat_dev = plan.acts[-1].to_chw_f32().cpu().numpy()[None]
+    e_feat = _rel(feat_dev, orc.vgg16_forward(x, params))
+    rois_dev = plan.prop.rois.cpu().numpy()[:R]
+    cls_ref, box_ref, aux = orc.head_forward(feat_dev, rois_dev, params, info)
+    pool_dev = (plan.pool5.hi.float() + plan.pool5.lo.float()).cpu().numpy().reshape(-1, 7, 7, 512)[:R]
+    assert np.array_equal(pool_dev.transpose(0, 3, 1, 2), aux["pool5"])
+    e_fc7 = _rel((plan.fc7.hi.float() + plan.fc7.lo.float()).cpu().numpy()[0, :R], aux["fc7"])
+    e_box = _rel(b, box_ref)
+    print("600x1000: conv5_3 %.2e, fc7 %.2e, boxes %.2e of max-norm vs the fp32 oracle" % (e_feat, e_fc7, e_box))
+    assert e_feat < 1e-4 and e_fc7 < 1e-4 and e_box < 1e-4
+    _check_probs(p, cls_ref)
 
 
 # ------------------------------------------------------------------ edge cases of the whole graph and error paths
