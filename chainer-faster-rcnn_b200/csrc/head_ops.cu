@@ -102,27 +102,47 @@ __global__ void pack_weights_kernel(const float* w, int Cout, int Cin, int taps,
 // borders, zeros for k >= 9*C).  conv1_1 (C_in = 3, K = 27) then runs as ONE 64-byte-row k-block per tile
 // instead of nine 32-byte-row blocks.  One thread per pixel; neighbouring threads share their loads in L1.
 __global__ void pack_image_im2col_kernel(const float* x, int C, int H, int W, __nv_bfloat16* hi, __nv_bfloat16* lo) {
-    // 4 threads per pixel, each producing one 16-byte chunk (8 consecutive k): consecutive threads write
-    // consecutive 16-B chunks -> fully coalesced stores of both planes.
-    const long total = (long)H * W * 4;
-    const int kmax = 9 * C;
-    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-        const long p = t >> 2;
-        const int q = (int)(t & 3);
+    // One thread per pixel: its 9 taps x C channels are 9*C scalar loads that coalesce across the warp (consecutive
+    // threads = consecutive w), then 4 + 4 16-byte stores of the pixel's 64-byte hi / lo rows.
+    const long total = (long)H * W;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
         const int h = (int)(p / W), w = (int)(p % W);
-        F8 f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = 8 * q + j;
-            float v = 0.0f;
-            if (k < kmax) {
-                const int tap = k / C, c = k - tap * C;
-                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((long)c * H + hh) * W + ww];
+        if (C != 3) {                                   // generic (C = 1, 2): one 8-value chunk at a time
+            for (int q = 0; q < 4; ++q) {
+                F8 f;
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 8 * q + j;
+                    float val = 0.0f;
+                    if (k < 9 * C) {
+                        const int tap = k / C, c = k - tap * C;
+                        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = x[((long)c * H + hh) * W + ww];
+                    }
+                    f.v[j] = val;
+                }
+                store8(hi, lo, p * 32 + 8 * q, f);
             }
-            f.v[j] = v;
+            continue;
         }
-        store8(hi, lo, p * 32 + 8 * q, f);
+        float v[32];                                    // C == 3: every index below is a compile-time constant (registers)
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                const long o = (long)hh * W + ww;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[tap * 3 + c] = x[(long)c * H * W + o];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            F8 f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f.v[j] = v[8 * q + j];
+            store8(hi, lo, p * 32 + 8 * q, f);
+        }
     }
 }
 
@@ -431,7 +451,7 @@ extern "C" int frcnn_preprocess_bgr8(const unsigned char* img_hwc, int h0, int w
 
 extern "C" int frcnn_pack_image_im2col3x3(const float* x_chw, int C, int H, int W, void* y_hi, void* y_lo, void* stream) {
     FRCNN_REQUIRE(x_chw && y_hi && C > 0 && C <= 3 && H > 0 && W > 0, "frcnn_pack_image_im2col3x3: needs 1 <= C <= 3 (got %d)", C);
-    pack_image_im2col_kernel<<<grid_for((long)H * W * 4, 256), 256, 0, (cudaStream_t)stream>>>(
+    pack_image_im2col_kernel<<<grid_for((long)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
         x_chw, C, H, W, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
