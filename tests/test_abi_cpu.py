@@ -134,3 +134,24 @@ def test_product_path_never_imports_the_oracle():
                 if re.search(r"frcnn_oracle|oracle_c|import\s+build_ref|from\s+oracle", txt):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_compute_calls_fail_loudly_without_a_gpu():
+    """No CPU fallback anywhere: on a box without a usable GPU a compute entry point returns FRCNN_ERR_CUDA with the CUDA
+    runtime's message (it never computes on the host, never crashes), and the Python wrappers refuse host tensors."""
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from frcnn_b200 import _lib, ops
+    lib = _lib.load()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)                         # noqa: E731
+    b, q, o = np.zeros((4, 4)), np.zeros((2, 4)), np.zeros((4, 2))
+    assert lib.frcnn_bbox_overlaps(p(b), 4, p(q), 2, p(o), None) == _lib.ERR_CUDA
+    assert "CUDA" in _lib.last_error() or "cuda" in _lib.last_error()
+    d, k = np.zeros((3, 5), np.float32), np.zeros(3, np.int32)
+    assert lib.frcnn_cpu_nms_host(p(d), 3, 0.7, p(k), 0) < 0
+    with pytest.raises(_lib.FrcnnError):
+        ops.nms(torch.zeros((4, 5)), 0.7)
+    with pytest.raises(_lib.FrcnnError):
+        ops.cpu_nms_host(d, 0.7)
