@@ -730,3 +730,40 @@ def test_faster_rcnn_class_rcnn_training_branch(dropin_installed):
         tr.keep.numel(), int(tr.prop.count.item())))
     # (that a step lowers the loss on a fixed kept set is asserted in test_rcnn_train_step_layerwise_and_end_to_end; here the
     #  proposals themselves move with the trunk, so the two losses are not comparable)
+
+
+def test_single_pass_bf16_mode_of_the_training_and_resnet_paths():
+    """The `bf16` fast mode (lo planes absent) through every added kernel family: finite results close to the bf16x3 ones."""
+    from frcnn_b200.resnet_engine import ResNetEngine
+    from frcnn_b200.train_engine import RcnnTrainer, RpnTrainer
+    H, W = 200, 264
+    params, x, gt, info = _train_case(H, W, 7)
+    gt[0, :, :4] = [[20, 30, 150, 170], [100, 20, 250, 190], [60, 80, 200, 180]]
+    xd, gd = _dev(x[0]), _dev(gt[0])
+    res = {}
+    for prec in ("bf16x3", "bf16"):
+        tr = RpnTrainer(params, H, W, ANCHORS, precision=prec, subsample="none")
+        l = tr.forward(xd, gd).cpu().numpy()
+        tr.backward()
+        assert bool(torch.isfinite(tr.g_flat).all())
+        res[prec] = (l, tr.grads("trunk/conv3_2/W").cpu().numpy().copy(), tr.grads("RPN/rpn_conv_3x3/b").cpu().numpy().copy())
+        tr.update()
+    assert abs(res["bf16"][0][3] - res["bf16x3"][0][3]) < 2e-2 * max(1.0, res["bf16x3"][0][3])
+    assert _rel(res["bf16"][1], res["bf16x3"][1]) < 0.1 and _rel(res["bf16"][2], res["bf16x3"][2]) < 0.1
+    keep = None
+    for prec in ("bf16x3", "bf16"):
+        rc = RcnnTrainer(params, H, W, ANCHORS, precision=prec, post_n=60, dropout=(prec == "bf16x3"))
+        np.random.seed(1)
+        l = rc.forward(xd, gd, keep_inds=keep).cpu().numpy()
+        rc.backward()
+        assert bool(torch.isfinite(rc.g_flat).all()) and np.isfinite(l).all()
+        rc.update()
+        assert bool(torch.isfinite(rc.w_flat).all())
+    rp = orc.make_resnet_params(50, seed=3)
+    feats = {}
+    for prec in ("bf16x3", "bf16"):
+        eng = ResNetEngine(rp, 50, precision=prec, anchors=ANCHORS, use_graph=False, post_n=50)
+        p, b, plan = eng(torch.from_numpy(orc.make_image(128, 160, seed=2)[0]).cuda())
+        feats[prec] = plan.acts[-1].to_chw_f32().cpu().numpy()
+        assert np.isfinite(feats[prec]).all() and p.shape[1] == 21
+    assert _rel(feats["bf16"], feats["bf16x3"]) < 5e-2
