@@ -155,3 +155,23 @@ def test_compute_calls_fail_loudly_without_a_gpu():
         ops.nms(torch.zeros((4, 5)), 0.7)
     with pytest.raises(_lib.FrcnnError):
         ops.cpu_nms_host(d, 0.7)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/frcnn_b200.h must be consumable from C (the reference-side bindings are Cython / cgo-style C callers):
+    a C99 translation unit that takes the address of every declared entry point compiles with -Wall -Werror and links
+    against libfrcnn_b200.so; running it prints the library version (no GPU needed)."""
+    from frcnn_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = sorted(_lib.SIGNATURES)
+    src = ['#include <stdio.h>', '#include "frcnn_b200.h"', "int main(void) {", "    const void* fns[] = {"]
+    src += ["        (const void*)&%s," % n for n in names]
+    src += ["    };", '    printf("%d %d\\n", frcnn_version(), (int)(sizeof(fns) / sizeof(fns[0])));', "    return 0;", "}"]
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(root, "include"), str(c), "-o", str(exe),
+                           "-L", libdir, "-lfrcnn_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert int(out[0]) >= 100 and int(out[1]) == len(names)
