@@ -421,3 +421,21 @@ def test_detections_assembly_matches_forward_py_loop(ops):
             x1, y1, x2, y2 = map(int, d[:4] / 1.6)                           # forward.py:58
             want.append((c, x1, y1, x2, y2, float(d[4])))
     assert got == want and len(got) > 0
+
+
+@pytest.mark.parametrize("x3", [True, False])
+def test_long_k_gemm_rotating_accumulators_exact(ops, x3):
+    """K = 25,088 (fc6) runs with three rotating TMEM accumulators (ConvParams::nacc): on small-integer operands every
+    partial sum is exactly representable, so the result must equal the integer GEMM exactly -- in both precision modes --
+    and a K just below the switch-over (one accumulator) must agree too."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for K in (25088, 16320):                       # 392 k-blocks (rotation on) / 255 k-blocks (rotation off)
+        M, N = 300, 128
+        x = torch.randint(-2, 3, (1, M, K), device="cuda", generator=g).float()
+        w = torch.randint(-2, 3, (N, K), device="cuda", generator=g).float()
+        b = torch.randint(-5, 6, (N,), device="cuda", generator=g).float()
+        xa = ops.Act(x.to(torch.bfloat16), torch.zeros_like(x, dtype=torch.bfloat16) if x3 else None)
+        hi, lo = ops.pack_conv_weights(w, precision="bf16x3" if x3 else "bf16")
+        y, y32 = ops.conv2d(xa, hi, lo, ops.pad_bias(b, N), 1, False, out_act=False, ld_f32=N)
+        want = (x[0].double() @ w.double().T + b.double()).float()
+        assert torch.equal(y32, want), (K, x3, float((y32 - want).abs().max()))
