@@ -71,6 +71,29 @@ __global__ void roi_targets_kernel(const float* __restrict__ rois, const float* 
         for (int j = 0; j < 4; ++j) row[4 * cls + j] = t[j];
 }
 
+// Stand-alone array helpers of models/bbox_transform.py (training side): bbox_transform (:18-38) on float32 rows and the
+// keep_inside predicate (:112-130).  gt rows may be wider than 4 (gt_stride floats per row).
+__global__ void bbox_transform_kernel(const float* __restrict__ ex, const float* __restrict__ gt, int gt_stride, int n,
+                                      float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 e = reinterpret_cast<const float4*>(ex)[i];
+    const float* q = gt + (size_t)i * gt_stride;
+    const float ew = __fadd_rn(__fsub_rn(e.z, e.x), 1.0f), eh = __fadd_rn(__fsub_rn(e.w, e.y), 1.0f);
+    const float ecx = __fadd_rn(e.x, __fmul_rn(0.5f, ew)), ecy = __fadd_rn(e.y, __fmul_rn(0.5f, eh));
+    const float gw = __fadd_rn(__fsub_rn(q[2], q[0]), 1.0f), gh = __fadd_rn(__fsub_rn(q[3], q[1]), 1.0f);
+    const float gcx = __fadd_rn(q[0], __fmul_rn(0.5f, gw)), gcy = __fadd_rn(q[1], __fmul_rn(0.5f, gh));
+    reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn(__fsub_rn(gcx, ecx), ew), __fdiv_rn(__fsub_rn(gcy, ecy), eh),
+                                                   logf(__fdiv_rn(gw, ew)), logf(__fdiv_rn(gh, eh)));
+}
+
+__global__ void keep_inside_kernel(const float* __restrict__ boxes, int n, float im_h, float im_w, unsigned char* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = reinterpret_cast<const float4*>(boxes)[i];
+    flags[i] = (b.x >= 0.f && b.y >= 0.f && b.z < im_w && b.w < im_h) ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------ losses + head gradient
 // One warp per kept row; per-row results go to shared memory and thread 0 adds them in row order (deterministic).
 __global__ void __launch_bounds__(1024) rcnn_loss_kernel(const float* __restrict__ head, int ld, int R_cap, const int* __restrict__ keep,
@@ -224,6 +247,24 @@ int frcnn_roi_targets(const float* rois, const float* gt_boxes, const int* argma
     if (n == 0) return FRCNN_OK;
     roi_targets_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(rois, gt_boxes, argmax, keep_inds, n, num_classes,
                                                                      use_gt_boxes, bbox_reg_targets, labels);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+int frcnn_bbox_transform(const float* ex_rois, const float* gt_rois, int gt_stride, int n, float* out, void* stream) {
+    FRCNN_REQUIRE(n >= 0 && gt_stride >= 4, "bbox_transform: bad arguments");
+    if (n == 0) return FRCNN_OK;
+    FRCNN_REQUIRE(ex_rois && gt_rois && out, "bbox_transform: null pointer");
+    bbox_transform_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(ex_rois, gt_rois, gt_stride, n, out);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+int frcnn_keep_inside(const float* boxes, int n, int im_h, int im_w, unsigned char* flags, void* stream) {
+    FRCNN_REQUIRE(n >= 0, "keep_inside: bad arguments");
+    if (n == 0) return FRCNN_OK;
+    FRCNN_REQUIRE(boxes && flags, "keep_inside: null pointer");
+    keep_inside_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(boxes, n, (float)im_h, (float)im_w, flags);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }

@@ -80,6 +80,8 @@ SIGNATURES = {
     "frcnn_subsample2x": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_roi_overlaps": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_roi_targets": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "frcnn_bbox_transform": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "frcnn_keep_inside": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "frcnn_rcnn_loss": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_double, c_void_p,
                                 c_void_p, c_void_p]),
     "frcnn_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_void_p]),

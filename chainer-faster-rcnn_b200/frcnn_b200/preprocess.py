@@ -7,8 +7,6 @@ The raw uint8 BGR image is uploaded (4x+ fewer H2D bytes than the float32 tensor
 subtraction + OpenCV-compatible bilinear resize + HWC->CHW run in frcnn_preprocess_bgr8; per-class NMS + confidence
 filter run in frcnn_detect.  Drawing (cv.rectangle / putText) stays out of scope.
 """
-import ctypes
-
 import numpy as np
 import torch
 

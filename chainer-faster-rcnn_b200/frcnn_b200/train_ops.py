@@ -270,3 +270,23 @@ def roi_pool_backward(feat, rois, count, g, outh=7, outw=7, scale=1.0 / 16, out=
     check(lib.frcnn_roi_pool_backward(_p(feat.hi), _p(feat.lo), H, W, C, _p(rois), _p(count), R, outh, outw, float(scale),
                                       _p(g.hi), _p(g.lo), _p(out), _p(ws), ws.numel(), _stream()), "frcnn_roi_pool_backward")
     return out
+
+
+def bbox_transform(ex_rois, gt_rois):
+    """frcnn_bbox_transform: ex [n,4], gt [n,>=4] float32 CUDA -> targets [n,4] (models/bbox_transform.py:18-38)."""
+    _need_cuda(ex_rois, gt_rois)
+    e, g = ex_rois.contiguous().float(), gt_rois.contiguous().float()
+    if e.shape[0] != g.shape[0] or e.shape[1] != 4 or g.shape[1] < 4:
+        raise FrcnnError("bbox_transform: expected (n,4) and (n,>=4), got %s and %s" % (tuple(e.shape), tuple(g.shape)))
+    out = torch.empty((e.shape[0], 4), dtype=torch.float32, device=e.device)
+    check(_lib.load().frcnn_bbox_transform(_p(e), _p(g), g.shape[1], e.shape[0], _p(out), _stream()), "frcnn_bbox_transform")
+    return out
+
+
+def keep_inside_flags(boxes, im_h, im_w):
+    """frcnn_keep_inside: boxes [n,4] float32 CUDA -> uint8 [n] (1 = fully inside the image)."""
+    _need_cuda(boxes)
+    b = boxes.contiguous().float()
+    flags = torch.empty((b.shape[0],), dtype=torch.uint8, device=b.device)
+    check(_lib.load().frcnn_keep_inside(_p(b), b.shape[0], int(im_h), int(im_w), _p(flags), _stream()), "frcnn_keep_inside")
+    return flags

@@ -5,10 +5,9 @@ functions on the forward path (bbox_transform_inv, clip_boxes, filter_boxes) run
 libfrcnn_b200.so (frcnn_bbox_decode) with bit-identical arithmetic to the fused kernels;
 bbox_transform / keep_inside are training-side helpers ("next" rows) kept as plain array code.
 """
-import numpy as np
 import torch
 
-from frcnn_b200 import arrays, ops
+from frcnn_b200 import arrays, ops, train_ops
 
 
 def bbox_transform_inv(boxes, trans):
@@ -47,22 +46,19 @@ def filter_boxes(boxes, min_size):
 
 
 def keep_inside(anchors, img_info):
-    """Indices + rows of anchors lying fully inside the image (reference :112-130; training side)."""
+    """Indices + rows of anchors lying fully inside the image (reference :112-130; training side): the predicate is
+    frcnn_keep_inside, the index compaction is plumbing."""
     fam = arrays.family(anchors)
     a = arrays.to_device(anchors)
     hw = arrays.to_host_ints(img_info)
-    ok = (a[:, 0] >= 0) & (a[:, 1] >= 0) & (a[:, 2] < float(hw[1])) & (a[:, 3] < float(hw[0]))
-    idx = torch.nonzero(ok, as_tuple=False).reshape(-1)
+    flags = train_ops.keep_inside_flags(a[:, :4], int(hw[0]), int(hw[1]))
+    idx = torch.nonzero(flags, as_tuple=False).reshape(-1)
     return arrays.from_device(idx, fam), arrays.from_device(a[idx], fam)
 
 
 def bbox_transform(ex_rois, gt_rois):
-    """Regression targets (dx, dy, dw, dh) of gt boxes w.r.t. example boxes (reference :18-38; training side)."""
+    """Regression targets (dx, dy, dw, dh) of gt boxes w.r.t. example boxes (reference :18-38; training side), float32
+    rows through frcnn_bbox_transform."""
     fam = arrays.family(ex_rois)
     e, g = arrays.to_device(ex_rois), arrays.to_device(gt_rois)
-    ew, eh = e[:, 2] - e[:, 0] + 1.0, e[:, 3] - e[:, 1] + 1.0
-    gw, gh = g[:, 2] - g[:, 0] + 1.0, g[:, 3] - g[:, 1] + 1.0
-    ecx, ecy = e[:, 0] + 0.5 * ew, e[:, 1] + 0.5 * eh
-    gcx, gcy = g[:, 0] + 0.5 * gw, g[:, 1] + 0.5 * gh
-    out = torch.stack([(gcx - ecx) / ew, (gcy - ecy) / eh, torch.log(gw / ew), torch.log(gh / eh)], dim=1)
-    return arrays.from_device(out, fam)
+    return arrays.from_device(train_ops.bbox_transform(e[:, :4], g), fam)

@@ -12,9 +12,6 @@ loss_rcnn from frcnn_b200.train_engine.RcnnTrainer (kept in `self.rcnn_trainer` 
 """
 import os
 
-import numpy as np
-import torch
-
 from frcnn_b200 import arrays, links
 from frcnn_b200.engine import Engine
 from models.bbox_transform import bbox_transform_inv, clip_boxes  # noqa: F401  (reference import surface)

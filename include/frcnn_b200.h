@@ -269,6 +269,11 @@ int frcnn_roi_overlaps(const float* rois, const int* count, int R_cap, const flo
  * (rows whose class is 0 stay zero). */
 int frcnn_roi_targets(const float* rois, const float* gt_boxes, const int* argmax, const int* keep_inds, int n, int num_classes,
                       float* use_gt_boxes, float* bbox_reg_targets, int* labels, void* stream);
+/* Array-level helpers of models/bbox_transform.py used by the training code: bbox_transform (:18-38) on float32 rows
+ * (ex_rois [n,4], gt rows gt_stride >= 4 floats apart) -> out [n,4] (dx, dy, dw, dh); keep_inside (:112-130) as a 0/1 flag
+ * per box: x1 >= 0, y1 >= 0, x2 < im_w, y2 < im_h. */
+int frcnn_bbox_transform(const float* ex_rois, const float* gt_rois, int gt_stride, int n, float* out, void* stream);
+int frcnn_keep_inside(const float* boxes, int n, int im_h, int im_w, unsigned char* flags, void* stream);
 /* faster_rcnn.py:151-165 on the merged head output head_out [R_cap][ld] (columns [0,num_classes) scores, then
  * 4*num_classes deltas): losses float32 [4] = {loss_cls, loss_bbox, cls_accuracy, loss_rcnn}; dhead (optional, same shape)
  * = grad_scale * d(loss_rcnn)/d(head_out), zero on rows not kept.  1 <= n <= 128. */

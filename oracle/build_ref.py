@@ -36,7 +36,6 @@ If /root/reference is absent (the GPU box) this script is a no-op and the
 pre-built ``.so`` -- if any -- is used as is.
 """
 import os
-import shutil
 import subprocess
 import sys
 import sysconfig

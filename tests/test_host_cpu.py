@@ -1,8 +1,6 @@
 """CPU tests of host-side logic that needs no GPU: pure-host C-ABI helpers (called through the real library), the ResNet
 graph description and BN folding, the oracle's training-step restatement against numerical differentiation."""
 import ctypes
-import os
-import sys
 
 import numpy as np
 import pytest

@@ -767,3 +767,20 @@ def test_single_pass_bf16_mode_of_the_training_and_resnet_paths():
         feats[prec] = plan.acts[-1].to_chw_f32().cpu().numpy()
         assert np.isfinite(feats[prec]).all() and p.shape[1] == 21
     assert _rel(feats["bf16"], feats["bf16x3"]) < 5e-2
+
+
+def test_bbox_transform_and_keep_inside_helpers(dropin_installed, tops):
+    """models.bbox_transform.{bbox_transform, keep_inside} (reference :18-38, :112-130) through their kernels."""
+    from models import bbox_transform as bt
+    ex, _ = gi.box_transform_case(300, 1, 23)
+    gt, _ = gi.box_transform_case(300, 1, 24)
+    got = bt.bbox_transform(ex, np.hstack([gt, np.ones((300, 1), f32)]))          # gt rows carry a class column
+    want = orc.bbox_transform(ex, gt)                                             # float32 in, float32 arithmetic
+    assert isinstance(got, np.ndarray) and got.dtype == np.float32 and want.dtype == np.float32
+    assert _ulp_diff_f32(got, want).max() <= 2
+    allb = orc.all_anchor_boxes(38, 63, 16, ANCHORS)
+    idx, rows = bt.keep_inside(allb, (600, 1000))
+    widx, wrows = orc.keep_inside(allb, (600, 1000))
+    assert np.array_equal(idx, widx) and np.array_equal(rows, wrows)
+    flags = tops.keep_inside_flags(_dev(allb), 600, 1000).cpu().numpy()
+    assert flags.sum() == len(widx) == 8151
