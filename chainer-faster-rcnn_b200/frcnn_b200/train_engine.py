@@ -178,6 +178,8 @@ class RpnTrainer(_ConvTrainer):
         ops.conv2d(x, hi, lo, b, 3, True, out=R["y"])
         (hi, lo), b, _ = self.packed["heads"]
         ops.conv2d(R["y"], hi, lo, b, 1, False, out_act=False, ld_f32=self.head_ld, out_f32=self.head_out)
+        if disable_pos is None and self.subsample == "numpy":
+            disable_pos = self._numpy_subsample(gt_boxes, im_h, im_w)
         if disable_pos is not None:
             mode, kw = train_ops.SUBSAMPLE_LIST, dict(disable_pos=disable_pos)
         elif self.subsample == "device":
@@ -192,6 +194,27 @@ class RpnTrainer(_ConvTrainer):
                                                        loss_lambda=self.loss_lambda, layout="nhwc", ld=self.head_ld)
         self.last_losses = losses
         return losses
+
+    def _numpy_subsample(self, gt_boxes, im_h, im_w):
+        """The reference's own subsampling (anchor_target_layer.py:148-168): labels before subsampling come back to the host
+        and np.random.choice draws from NumPy's global RNG in the reference's order (a seeded run reproduces the reference's
+        labels bit for bit); returns the positions to disable in the inside-compact numbering (int32 CUDA tensor)."""
+        w = train_ops.anchor_targets(self.anchors, self.A, self.fh, self.fw, self.feat_stride, gt_boxes, im_h, im_w,
+                                     mode=train_ops.SUBSAMPLE_NONE, work=self.targets)
+        n_inside = int(w.counts[0].item())
+        labels = w.labels_full[w.inds_inside[:n_inside].long()].cpu().numpy()
+        num_fg = int(train_ops.RPN_FG_FRACTION * train_ops.RPN_BATCHSIZE)
+        disable = [np.zeros((0,), np.int64)]
+        fg_inds = np.where(labels == 1)[0]
+        if len(fg_inds) > num_fg:
+            d = np.random.choice(fg_inds, size=int(len(fg_inds) - num_fg), replace=False)
+            labels[d] = -1
+            disable.append(d)
+        num_bg = train_ops.RPN_BATCHSIZE - np.sum(labels == 1)
+        bg_inds = np.where(labels == 0)[0]
+        if len(bg_inds) > num_bg:
+            disable.append(np.random.choice(bg_inds, size=int(len(bg_inds) - num_bg), replace=False))
+        return torch.from_numpy(np.concatenate(disable).astype(np.int32)).to(self.device)
 
     def _forward_trunk(self, x_chw):
         """The 13 VGG16 convolutions with every output kept (pools un-fused: backward needs the un-pooled maps)."""

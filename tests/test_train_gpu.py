@@ -784,3 +784,23 @@ def test_bbox_transform_and_keep_inside_helpers(dropin_installed, tops):
     assert np.array_equal(idx, widx) and np.array_equal(rows, wrows)
     flags = tops.keep_inside_flags(_dev(allb), 600, 1000).cpu().numpy()
     assert flags.sum() == len(widx) == 8151
+
+
+def test_rpn_trainer_numpy_subsampling_reproduces_the_reference_labels():
+    """RpnTrainer(subsample="numpy"): with np.random.seed(s) the labels the loss sees are the reference run's
+    (oracle under the same seed, itself pinned to the reference's AnchorTargetLayer)."""
+    from frcnn_b200.train_engine import RpnTrainer
+    H, W = 600, 1000
+    fh, fw, gt, info, seed = gi.anchor_target_case("c1_g8")
+    params = orc.make_params(seed=77)
+    x = orc.make_image(H, W, seed=1)
+    tr = RpnTrainer(params, H, W, ANCHORS, subsample="numpy")
+    np.random.seed(seed)
+    tr.forward(_dev(x[0]), _dev(gt[0]))
+    np.random.seed(seed)
+    r = orc.anchor_target_layer(fh, fw, gt, info)
+    n_in = int(tr.targets.counts[0].item())
+    inds = tr.targets.inds_inside[:n_in].cpu().numpy()
+    assert np.array_equal(tr.targets.labels_full.cpu().numpy()[inds], r["labels"])
+    c = tr.targets.counts.cpu().numpy()
+    assert (int(c[1]), int(c[2])) == (int((r["labels"] == 1).sum()), int((r["labels"] == 0).sum()))
