@@ -289,6 +289,14 @@ int frcnn_roi_pool_backward(const void* feat_hi, const void* feat_lo, int H, int
                             int R_cap, int outh, int outw, float scale, const void* g_hi, const void* g_lo, float* dfeat,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the backward pass of the reference's training steps.  In the reference it is `loss.backward()` inside Chainer's
+ * updater (train_rpn.py:169-174 / train_rcnn.py with StandardUpdater or ParallelUpdater; the graph is the one
+ * models/vgg16.py:38-82, models/region_proposal_network.py:117-120 and models/faster_rcnn.py:123-134 build) followed by
+ * MomentumSGD + WeightDecay (train_rpn.py:165-167).  Chainer's per-function backward code is un-vendored; these entry
+ * points are its replacement: L.Convolution2D / L.Linear backward-data = frcnn_conv2d on frcnn_pack_conv_weights_dgrad,
+ * backward-filter = frcnn_gemm_nt_splitk (+ frcnn_wgrad_reduce, frcnn_bias_grad), F.relu / F.max_pooling_2d / F.dropout
+ * backward = frcnn_grad_prepare, F.roi_pooling_2d backward = frcnn_roi_pool_backward, the optimizer = frcnn_sgd_momentum. */
+
 /* Split-K "NT" GEMM on the tensor-core kernel of frcnn_conv2d (same bf16 hi/lo operand planes), the engine of the
  * weight-gradient pass (conv backward-filter as a GEMM over the pixel axis):
  *     parts[g][s][m][n] = sum over k in split s of  A[m][k] * B_g[n][k + off(g)]        (fp32, row stride ld)
