@@ -93,3 +93,20 @@ def test_oracle_train_step_gradient_is_the_derivative_of_its_loss():
     g = out["grads"][k] + 0.0005 * params[k]
     np.testing.assert_allclose(out["velocity"][k], -0.001 * g, rtol=1e-12, atol=0)
     np.testing.assert_allclose(out["params"][k], params[k] - 0.001 * g, rtol=1e-12, atol=0)
+
+
+def test_preprocess_size_rule_matches_oracle_and_opencv():
+    """frcnn_b200.preprocess.plan_size (host logic of forward.py:34-45): same scale and output size as the oracle's
+    restatement for a sweep of image shapes, and the output size is what cv2.resize(fx=fy=scale) actually produces."""
+    import cv2
+    from frcnn_b200 import preprocess
+    rng = np.random.default_rng(0)
+    shapes = [(375, 500), (500, 375), (333, 500), (720, 1280), (600, 600), (97, 211), (1200, 400), (480, 640), (375, 625)]
+    shapes += [tuple(int(v) for v in rng.integers(60, 1500, 2)) for _ in range(30)]
+    for h0, w0 in shapes:
+        s, H, W = preprocess.plan_size(h0, w0)
+        so, Ho, Wo = orc.preprocess_plan(h0, w0)
+        assert (H, W) == (Ho, Wo) and s == so, (h0, w0)
+        out = cv2.resize(np.zeros((h0, w0, 3), np.float32), None, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR)
+        assert out.shape[:2] == (H, W), (h0, w0, out.shape, (H, W))
+        assert min(H, W) <= 600 + 1 and max(H, W) <= 1000 + 1
