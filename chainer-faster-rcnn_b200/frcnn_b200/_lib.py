@@ -88,6 +88,9 @@ SIGNATURES = {
     "frcnn_roi_pool_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "frcnn_roi_pool_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_forward_workspace_bytes": (c_size_t, [c_void_p]),
+    "frcnn_forward_vgg16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "frcnn_debug_sort_clocks": (None, [c_void_p]),
     "frcnn_detect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_float, c_void_p, c_void_p,
                              c_void_p, c_void_p]),
@@ -122,3 +125,18 @@ def last_error():
 def check(status, what):
     if status != OK:
         raise FrcnnError("%s failed (status %d): %s" % (what, status, last_error()))
+
+
+# ---- the structs of the whole-graph entry (include/frcnn_b200.h: frcnn_forward_config / frcnn_packed_layer / frcnn_vgg16_weights)
+class ForwardConfig(ctypes.Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("num_classes", c_int), ("n_anchors", c_int), ("feat_stride", c_int),
+                ("pre_nms_top_n", c_int), ("post_nms_top_n", c_int), ("min_size", c_int), ("nms_thresh", c_double), ("x3", c_int)]
+
+
+class PackedLayer(ctypes.Structure):
+    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("bias", c_void_p)]
+
+
+class Vgg16Weights(ctypes.Structure):
+    _fields_ = [("conv", PackedLayer * 13), ("rpn3", PackedLayer), ("rpn_heads", PackedLayer), ("fc6", PackedLayer),
+                ("fc7", PackedLayer), ("head", PackedLayer), ("anchors", c_void_p)]

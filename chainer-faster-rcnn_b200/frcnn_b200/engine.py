@@ -387,3 +387,47 @@ class Engine(object):
         prob, boxes, count = p.forward(x_chw)
         R = int(count.item())           # the one documented D2H sync
         return prob[:R], boxes[:R], p
+
+
+class CForward(object):
+    """frcnn_forward_vgg16: the whole forward path behind the single C-ABI entry (include/frcnn_b200.h) -- what a caller
+    without Python binds.  Same kernels, same order as ForwardPlan._run; this wrapper only fills the C structs from a
+    PackedWeights and owns the workspace / output tensors."""
+
+    def __init__(self, weights, H, W, anchors, pre_n=6000, post_n=300, nms_thresh=0.7, min_size=16, feat_stride=16):
+        import ctypes
+        from . import _lib
+        self._lib, self._ct = _lib.load(), ctypes
+        self.w, self.H, self.W, self.post_n = weights, H, W, post_n
+        dev = weights.device
+        self.anchors = torch.from_numpy(np.ascontiguousarray(anchors, dtype=np.float64)).to(dev)
+        cfg = _lib.ForwardConfig(H, W, weights.num_classes, weights.n_anchors, feat_stride, pre_n, post_n, min_size,
+                                 float(nms_thresh), 1 if weights.precision == "bf16x3" else 0)
+        p = lambda t: None if t is None else t.data_ptr()                     # noqa: E731
+        layer = lambda hi, lo, b: _lib.PackedLayer(p(hi), p(lo), p(b))         # noqa: E731
+        wt = _lib.Vgg16Weights()
+        for i, item in enumerate([it for it in VGG16_LAYERS if it != "pool"]):
+            wt.conv[i] = layer(*weights.convs[item[0]])
+        wt.rpn3, wt.rpn_heads = layer(*weights.rpn3), layer(*weights.rpn_heads)
+        wt.fc6, wt.fc7, wt.head = layer(*weights.fc6), layer(*weights.fc7), layer(*weights.head)
+        wt.anchors = self.anchors.data_ptr()
+        self.cfg, self.wt = cfg, wt
+        nbytes = self._lib.frcnn_forward_workspace_bytes(ctypes.byref(cfg))
+        if nbytes == 0:
+            raise FrcnnError("frcnn_forward_workspace_bytes: %s" % _lib.last_error())
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        self.prob = torch.empty((post_n, weights.num_classes), dtype=torch.float32, device=dev)
+        self.boxes = torch.empty((post_n, 4 * weights.num_classes), dtype=torch.float32, device=dev)
+        self.count = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def forward(self, x_chw, im_info=None):
+        """x_chw (3,H,W) float32 CUDA.  Returns (prob, boxes, count) device tensors (rows past count are zero)."""
+        from . import _lib
+        im_h, im_w = (self.H, self.W) if im_info is None else (int(im_info[0]), int(im_info[1]))
+        x = x_chw.contiguous().float()
+        ct = self._ct
+        _lib.check(self._lib.frcnn_forward_vgg16(ct.byref(self.cfg), ct.byref(self.wt), ct.c_void_p(x.data_ptr()), im_h, im_w,
+                                                 ct.c_void_p(self.ws.data_ptr()), self.ws.numel(), ct.c_void_p(self.prob.data_ptr()),
+                                                 ct.c_void_p(self.boxes.data_ptr()), ct.c_void_p(self.count.data_ptr()),
+                                                 ct.c_void_p(torch.cuda.current_stream().cuda_stream)), "frcnn_forward_vgg16")
+        return self.prob, self.boxes, self.count

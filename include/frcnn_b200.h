@@ -185,6 +185,42 @@ int frcnn_detect(const float* prob, const float* boxes, const int* count, int R_
                  double nms_thresh, float conf, int* keep_idx, int* keep_count, int* conf_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The whole forward path behind one call (forward_graph.cu): FasterRCNN.__call__, inference branch
+ * (models/faster_rcnn.py:92-134,175-178) with the VGG16 trunk -- host orchestration only: it carves the caller's
+ * workspace and enqueues, on `stream`, the same kernels in the same order as the entry points above (static launch
+ * sequence: capturable into a CUDA graph).  No allocation, no synchronisation.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int H, W;                               /* image size (the trunk needs H, W >= 16) */
+    int num_classes, n_anchors, feat_stride; /* 21, 9, 16 */
+    int pre_nms_top_n, post_nms_top_n, min_size; /* ProposalLayer limits (models/proposal_layer.py:51-56) */
+    double nms_thresh;                       /* RPN_NMS_THRESH 0.7 */
+    int x3;                                  /* 1: bf16 hi+lo planes ("bf16x3"), 0: hi planes only */
+} frcnn_forward_config;
+
+typedef struct {                             /* one layer as frcnn_pack_conv_weights* / a padded fp32 bias produce it */
+    const void* hi; const void* lo; const float* bias;
+} frcnn_packed_layer;
+
+typedef struct {
+    frcnn_packed_layer conv[13];             /* conv1_1 (frcnn_pack_conv_weights_im2col3x3) ... conv5_3 */
+    frcnn_packed_layer rpn3;                 /* RPN/rpn_conv_3x3 */
+    frcnn_packed_layer rpn_heads;            /* rpn_cls_score | rpn_bbox_pred rows concatenated: [1, 6A, 512] */
+    frcnn_packed_layer fc6;                  /* K axis permuted (c,h,w) -> (h,w,c) (perm_chw_to_hwc) */
+    frcnn_packed_layer fc7;
+    frcnn_packed_layer head;                 /* cls_score | bbox_pred rows concatenated: [1, 5*num_classes, 4096] */
+    const double* anchors;                   /* [n_anchors, 4] float64 (generate_anchors) */
+} frcnn_vgg16_weights;
+
+size_t frcnn_forward_workspace_bytes(const frcnn_forward_config* config);      /* 0 on a bad config (see frcnn_last_error) */
+/* image_chw: (3,H,W) float32 device image (mean-subtracted, as forward.py:45 builds it); im_h/im_w: the clip bounds the
+ * caller passes as img_info (forward.py:93 passes (H, H), Q7).  Outputs (device): out_prob [post_nms_top_n, num_classes]
+ * softmax, out_boxes [post_nms_top_n, 4*num_classes] decoded + clipped, *out_count valid rows (rows past it are zero). */
+int frcnn_forward_vgg16(const frcnn_forward_config* config, const frcnn_vgg16_weights* weights, const float* image_chw,
+                        int im_h, int im_w, void* workspace, size_t workspace_bytes, float* out_prob, float* out_boxes,
+                        int* out_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * ResNet trunk support (chainer ResNetLayers as used by models/resnet.py:11-45).
  * ------------------------------------------------------------------------------------------------ */
 

@@ -313,3 +313,26 @@ def test_argument_errors_raise_instead_of_crashing(params):
     # the library is still usable afterwards
     y, _ = ops.conv2d(x, hi, lo, b, 3, True)
     assert y.hi.shape == (8, 8, 64)
+
+
+@pytest.mark.parametrize("precision,shape", [("bf16x3", (150, 201)), ("bf16", (96, 128)), ("bf16x3", (600, 1000))])
+def test_single_c_abi_call_equals_the_engine(params, precision, shape):
+    """frcnn_forward_vgg16 (one C call, caller-owned workspace) returns bit for bit what the Python-composed graph returns --
+    it enqueues the same kernels in the same order -- including the Q7 clip bounds (img_info = (H, H))."""
+    from frcnn_b200.engine import CForward
+    H, W = shape
+    eng = _engine(params, precision, use_graph=False)
+    x = torch.from_numpy(orc.make_image(H, W, seed=11)[0]).cuda()
+    for info in ((H, W), (H, H)):
+        prob, boxes, plan = eng(x, img_info=info)
+        cf = CForward(eng.weights, H, W, ANCHORS)
+        p2, b2, c2 = cf.forward(x, im_info=info)
+        torch.cuda.synchronize()
+        R = int(c2.item())
+        assert R == prob.shape[0] and torch.equal(p2[:R], prob) and torch.equal(b2[:R], boxes)
+        assert not p2[R:].any().item() and not b2[R:].any().item()
+    # the workspace query rejects a bad configuration through the error channel
+    from frcnn_b200 import _lib
+    import ctypes
+    bad = _lib.ForwardConfig(8, 8, 21, 9, 16, 6000, 300, 16, 0.7, 1)
+    assert _lib.load().frcnn_forward_workspace_bytes(ctypes.byref(bad)) == 0 and "too small" in _lib.last_error()
