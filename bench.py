@@ -163,7 +163,8 @@ def run_reference_arm(args, rank):
     x = None
     raw = np.random.default_rng(7).integers(0, 256, (375, 625, 3), dtype=np.uint8)     # resizes to 600x1000
     info = np.array([[H_IMG, W_IMG]], np.int32)
-    for _ in range(max(1, min(args.warmup, 1))):
+    warm = max(args.warmup, 3)               # the same warm-up count as the B200 arm
+    for _ in range(warm):
         t_probe, _ = cpu_pipeline_once(orc, params, x, info, ref_nms, raw=raw)
     steps = args.steps
     if t_probe * steps > 240.0:                 # keep the whole run within a few minutes
@@ -178,11 +179,11 @@ def run_reference_arm(args, rank):
     kind = "reference" if ref_nms is not None else "port"
     line = {
         "impl": "reference", "metric": "images/sec end-to-end VGG16 Faster R-CNN forward @600x1000",
-        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VGG16 Faster R-CNN forward, synthetic 600x1000, 300 proposals (config #2)",
-                   "device": "host CPU", "requested_steps": args.steps},
+        "config": bench_config(),
+        "detail": {"device": "host CPU", "requested_steps": args.steps},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": "%d whole image(s): raw uint8 375x625 -> preprocessing -> 600x1000 forward -> per-class "
                                    "NMS; dense ops torch-CPU fp32 (Chainer not installable offline), NMS = %s; NMS share %.1f%%" %
@@ -195,27 +196,38 @@ def run_reference_arm(args, rank):
 
 # ----------------------------------------------------------------------------------------- B200 arm
 def conv_layer_table(plan, torch, reps=3, spin=True):
-    """Per-launch device time of the tensor-core kernel over one forward: eager re-run with CUDA events
-    around each frcnn_conv2d call (same stream, same buffers).  Returns [(name, ms, gflop)]."""
+    """Per-launch device time of the tensor-core kernel over one forward: eager re-run with CUDA events around each
+    frcnn_conv2d / frcnn_linear call (same stream, same buffers).  Returns [(name, ms, gflop)].  (frcnn_linear = the
+    split-K GEMM + its small reduction kernel, timed together.)"""
     from frcnn_b200 import ops
     rows = []
-    orig = ops.conv2d
+    orig_conv, orig_lin = ops.conv2d, ops.linear
 
-    def timed(x, w_hi, w_lo, bias, ksize, relu, **kw):
+    def bracket(fn, gflop, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # a ~40 us spin kernel first: while the GPU spins, the host enqueues e0 + the conv launch + e1, so the interval
+        # a ~40 us spin kernel first: while the GPU spins, the host enqueues e0 + the launch + e1, so the interval
         # between the events is the kernel's execution alone (no host launch latency inside it, even on a slow host)
         if spin:
             torch.cuda._sleep(80000)
         e0.record()
-        r = orig(x, w_hi, w_lo, bias, ksize, relu, **kw)
+        r = fn()
         e1.record()
+        rows.append([(e0, e1), gflop, name])
+        return r
+
+    def timed_conv(x, w_hi, w_lo, bias, ksize, relu, **kw):
         Hh, Ww, Cin = x.hi.shape
         taps, Cout, _ = w_hi.shape
         k_true = 27 if (Cin == 32 and taps == 1 and Hh > 1) else taps * Cin     # conv1_1 = im2col GEMM, 27 real K
-        rows.append([(e0, e1), 2.0 * Hh * Ww * Cout * k_true / 1e9, "%dx%dx%d->%d k%d" % (Hh, Ww, Cin, Cout, ksize)])
-        return r
-    ops.conv2d = timed
+        return bracket(lambda: orig_conv(x, w_hi, w_lo, bias, ksize, relu, **kw), 2.0 * Hh * Ww * Cout * k_true / 1e9,
+                       "%dx%dx%d->%d k%d" % (Hh, Ww, Cin, Cout, ksize))
+
+    def timed_lin(x, w_hi, w_lo, bias, relu, **kw):
+        _, R, K = x.hi.shape
+        Cout = w_hi.shape[1]
+        return bracket(lambda: orig_lin(x, w_hi, w_lo, bias, relu, **kw), 2.0 * R * Cout * K / 1e9,
+                       "linear %dx%d->%d" % (R, K, Cout))
+    ops.conv2d, ops.linear = timed_conv, timed_lin
     acc = {}
     try:
         for _ in range(reps):
@@ -225,14 +237,82 @@ def conv_layer_table(plan, torch, reps=3, spin=True):
             for i, (ev, gf, name) in enumerate(rows):
                 acc.setdefault(i, [name, gf, []])[2].append(ev[0].elapsed_time(ev[1]))
     finally:
-        ops.conv2d = orig
+        ops.conv2d, ops.linear = orig_conv, orig_lin
     return [(v[0], min(v[2]), v[1]) for _, v in sorted(acc.items())]
+
+
+WORKLOAD = ("VGG16 Faster R-CNN forward + the caller's per-class NMS (forward.py:48-57: thresh 0.3, conf 0.8), synthetic "
+            "600x1000, 300 proposals (config #2), one image per GPU")
+
+
+def bench_config():
+    """The SAME `config` object in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "image": [H_IMG, W_IMG], "proposals": 300, "num_classes": 21,
+            "l2": "no L2 flush needed: the per-step working set (activations + weights, ~1.5 GB) exceeds the 126 MB L2 and 4 "
+                  "input images are rotated"}
+
+
+def host_link_probe(torch, nbytes=7200000, reps=20):
+    """Bare pinned-memory H2D / D2H bandwidth of this box (CUDA events on the copying stream), so that an e2e number
+    limited by the host link can be told from one limited by the code."""
+    h = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+    d = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        out[name + "_gbs_median"] = nbytes / ts[len(ts) // 2] / 1e6
+        out[name + "_gbs_worst"] = nbytes / ts[-1] / 1e6
+    out["bytes"] = nbytes
+    return out
+
+
+def build_reference_api_model(params):
+    """models.faster_rcnn.FasterRCNN (the drop-in mirror of the reference class) filled with `params`."""
+    from frcnn_b200 import dropin
+    dropin.install()
+    from models.faster_rcnn import FasterRCNN
+    from models.vgg16 import VGG16Prev
+    model = FasterRCNN(trunk_class=VGG16Prev)
+    model.rcnn_train = False
+    model.rpn_train = False
+    named = dict(model.namedparams())
+    for k, v in params.items():
+        named["/" + k].data[...] = v
+    model._params_changed()
+    return model
+
+
+def reference_api_image(model, x_var, info_var, nms, np_):
+    """One image through the REFERENCE's interface, exactly what forward.py does per image (:88-99, :48-57):
+    model(x, img_info) with a HOST float32 image, then the caller's per-class loop of 20 cpu_nms calls on host arrays."""
+    cls_score, bbox_pred = model(x_var, info_var)
+    prob = cls_score.data
+    n_det = 0
+    for cls_id in range(1, 21):
+        _cls = prob[:, cls_id][:, np_.newaxis]
+        _bbx = bbox_pred[:, cls_id * 4: (cls_id + 1) * 4]
+        dets = np_.hstack((_bbx, _cls))
+        keep = nms(dets, 0.3)
+        dets = dets[keep, :]
+        n_det += int((dets[:, -1] >= 0.8).sum())
+    return prob.shape[0], n_det
 
 
 def run_b200_arm(args, rank, local_rank, world):
     import torch
     import frcnn_oracle as orc              # synthetic weights / image generators + cpu_baseline only
-    from frcnn_b200.engine import Engine
+    from frcnn_b200 import shard
+    from frcnn_b200.engine import Engine, LanePool, StreamRunner
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -240,12 +320,20 @@ def run_b200_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
     params = orc.make_params(seed=1234)
-    eng = Engine(params, precision=args.precision, anchors=anchors, use_graph=True)
+    # the whole north_star path: the caller's per-class NMS (forward.py:48-57, thresholds of :75-76) runs inside the graph
+    eng = Engine(params, precision=args.precision, anchors=anchors, use_graph=True, with_detect=True,
+                 det_nms_thresh=0.3, det_conf=0.8)
     plan = eng.plan(H_IMG, W_IMG)
     n_img = 4                                # rotate distinct images: no step sees the previous step's input
-    from frcnn_b200.shard import image_seed
-    imgs_host = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=image_seed(rank, i))[0]).pin_memory() for i in range(n_img)]
-    imgs_dev = [t.cuda() for t in imgs_host]
+    imgs_np = [orc.make_image(H_IMG, W_IMG, seed=shard.image_seed(rank, i)) for i in range(n_img)]       # (1,3,H,W) float32
+    from frcnn_b200 import ops as _ops
+    imgs_host = []
+    for a in imgs_np:                        # pinned by the library (cudaHostAlloc), see frcnn_host_alloc
+        blk = _ops.PinnedBlock(a[0].shape, np.float32)
+        blk.np[...] = a[0]
+        imgs_host.append(blk)
+    imgs_dev = [torch.from_numpy(a[0]).cuda() for a in imgs_np]
+    warm = max(args.warmup, 3)
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,16 +342,14 @@ def run_b200_arm(args, rank, local_rank, world):
             torch.cuda.synchronize()
 
     # ---------------- device-timed value: inputs resident in HBM
-    from frcnn_b200.engine import LanePool
     pool = LanePool(plan, lanes=args.in_flight)      # args.in_flight independent images in flight (one stream + graph each)
-    # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from the warm-up through the timed region and the
-    # one-image-in-flight repeat of it: the GPU is under the same load throughout, and a 25 ms timed region alone would
-    # yield a single sample
+    # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from the warm-up through the timed region, the
+    # one-image-in-flight repeat of it and the sustained run: the GPU is under the same load throughout
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     pool.fork()
-    for i in range(max(args.warmup, 3)):
+    for i in range(warm):
         pool.submit(i, imgs_dev[i % n_img])
     pool.join()
     barrier()
@@ -278,6 +364,10 @@ def run_b200_arm(args, rank, local_rank, world):
     barrier()
     ms = e0.elapsed_time(e1)
     R_last = int(plan.prop.count.item())
+    n_conf_last = int(plan.det[2].sum().item())
+    # tie-free-ness of the run: distinct fg scores among the anchors of the last image
+    fg = torch.softmax(plan.rpn_out[:, :18], dim=1)[:, 9:18].reshape(-1)
+    unique_fg = int(torch.unique(fg).numel())
     # the same K steps with ONE image in flight (no overlap between images): reported beside the headline
     barrier()
     e0.record()
@@ -286,49 +376,38 @@ def run_b200_arm(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms_single = e0.elapsed_time(e1)
+    # a sustained run (>= 200 images, whatever --steps says): the number to hold against bf16_tflops_sustained
+    n_sus = max(200, args.steps)
+    barrier()
+    e0.record()
+    pool.fork()
+    for i in range(n_sus):
+        pool.submit(i, imgs_dev[i % n_img])
+    pool.join()
+    e1.record()
+    barrier()
+    ms_sus = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     clocks = sampler.stop() if rank == 0 else None
     # per-launch times of the tensor-core kernel, taken right here: same thermal / power state as the timed region above
     table = conv_layer_table(plan, torch) if rank == 0 else None
-    from frcnn_b200 import shard
     ms_max = shard.max_over_ranks(ms, device="cuda")          # slowest rank decides
     value = world * args.steps / (ms_max / 1e3)
-
-    # ---------------- e2e: host image in, host result out, every step (public call)
-    res_prob = torch.empty((plan.post_n, 21), dtype=torch.float32).pin_memory()
-    res_box = torch.empty((plan.post_n, 84), dtype=torch.float32).pin_memory()
-    res_cnt = torch.empty((1,), dtype=torch.int32).pin_memory()
-
-    dbg = os.environ.get("FRCNN_BENCH_DEBUG") == "1"
-    dbg_rows = []
-
-    def e2e_step(i):
-        t = [time.perf_counter()]
-        plan.x_in.copy_(imgs_host[i % n_img], non_blocking=True)        # H2D from pinned memory
-        t.append(time.perf_counter())
-        prob, boxes, count = plan.forward(None)
-        t.append(time.perf_counter())
-        res_prob.copy_(prob, non_blocking=True)                         # D2H
-        res_box.copy_(boxes, non_blocking=True)
-        res_cnt.copy_(count, non_blocking=True)
-        t.append(time.perf_counter())
-        torch.cuda.synchronize()                                        # the caller reads the result
-        t.append(time.perf_counter())
-        if dbg:
-            dbg_rows.append([1e3 * (b - a) for a, b in zip(t, t[1:])])
-        return int(res_cnt[0])
-    for i in range(3):
-        e2e_step(i)
+    # seeds 0-4: one image in flight, 20 images per seed, this rank
+    seed_rates = {}
+    if rank == 0:
+        for sd in range(5):
+            xi = torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=sd)[0]).cuda()
+            plan.forward(xi)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                plan.forward(xi)
+            e1.record()
+            torch.cuda.synchronize()
+            seed_rates[str(sd)] = {"images_per_s": 20e3 / e0.elapsed_time(e1), "proposals": int(plan.prop.count.item())}
     barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
-    t_serial = time.perf_counter() - t0                      # one image at a time: latency, not throughput
-    if dbg:
-        print("e2e serial phases ms [h2d-call, replay-call, d2h-calls, sync] median:",
-              np.round(np.median(np.array(dbg_rows[3:]), 0), 3), file=sys.stderr)
-    # the public streaming call: host image in, host result out for EVERY step; the H2D of image i+1
-    # overlaps the graph of image i (frcnn_b200.engine.StreamRunner)
-    from frcnn_b200.engine import StreamRunner
+
+    # ---------------- e2e (1): the public streaming call -- host image in, host result out, every step
     runner = StreamRunner(pool)
     seq = [imgs_host[i % n_img] for i in range(args.steps)]
     runner.run(seq[: min(4, len(seq))])                      # warm-up
@@ -338,14 +417,15 @@ def run_b200_arm(args, rank, local_rank, world):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     assert len(counts) == args.steps and all(c > 0 for c in counts)
-    e2e_val = world * args.steps / shard.max_over_ranks(t_e2e, device="cuda")
-    e2e_serial_ms = 1e3 * shard.max_over_ranks(t_serial, device="cuda") / args.steps
-    h2d = runner.h2d_bytes
-    d2h = runner.d2h_bytes
+    e2e_f32_val = world * args.steps / shard.max_over_ranks(t_e2e, device="cuda")
     # same streaming call fed with RAW uint8 375x625 BGR images: mean-subtract + OpenCV-compatible bilinear resize to
-    # 600x1000 run on the device (forward.py:34-45 moved onto the GPU); reported beside the float32-input number
+    # 600x1000 run on the device (forward.py:34-45 moved onto the GPU)
     rng8 = np.random.default_rng(7 + rank)
-    raw = [torch.from_numpy(rng8.integers(0, 256, (375, 625, 3), dtype=np.uint8)).pin_memory() for _ in range(n_img)]
+    raw = []
+    for _ in range(n_img):
+        blk = _ops.PinnedBlock((375, 625, 3), np.uint8)
+        blk.np[...] = rng8.integers(0, 256, (375, 625, 3), dtype=np.uint8)
+        raw.append(blk)
     runner8 = StreamRunner(pool, src_hw=(375, 625))
     seq8 = [raw[i % n_img] for i in range(args.steps)]
     runner8.run(seq8[: min(4, len(seq8))])
@@ -355,36 +435,112 @@ def run_b200_arm(args, rank, local_rank, world):
     torch.cuda.synchronize()
     e2e8_val = world * args.steps / shard.max_over_ranks(time.perf_counter() - t0, device="cuda")
 
+    # ---------------- e2e (2): the REFERENCE's interface -- models.faster_rcnn.FasterRCNN.__call__ fed a host float32
+    # (1,3,600,1000) chainer.Variable + img_info, then the caller's 20 models.cpu_nms.cpu_nms calls (forward.py:88-99,48-57)
+    import threading
+    model = build_reference_api_model(params)
+    model.precision = args.precision
+    from chainer import Variable
+    from models.cpu_nms import cpu_nms as ref_nms
+    info_var = Variable(np.array([[H_IMG, W_IMG]], dtype=np.int32))
+    x_vars = [Variable(a) for a in imgs_np]
+    for i in range(3):
+        reference_api_image(model, x_vars[i % n_img], info_var, ref_nms, np)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        r_api = reference_api_image(model, x_vars[i % n_img], info_var, ref_nms, np)
+    t_api = time.perf_counter() - t0
+    api_serial = world * args.steps / shard.max_over_ranks(t_api, device="cuda")
+    # the model call alone (no caller NMS), serial: where the time of the serial number goes
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        model(x_vars[i % n_img], info_var)
+    api_model_only_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    # T caller threads, each running the same serial per-image code on its own images (a thread-per-request server):
+    # the drop-in keeps a plan per calling thread, so the threads' graphs overlap on the GPU
+    T = max(1, args.api_threads)
+    per = [(args.steps + T - 1 - k) // T for k in range(T)]
+    errs = []
+
+    def worker(k, n_local, sync):
+        try:
+            torch.cuda.set_device(local_rank)
+            for i in range(2):
+                reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)     # per-thread plan + graph
+            sync.wait()
+            for i in range(n_local):
+                reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)
+        except Exception as exc:          # noqa: BLE001
+            errs.append(repr(exc))
+            try:
+                sync.abort()
+            except Exception:             # noqa: BLE001
+                pass
+    sync = threading.Barrier(T + 1)
+    ths = [threading.Thread(target=worker, args=(k, per[k], sync)) for k in range(T)]
+    for t in ths:
+        t.start()
+    try:
+        sync.wait()
+    except threading.BrokenBarrierError:
+        pass
+    t0 = time.perf_counter()
+    for t in ths:
+        t.join()
+    t_thr = time.perf_counter() - t0
+    if errs:
+        raise RuntimeError("reference-API worker failed: %s" % errs[0])
+    api_threads = world * args.steps / shard.max_over_ranks(t_thr, device="cuda")
+    link = host_link_probe(torch) if rank == 0 else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---------------- roofline of the tensor-core kernel (live, CUDA events, rank 0)
-    peak_tf, peak_hbm, peak_src = load_peaks()
-    conv_rows = [r for r in table if " k3" in r[0] or "->64 k1" in r[0]]   # trunk + RPN convs (3x3 and the twin 1x1)
+    pk = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+    peak_burst = pk.get("bf16_tflops", 1590.0)
+    peak_sus = pk.get("bf16_tflops_sustained", 1421.6)
+    peak_hbm = pk.get("hbm_gbs", 6571.9)
+    peak_src = "MEASURED_PEAKS.json" if pk else "fallback (B200_PROFILING.md)"
+    conv_rows = [r for r in table if " k3" in r[0] or "->64 k1" in r[0]]   # trunk + RPN convs (3x3, conv1_1, the twin 1x1)
     conv_ms = sum(r[1] for r in conv_rows)
     all_ms = sum(r[1] for r in table)
     exec_mult = 3.0 if args.precision == "bf16x3" else 1.0
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_stack_dram.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_stack_dram.json")
     if args.precision == "bf16x3" and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["conv_stack_dram_bytes_per_step"], tj["source"]
     achieved = CONV_STACK_GFLOP / conv_ms          # GFLOP/ms == TFLOP/s (algorithmic flops)
+    sus_ips = n_sus / (ms_sus / 1e3)               # per rank set: all ranks ran n_sus images in ms_sus
     roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM, %d launches/step)" % len(table),
-        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "peak_source": "%s bf16_tflops_sustained (kernel timed inside a step)" % peak_src,
+        "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM; %d GEMM launches/step)" % len(table),
+        # isolated per-launch timings (a spin kernel ahead of every launch, clocks near max) -> the BURST peak applies
+        "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s", "frac": achieved / peak_burst,
+        "peak_source": "%s bf16_tflops (burst: every launch timed alone between CUDA events)" % peak_src,
         "algorithmic_gflop_per_step": CONV_STACK_GFLOP, "conv_stack_ms": conv_ms, "all_gemm_ms": all_ms,
         "executed_mma_flop_multiplier": exec_mult, "executed_tflops": achieved * exec_mult,
-        "traffic": traffic,     # DRAM read+write bytes of the conv-stack launches of one step, from the committed ncu pass
+        "executed_frac_of_burst": achieved * exec_mult / peak_burst,
+        # the whole step over a long run against the SUSTAINED peak: images/s x conv-stack GFLOP
+        "sustained": {"images": n_sus, "images_per_s_per_gpu": sus_ips, "ms_per_image": ms_sus / n_sus,
+                      "achieved": sus_ips * CONV_STACK_GFLOP / 1e3, "peak": peak_sus, "unit": "TFLOP/s",
+                      "frac": sus_ips * CONV_STACK_GFLOP / 1e3 / peak_sus,
+                      "executed_frac": sus_ips * CONV_STACK_GFLOP * exec_mult / 1e3 / peak_sus,
+                      "note": "whole forward steps (3 images in flight), conv-stack flops only in the numerator; "
+                              "peak = bf16_tflops_sustained"},
+        "traffic": traffic,     # DRAM read+write bytes of the conv-stack launches of one step (ncu pass of this binary)
         "traffic_source": traffic_src,
         # every conv-stack activation written once + read once (hi+lo planes, 4 B/elem), the im2col input read
-        # once, weights (17.1 M params, hi+lo) read once: 1.02 GB; measured DRAM traffic below that
-        # means part of the producer->consumer traffic stays in the 126 MB L2, above it would mean re-reads
+        # once, weights (17.1 M params, hi+lo) read once: 1.02 GB
         "algorithmic_bytes_per_step": 1.02e9 if args.precision == "bf16x3" else 0.51e9,
+        "hbm_peak_gbs": peak_hbm,
         "layers": [{"shape": n, "ms": round(m, 4), "tflops_algorithmic": round(g / m, 1)} for n, m, g in table],
     }
 
@@ -393,43 +549,55 @@ def run_b200_arm(args, rank, local_rank, world):
     if world == 1 and not args.no_cpu_baseline:
         import build_ref
         cores = pick_cpu_threads(torch)
-        ref_nms = build_ref.load()
+        ref_nms_c = build_ref.load()
         raw0 = np.random.default_rng(7).integers(0, 256, (375, 625, 3), dtype=np.uint8)
         info = np.array([[H_IMG, W_IMG]], np.int32)
-        cpu_pipeline_once(orc, params, None, info, ref_nms, raw=raw0)          # warm-up
-        tt, tn = cpu_pipeline_once(orc, params, None, info, ref_nms, raw=raw0)
+        cpu_pipeline_once(orc, params, None, info, ref_nms_c, raw=raw0)          # warm-up
+        tt, tn = cpu_pipeline_once(orc, params, None, info, ref_nms_c, raw=raw0)
         cpu_baseline = {"value": 1.0 / tt, "unit": "images/s", "cores": cores,
-                        "kind": "reference" if ref_nms is not None else "port",
+                        "kind": "reference" if ref_nms_c is not None else "port",
                         "sample": "1 whole image (raw 375x625 -> 600x1000) after 1 warm-up (%.2f s, NMS %.2f s); dense ops torch-CPU fp32 "
                                   "stand-in for Chainer, NMS = %s" %
-                                  (tt, tn, "reference cpu_nms.pyx" if ref_nms is not None else "C port of cpu_nms.pyx")}
+                                  (tt, tn, "reference cpu_nms.pyx" if ref_nms_c is not None else "C port of cpu_nms.pyx")}
 
+    d2h_api = 4 * plan.result_words_nodetect
     line = {
         "metric": "images/sec end-to-end VGG16 Faster R-CNN forward @600x1000",
-        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (bf16 hi/lo split operands, 3 tcgen05 MMAs per product, fp32 accumulate)"
                  if args.precision == "bf16x3" else "bf16 (fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": "VGG16 Faster R-CNN forward, synthetic 600x1000, 300 proposals (config #2), one image per GPU",
-                   "precision": args.precision, "proposals_last_step": R_last,
-                   "l2": "per-step working set (activations+weights ~1.5 GB) exceeds the 126 MB L2; 4 input images rotated",
+        "config": bench_config(),
+        "detail": {"precision": args.precision, "proposals_last_step": R_last, "detections_conf_0.8_last_step": n_conf_last,
+                   "unique_fg_scores_last_step": [unique_fg, int(fg.numel())],
                    "images_in_flight_per_gpu": len(pool),
                    "one_image_in_flight": {"images_per_s_this_rank": args.steps / (ms_single / 1e3),
                                            "ms_per_image": ms_single / args.steps},
-                   "cuda_graph": True, "frac_of_conv_roofline": (value / world) * CONV_STACK_GFLOP / 1e3 / peak_tf},
+                   "seeds_one_image_in_flight": seed_rates,
+                   "cuda_graph": True, "programmatic_dependent_launch": os.environ.get("FRCNN_PDL", "1") != "0",
+                   "launches_per_image": plan.n_launches,
+                   "frac_of_conv_roofline_burst": (value / world) * CONV_STACK_GFLOP / 1e3 / peak_burst},
         "clocks": clocks,
-        # headline e2e = the public streaming call fed with what a caller actually has: the decoded RAW image.
-        # Every step: H2D of a pinned uint8 375x625 BGR image, device preprocessing (forward.py:34-45: mean-sub +
-        # OpenCV-compatible bilinear resize to 600x1000), the whole graph, D2H of (prob, boxes, count).
-        "e2e": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes, "d2h_bytes_per_step": d2h,
-                "mode": "StreamRunner(src_hw=(375,625)): pinned RAW uint8 image H2D + device preprocessing + graph + D2H "
-                        "of (prob, boxes, count) every step; ring of %d slots, copy stream + %d compute lanes" % (runner8.depth, len(pool)),
-                "float32_chw_input": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d,
-                                      "note": "the reference's model-input interface: the already preprocessed "
-                                              "(3,600,1000) float32 tensor is uploaded every step (7.2 MB)"},
-                "latency_ms_one_image_serial_float32_input": e2e_serial_ms},
-        "gpu_launches": (plan.n_launches + 1) * args.steps,
+        # headline e2e = the REFERENCE's interface: FasterRCNN.__call__ with a host float32 (1,3,600,1000) Variable and
+        # img_info, then the caller's 20 cpu_nms calls on host arrays -- per image, inside the timed region: the pinned
+        # upload of the 7.2 MB image, the graph, ONE download of (prob, boxes, proposals), 20 host-array NMS round trips.
+        "e2e": {"value": api_threads, "unit": "images/s", "h2d_bytes_per_step": 4 * 3 * H_IMG * W_IMG + 20 * 300 * 5 * 4,
+                "d2h_bytes_per_step": d2h_api + 20 * 300 * 4,
+                "mode": "models.faster_rcnn.FasterRCNN.__call__(Variable float32 (1,3,600,1000) HOST, img_info) + 20 x "
+                        "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads" % T,
+                "reference_api_one_thread": {"value": api_serial, "unit": "images/s", "ms_per_image": 1e3 / (api_serial / world),
+                                             "model_call_only_ms": api_model_only_ms, "last": list(r_api)},
+                "reference_api_threads": T,
+                "stream_runner_raw_uint8": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
+                                            "d2h_bytes_per_step": runner8.d2h_bytes,
+                                            "note": "the build's own streaming API (engine.StreamRunner): pinned RAW uint8 375x625 "
+                                                    "image H2D + device preprocessing (forward.py:34-45) + graph incl. per-class "
+                                                    "NMS + one D2H of (prob, boxes, proposals, keep lists), ring of %d slots" % runner8.depth},
+                "stream_runner_float32": {"value": e2e_f32_val, "unit": "images/s", "h2d_bytes_per_step": runner.h2d_bytes,
+                                          "d2h_bytes_per_step": runner.d2h_bytes},
+                "host_link": link},
+        "gpu_launches": plan.n_launches * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
@@ -633,6 +801,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
+    ap.add_argument("--api-threads", type=int, default=4, help="caller threads of the reference-interface e2e leg")
     ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")
     args = ap.parse_args()

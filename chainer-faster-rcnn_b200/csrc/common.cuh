@@ -30,6 +30,38 @@ void set_error(const char* fmt, ...);
 
 #define FRCNN_LAUNCH_OK() FRCNN_CUDA_OK(cudaGetLastError())
 
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The forward path is a chain of ~35 dependent kernels; launched with the
+// programmatic-stream-serialization attribute a kernel's CTAs may become resident while the previous kernel drains
+// (its CTAs exit one by one), run their prologue (barrier init, TMEM allocation, tensor-map prefetch, argument setup)
+// and then block in grid_dep_wait() until the previous grid has completed and its writes are visible.  EVERY kernel
+// launched through launch_pdl() must call grid_dep_wait() before its first global-memory access.  Inside a stream
+// capture the attribute becomes a programmatic edge of the CUDA graph.  frcnn_set_programmatic_launch(0) turns the
+// attribute off for the calling thread (plain stream order; grid_dep_wait() is then a no-op).
+bool pdl_enabled();
+
+__device__ __forceinline__ void grid_dep_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -209,6 +209,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     if constexpr (CG == 2) ptx::cluster_sync();      // peer barriers initialised before any remote arrive / TMA signal
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // programmatic dependent launch: everything above overlapped the previous kernel's drain; from here on this kernel
+    // reads the previous kernel's output (TMA loads, residual, m_valid) and overwrites buffers it may still be reading
+    grid_dep_wait();
 
     const int num_kb = p.taps * p.cin_blocks;
     const int pad = (p.ksize - 1) / 2;
@@ -401,14 +404,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
                 }
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+                if (p.bias != nullptr) {                    // split-K partial sums carry no bias (the reduction adds it once)
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(b4 + j);
-                    v[4 * j + 0] += b.x;
-                    v[4 * j + 1] += b.y;
-                    v[4 * j + 2] += b.z;
-                    v[4 * j + 3] += b.w;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        v[4 * j + 0] += b.x;
+                        v[4 * j + 1] += b.y;
+                        v[4 * j + 2] += b.z;
+                        v[4 * j + 3] += b.w;
+                    }
                 }
                 if (p.res_hi != nullptr && in_img && n < p.Cout) {
                     // residual add (h + shortcut) of a bottleneck block, fused ahead of the ReLU
@@ -538,8 +543,39 @@ static EncodeTiledFn get_encode_fn() {
 
 // 3-D bf16 tensor map: dims (innermost first) {d0,d1,d2}, row pitch d0 elements, box {b0,b1,b2};
 // swizzle span = the box's inner extent in bytes (32 / 64 / 128).
+// Encoded maps are cached per thread, keyed by (base, dims, box): an eager caller of frcnn_forward_vgg16 re-encodes
+// nothing after its first image (six driver calls per conv launch otherwise); graph replay never comes here.
+struct TmapKey {
+    const void* base;
+    uint64_t d0, d1, d2;
+    uint32_t b0, b1, b2;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2;
+    }
+};
+constexpr int kTmapCacheSlots = 512;
+struct TmapCache {
+    TmapKey key[kTmapCacheSlots];
+    CUtensorMap map[kTmapCacheSlots];
+    bool used[kTmapCacheSlots];
+};
+static TmapCache* tmap_cache() {
+    static thread_local TmapCache* c = nullptr;
+    if (c == nullptr) c = new TmapCache();          // value-initialised: used[] all false
+    return c;
+}
+
 static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
                         uint32_t b1, uint32_t b2) {
+    const TmapKey key{base, d0, d1, d2, b0, b1, b2};
+    uint64_t hsh = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull;
+    hsh ^= (d0 * 31 + d1) * 0xC2B2AE3D27D4EB4Full + d2 * 0x165667B19E3779F9ull + b0 * 131 + b1 * 17 + b2;
+    const int slot = (int)((hsh >> 20) % kTmapCacheSlots);
+    TmapCache* cache = tmap_cache();
+    if (cache->used[slot] && cache->key[slot] == key) {
+        *tm = cache->map[slot];
+        return FRCNN_OK;
+    }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -559,10 +595,15 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
                   (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2, base);
         return FRCNN_ERR_CUDA;
     }
+    cache->key[slot] = key;
+    cache->map[slot] = *tm;
+    cache->used[slot] = true;
     return FRCNN_OK;
 }
 
-static int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0;
+// Tuning overrides (frcnn_conv2d_set_*): per calling thread, read when a launch is enqueued (and therefore fixed inside
+// a captured graph) -- two engines driven from different threads cannot disturb each other.
+static thread_local int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0;
 
 static int device_sm_count() {
     static int sms = 0;
@@ -597,17 +638,20 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     p.a_stages = a_stages;
     const size_t smem = (size_t)stages * stage_bytes + a_bytes + fixed;
     p.acc_cols = p.x3 ? 2 * BN : BN;
-    // long K (>= 256 k-blocks of 64, not a split-K part, per-tap path): rotate over up to 3 main accumulators
-    p.nacc = 1;
+    // long K (>= 256 k-blocks of 64 on the per-tap path, or a split-K GEMM that asks for it): rotate over up to 3 main accumulators
     p.acc_chunk = 1 << 30;
-    if (!HALO && p.n_parts == 1 && p.taps * p.cin_blocks >= 256) {
-        int nacc = 3;
+    if (!HALO && ((p.n_parts == 1 && p.taps * p.cin_blocks >= 256) || (p.n_parts > 1 && p.nacc > 1))) {
+        int nacc = p.n_parts > 1 ? p.nacc : 3;
         while (nacc > 1 && (p.acc_cols + (nacc - 1) * BN > 512)) --nacc;
         if (nacc > 1) {
             p.nacc = nacc;
             p.acc_chunk = 8;
             p.acc_cols += (nacc - 1) * BN;
+        } else {
+            p.nacc = 1;
         }
+    } else {
+        p.nacc = 1;
     }
     p.acc_bufs = (2 * p.acc_cols <= 512) ? 2 : 1;
     p.tmem_cols = 32;
@@ -623,13 +667,22 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CG;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CG == 2 ? 1 : 0;
+    cfg.numAttrs = na;
     FRCNN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p));
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
@@ -653,6 +706,8 @@ namespace {
 struct GemmExtra {          // split-K GEMM mode of the same kernel (frcnn_gemm_nt_splitk)
     int groups, row_stride, splits;
     long part_stride;
+    int bn = 0;             // 0: the weight-gradient rule (128 / 64); else the N tile to use (64, 128, 160, 256)
+    int nacc = 1;           // > 1: every split rotates its k-blocks over up to this many main accumulators (long K)
 };
 struct ResExtra {           // residual input of frcnn_conv2d_res
     const void *hi, *lo;
@@ -664,7 +719,7 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
                        void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_,
                        const GemmExtra* ge, const ResExtra* re = nullptr) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    FRCNN_REQUIRE(x_hi && w_hi && bias, "frcnn_conv2d: x_hi, w_hi and bias are required");
+    FRCNN_REQUIRE(x_hi && w_hi && (bias || ge), "frcnn_conv2d: x_hi, w_hi and bias are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
     FRCNN_REQUIRE(ksize == 1 || ksize == 3, "frcnn_conv2d: ksize must be 1 or 3 (got %d)", ksize);
     FRCNN_REQUIRE(H > 0 && W > 0 && Cin > 0 && Cout > 0, "frcnn_conv2d: bad shape H=%d W=%d Cin=%d Cout=%d", H, W, Cin, Cout);
@@ -707,8 +762,10 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     // ---- N tile: minimise waves x measured per-k-block cost
     const int cout_cover = y_f32 ? (ld_f32 > Cout ? ld_f32 : Cout) : Cout;
     int BN = 0;
-    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 256) {
+    if (g_force_bn == 64 || g_force_bn == 128 || g_force_bn == 160 || g_force_bn == 256) {
         BN = g_force_bn;
+    } else if (ge != nullptr && ge->bn != 0) {
+        BN = ge->bn;
     } else if (ge != nullptr) {
         // split-K GEMM mode has tiles to spare (groups x splits): N = 128 halves the re-reads of A and is the measured
         // optimum on every VGG weight-gradient shape (tests/gpu_wgrad_tune.py); N = 256 loses the accumulator double buffer
@@ -756,6 +813,7 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
         p.num_tiles *= p.n_parts;
     }
     p.num_stages = 0;
+    p.nacc = ge != nullptr ? ge->nacc : 1;
     p.x3 = x_lo != nullptr;
     p.relu = relu;
     p.pool = fuse_pool2x2 ? 1 : 0;
@@ -806,6 +864,8 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     FRCNN_DISPATCH(128, 64, false, 2)
     FRCNN_DISPATCH(64, 64, true, 2)
     FRCNN_DISPATCH(64, 64, false, 2)
+    FRCNN_DISPATCH(160, 64, false, 2)
+    FRCNN_DISPATCH(160, 64, false, 1)
     FRCNN_DISPATCH(256, 64, true, 1)
     FRCNN_DISPATCH(128, 64, true, 1)
     FRCNN_DISPATCH(64, 64, true, 1)
@@ -851,3 +911,17 @@ extern "C" int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, i
     GemmExtra ge{groups, row_stride, splits, (long)M * ld};
     return conv2d_impl(a_hi, a_lo, 1, M, K, b_hi, b_lo, zero_bias, N, 1, 0, 0, nullptr, nullptr, parts, ld, nullptr, stream_, &ge);
 }
+
+// Internal entry of linear_swapab.cu: parts[split][M][ld] = A[M,K] . B[N,K]^T over that split's K range, no bias, N tile
+// `bn`, each split rotating over `nacc` main accumulators.  Returns the effective number of splits through *splits_out.
+namespace frcnn {
+int gemm_nt_splitk_parts(const void* a_hi, const void* a_lo, int M, int K, const void* b_hi, const void* b_lo, int N, int splits,
+                         int bn, int nacc, float* parts, int ld, int* splits_out, void* stream_) {
+    FRCNN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0 && splits >= 1 && parts, "gemm_nt_splitk_parts: bad arguments");
+    GemmExtra ge{1, 0, splits, (long)M * ld};
+    ge.bn = bn;
+    ge.nacc = nacc;
+    if (splits_out) *splits_out = frcnn_gemm_nt_splitk_splits(K, splits);
+    return conv2d_impl(a_hi, a_lo, 1, M, K, b_hi, b_lo, nullptr, N, 1, 0, 0, nullptr, nullptr, parts, ld, nullptr, stream_, &ge);
+}
+}  // namespace frcnn

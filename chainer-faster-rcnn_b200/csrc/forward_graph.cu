@@ -37,8 +37,8 @@ const int kVgg[13][3] = {{3, 64, 0},    {64, 64, 1},   {64, 128, 0},  {128, 128,
 struct Layout {
     Plane x_col, act[13], rpn_mid, pool5, fc6, fc7;
     float *rpn_out, *head_out, *rois, *scores;
-    void* prop_ws;
-    size_t prop_ws_bytes;
+    void *prop_ws, *fc_ws;
+    size_t prop_ws_bytes, fc_ws_bytes;
     int fh, fw, rpn_ld, head_ld;
     size_t total;
 };
@@ -67,6 +67,12 @@ Layout carve(const frcnn_forward_config& c, void* workspace) {
     L.fc6 = k.act((long)c.post_nms_top_n * 4096);
     L.fc7 = k.act((long)c.post_nms_top_n * 4096);
     L.head_out = (float*)k.take((size_t)c.post_nms_top_n * L.head_ld * 4);
+    L.fc_ws_bytes = frcnn_linear_workspace_bytes(c.post_nms_top_n, 49 * 512, 4096);
+    const size_t b7 = frcnn_linear_workspace_bytes(c.post_nms_top_n, 4096, 4096);
+    const size_t bh = frcnn_linear_workspace_bytes(c.post_nms_top_n, 4096, 5 * c.num_classes);
+    if (b7 > L.fc_ws_bytes) L.fc_ws_bytes = b7;
+    if (bh > L.fc_ws_bytes) L.fc_ws_bytes = bh;
+    L.fc_ws = k.take(L.fc_ws_bytes);
     L.total = k.off;
     return L;
 }
@@ -128,12 +134,12 @@ int frcnn_forward_vgg16(const frcnn_forward_config* config, const frcnn_vgg16_we
     const int R = c.post_nms_top_n;
     if ((rc = frcnn_roi_pool(feat.hi, feat.lo, h, w, 512, L.rois, out_count, R, 7, 7, 1.0f / (float)c.feat_stride, L.pool5.hi,
                              L.pool5.lo, nullptr, stream)) != FRCNN_OK) return rc;
-    if ((rc = frcnn_conv2d(L.pool5.hi, L.pool5.lo, 1, R, 49 * 512, wts->fc6.hi, wts->fc6.lo, wts->fc6.bias, 4096, 1, 1, 0, L.fc6.hi,
-                           L.fc6.lo, nullptr, 0, out_count, stream)) != FRCNN_OK) return rc;
-    if ((rc = frcnn_conv2d(L.fc6.hi, L.fc6.lo, 1, R, 4096, wts->fc7.hi, wts->fc7.lo, wts->fc7.bias, 4096, 1, 1, 0, L.fc7.hi, L.fc7.lo,
-                           nullptr, 0, out_count, stream)) != FRCNN_OK) return rc;
-    if ((rc = frcnn_conv2d(L.fc7.hi, L.fc7.lo, 1, R, 4096, wts->head.hi, wts->head.lo, wts->head.bias, 5 * c.num_classes, 1, 0, 0,
-                           nullptr, nullptr, L.head_out, L.head_ld, out_count, stream)) != FRCNN_OK) return rc;
+    if ((rc = frcnn_linear(L.pool5.hi, L.pool5.lo, R, 49 * 512, wts->fc6.hi, wts->fc6.lo, wts->fc6.bias, 4096, 1, out_count, L.fc6.hi,
+                           L.fc6.lo, nullptr, 0, L.fc_ws, L.fc_ws_bytes, stream)) != FRCNN_OK) return rc;
+    if ((rc = frcnn_linear(L.fc6.hi, L.fc6.lo, R, 4096, wts->fc7.hi, wts->fc7.lo, wts->fc7.bias, 4096, 1, out_count, L.fc7.hi, L.fc7.lo,
+                           nullptr, 0, L.fc_ws, L.fc_ws_bytes, stream)) != FRCNN_OK) return rc;
+    if ((rc = frcnn_linear(L.fc7.hi, L.fc7.lo, R, 4096, wts->head.hi, wts->head.lo, wts->head.bias, 5 * c.num_classes, 0, out_count,
+                           nullptr, nullptr, L.head_out, L.head_ld, L.fc_ws, L.fc_ws_bytes, stream)) != FRCNN_OK) return rc;
     return frcnn_head_decode(L.head_out, L.head_out + c.num_classes, L.head_ld, L.rois, out_count, R, c.num_classes, im_h, im_w,
                              out_prob, out_boxes, stream);
 }

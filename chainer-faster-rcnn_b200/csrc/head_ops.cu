@@ -218,6 +218,7 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* hi, const __nv_bfloat16*
 // ------------------------------------------------------------------------------------------ max-pool 2x2/2 ceil
 __global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl, int H, int W, int C,
                                __nv_bfloat16* yh, __nv_bfloat16* yl) {
+    grid_dep_wait();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C8 = C / 8;
     const long total = (long)Ho * Wo * C8;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -250,6 +251,7 @@ __global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl,
 __global__ void roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl, int H, int W, int C,
                                 const float* rois, const int* count, int R_cap, int PH, int PW, float scale,
                                 __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32) {
+    grid_dep_wait();
     const int C8 = C / 8;
     const long total = (long)R_cap * PH * PW * C8;
     const int R = count ? min(*count, R_cap) : R_cap;
@@ -299,6 +301,7 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl
 __global__ void head_decode_kernel(const float* scores, const float* deltas, int ld, const float* rois,
                                    const int* count, int R_cap, int NC, int im_h, int im_w, float* prob,
                                    float* boxes) {
+    grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R_cap * NC) return;
     const int r = i / NC, c = i - r * NC;
@@ -352,6 +355,7 @@ __device__ __forceinline__ float det_iou(const float4 a, const float4 b) {
 __global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, const float* boxes, const int* count,
                                                              int R_cap, int NC, double thr, float conf,
                                                              int* keep_idx, int* keep_count, int* conf_count) {
+    grid_dep_wait();
     extern __shared__ __align__(16) unsigned char dsm[];
     const int R = count ? min(*count, R_cap) : R_cap;
     float4* sbox = reinterpret_cast<float4*>(dsm);                   // [R_cap] boxes by rank
@@ -410,6 +414,16 @@ using namespace frcnn;
 
 extern "C" int frcnn_version(void) { return 100; }
 extern "C" const char* frcnn_last_error(void) { return g_err; }
+
+namespace frcnn {
+static int pdl_default() {
+    const char* e = getenv("FRCNN_PDL");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+}
+static thread_local int g_pdl = -1;          // -1: not set by this thread -> environment default
+bool pdl_enabled() { return (g_pdl < 0 ? pdl_default() : g_pdl) != 0; }
+}  // namespace frcnn
+extern "C" void frcnn_set_programmatic_launch(int on) { frcnn::g_pdl = on < 0 ? -1 : (on ? 1 : 0); }
 
 extern "C" int frcnn_pack_image(const float* x_chw, int C, int H, int W, int C_pad, void* y_hi, void* y_lo,
                                 void* stream) {
@@ -480,9 +494,9 @@ extern "C" int frcnn_maxpool2x2_ceil(const void* x_hi, const void* x_lo, int H, 
     FRCNN_REQUIRE(x_hi && y_hi && H > 0 && W > 0 && C > 0 && C % 8 == 0, "frcnn_maxpool2x2_ceil: bad arguments (C=%d)", C);
     FRCNN_REQUIRE((x_lo == nullptr) == (y_lo == nullptr), "frcnn_maxpool2x2_ceil: lo planes must both be given or both NULL");
     const long total = (long)((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, H, W, C, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(maxpool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, H, W, C, (__nv_bfloat16*)y_hi,
+                             (__nv_bfloat16*)y_lo));
     return FRCNN_OK;
 }
 
@@ -494,10 +508,9 @@ extern "C" int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, i
                   "frcnn_roi_pool: bad arguments");
     FRCNN_REQUIRE(!out_lo || out_hi, "frcnn_roi_pool: out_lo without out_hi");
     const long total = (long)R_cap * outh * outw * (C / 8);
-    roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)feat_hi, (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw, scale,
-        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(roi_pool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)feat_hi, (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw,
+                             scale, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32));
     return FRCNN_OK;
 }
 
@@ -507,9 +520,8 @@ extern "C" int frcnn_head_decode(const float* scores, const float* deltas, int l
     FRCNN_REQUIRE(scores && deltas && rois && out_prob && out_boxes && R_cap > 0 && num_classes > 0 && ld >= num_classes,
                   "frcnn_head_decode: bad arguments");
     const int total = R_cap * num_classes;
-    head_decode_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(scores, deltas, ld, rois, count, R_cap,
-                                                                          num_classes, im_h, im_w, out_prob, out_boxes);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(head_decode_kernel, dim3(cdiv(total, 128)), dim3(128), 0, (cudaStream_t)stream, scores, deltas, ld,
+                             rois, count, R_cap, num_classes, im_h, im_w, out_prob, out_boxes));
     return FRCNN_OK;
 }
 
@@ -568,9 +580,7 @@ extern "C" int frcnn_detect(const float* prob, const float* boxes, const int* co
     FRCNN_REQUIRE(R_cap > 0 && R_cap <= kDetMaxR, "frcnn_detect: R_cap must be in [1,%d] (got %d)", kDetMaxR, R_cap);
     const size_t smem = (size_t)R_cap * (sizeof(float) + sizeof(int) + sizeof(float4) + 1) + 16;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    detect_kernel<<<num_classes - 1, kDetThreads, smem, (cudaStream_t)stream>>>(prob, boxes, count, R_cap, num_classes,
-                                                                                nms_thresh, conf, keep_idx, keep_count,
-                                                                                conf_count);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(detect_kernel, dim3(num_classes - 1), dim3(kDetThreads), smem, (cudaStream_t)stream, prob, boxes,
+                             count, R_cap, num_classes, nms_thresh, conf, keep_idx, keep_count, conf_count));
     return FRCNN_OK;
 }

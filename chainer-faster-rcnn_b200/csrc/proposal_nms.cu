@@ -32,6 +32,7 @@ struct DecodeArgs {
 };
 
 __global__ void rpn_decode_kernel(const DecodeArgs a) {
+    grid_dep_wait();
     const int n = a.A * a.H * a.W;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -97,6 +98,7 @@ __global__ void rpn_decode_kernel(const DecodeArgs a) {
 }
 
 __global__ void dets_keys_kernel(const float* dets, int n, float4* boxes, float* scores, uint32_t* keys) {
+    grid_dep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* d = dets + 5l * i;
@@ -153,6 +155,7 @@ struct SortArgs {
 // dynamic smem: uint64 comp[P] (P >= min(top_k, n)) followed, when it fits, by a copy of the n keys
 // (the select passes then never touch global memory again).
 __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortArgs a, const int P, const int cache_keys) {
+    grid_dep_wait();
     extern __shared__ unsigned long long comp[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned long long red[33];
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) topk_sort_kernel(const SortAr
 // a shared-memory copy) and scatters box / score / index straight to the sorted position.
 constexpr int kRankThreads = 256, kRankPerBlock = 32;
 __global__ void __launch_bounds__(kRankThreads) rank_scatter_kernel(const SortArgs a) {
+    grid_dep_wait();
     extern __shared__ unsigned long long scomp[];
     const int K = *a.num_sorted;
     const int e0 = blockIdx.x * kRankPerBlock;
@@ -314,6 +318,7 @@ __device__ __forceinline__ bool suppresses(float ovr, double thr_d, float thr_f,
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* boxes, const int* n_ptr, int n_cap,
                                                       double thr_d, float thr_f, int mode,
                                                       unsigned long long* mask, int col_blocks) {
+    grid_dep_wait();
     const int n = n_ptr ? min(*n_ptr, n_cap) : n_cap;
     const int rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
@@ -364,6 +369,7 @@ struct ScanArgs {
 };
 
 __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
+    grid_dep_wait();
     extern __shared__ unsigned long long removed[];   // [col_blocks]
     __shared__ int s_keep[64];
     __shared__ int s_nk, s_total;
@@ -525,18 +531,15 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
     const int cache_keys = sort_smem + keys_bytes <= 200 * 1024;     // smem copy of the keys when it fits
     if (cache_keys) sort_smem += keys_bytes;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    topk_sort_kernel<<<1, kSortThreads, sort_smem, stream>>>(sa, P, cache_keys);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(topk_sort_kernel, dim3(1), dim3(kSortThreads), sort_smem, stream, sa, P, cache_keys));
     const size_t rank_smem = sizeof(unsigned long long) * (size_t)k_cap;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(rank_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rank_smem));
-    rank_scatter_kernel<<<cdiv(k_cap, kRankPerBlock), kRankThreads, rank_smem, stream>>>(sa);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(rank_scatter_kernel, dim3(cdiv(k_cap, kRankPerBlock)), dim3(kRankThreads), rank_smem, stream, sa));
 
     const int cbs = cdiv(k_cap, 64);
     dim3 grid(cbs, cbs);
-    nms_mask_kernel<<<grid, 64, 0, stream>>>(w.sorted_boxes, w.num_sorted, k_cap, thresh, (float)thresh, mode, w.mask,
-                                             w.col_blocks);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(nms_mask_kernel, grid, dim3(64), 0, stream, (const float4*)w.sorted_boxes, (const int*)w.num_sorted,
+                             k_cap, thresh, (float)thresh, mode, w.mask, w.col_blocks));
 
     ScanArgs sc;
     sc.mask = w.mask; sc.col_blocks = w.col_blocks;
@@ -549,8 +552,7 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
     sc.diag_in_smem = (scan_smem + sizeof(unsigned long long) * (size_t)k_cap) <= 200 * 1024;
     if (sc.diag_in_smem) scan_smem += sizeof(unsigned long long) * (size_t)k_cap;
     FRCNN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
-    nms_scan_kernel<<<1, 256, scan_smem, stream>>>(sc);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(nms_scan_kernel, dim3(1), dim3(256), scan_smem, stream, sc));
     return FRCNN_OK;
 }
 
@@ -591,8 +593,7 @@ extern "C" int frcnn_proposals(const float* cls, long cls_chan_stride, long cls_
     da.anchors = anchors;
     da.A = A; da.H = H; da.W = W; da.feat_stride = feat_stride; da.im_h = im_h; da.im_w = im_w; da.min_size = min_size;
     da.boxes = w.boxes; da.scores = w.scores; da.keys = w.keys;
-    rpn_decode_kernel<<<cdiv(n_all, 128), 128, 0, stream>>>(da);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(rpn_decode_kernel, dim3(cdiv(n_all, 128)), dim3(128), 0, stream, da));
     return run_sort_nms(w, n_all, pre_nms_top_n, nms_thresh, FRCNN_NMS_GE_DOUBLE, post_nms_top_n, nullptr, out_count,
                         out_rois, out_scores, post_nms_top_n, dbg_sorted_dets, dbg_sorted_anchor_idx, dbg_num_sorted,
                         false, stream);
@@ -619,60 +620,9 @@ extern "C" int frcnn_nms(const float* dets, int n, double thresh, int mode, int 
         set_error("frcnn_nms: workspace %zu < required %zu", ws_bytes, w.total);
         return FRCNN_ERR_WORKSPACE;
     }
-    dets_keys_kernel<<<cdiv(n, 256), 256, 0, stream>>>(dets, n, w.boxes, w.scores, w.keys);
-    FRCNN_LAUNCH_OK();
+    FRCNN_CUDA_OK(launch_pdl(dets_keys_kernel, dim3(cdiv(n, 256)), dim3(256), 0, stream, dets, n, w.boxes, w.scores, w.keys));
     return run_sort_nms(w, n, n, thresh, mode, max_keep, keep_out, num_out, nullptr, nullptr, 0, nullptr, nullptr,
                         nullptr, true, stream);
-}
-
-// ------------------------------------------------------------------------------------------ host-pointer entry points
-static int nms_host_impl(const float* dets_host, int n, int dim, double thresh, int mode, int presorted,
-                         int* keep_out_host, int device_id) {
-    if (n < 0 || dim < 4) { set_error("nms host: bad n=%d dim=%d", n, dim); return FRCNN_ERR_ARG; }
-    if (n == 0) return 0;
-    if (n > 16384) { set_error("nms host: n=%d > 16384", n); return FRCNN_ERR_ARG; }
-    FRCNN_CUDA_OK(cudaSetDevice(device_id));
-    // [n,5] staging: a pre-sorted input without scores gets strictly descending synthetic scores so the
-    // internal (stable) sort is the identity.
-    float* h5 = static_cast<float*>(malloc(sizeof(float) * 5 * (size_t)n));
-    if (!h5) { set_error("nms host: out of host memory"); return FRCNN_ERR_ARG; }
-    for (int i = 0; i < n; ++i) {
-        for (int j = 0; j < 4; ++j) h5[5 * i + j] = dets_host[(size_t)dim * i + j];
-        h5[5 * i + 4] = presorted ? (float)(n - i) : dets_host[(size_t)dim * i + 4];
-    }
-    const size_t wsb = frcnn_nms_workspace_bytes(n);
-    char* dev = nullptr;
-    const size_t dets_b = align_up(sizeof(float) * 5 * (size_t)n, 256), keep_b = align_up(sizeof(int) * (size_t)n, 256);
-    cudaError_t e = cudaMalloc(&dev, dets_b + keep_b + 256 + wsb);
-    if (e != cudaSuccess) { free(h5); set_error("nms host: cudaMalloc: %s", cudaGetErrorString(e)); return FRCNN_ERR_CUDA; }
-    float* d_dets = reinterpret_cast<float*>(dev);
-    int* d_keep = reinterpret_cast<int*>(dev + dets_b);
-    int* d_num = reinterpret_cast<int*>(dev + dets_b + keep_b);
-    void* d_ws = dev + dets_b + keep_b + 256;
-    int rc = FRCNN_OK, num = 0;
-    do {
-        if ((e = cudaMemcpy(d_dets, h5, sizeof(float) * 5 * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        rc = frcnn_nms(d_dets, n, thresh, mode, 0, d_keep, d_num, d_ws, wsb, nullptr);
-        if (rc != FRCNN_OK) break;
-        if ((e = cudaMemcpy(&num, d_num, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-        if (num > 0 && (e = cudaMemcpy(keep_out_host, d_keep, sizeof(int) * (size_t)num, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
-    } while (0);
-    cudaFree(dev);
-    free(h5);
-    if (e != cudaSuccess) { set_error("nms host: %s", cudaGetErrorString(e)); return FRCNN_ERR_CUDA; }
-    if (rc != FRCNN_OK) return rc;
-    return num;
-}
-
-extern "C" void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
-                     float nms_overlap_thresh, int device_id) {
-    int r = nms_host_impl(boxes_host, boxes_num, boxes_dim, (double)nms_overlap_thresh, FRCNN_NMS_GT_FLOAT, 1, keep_out,
-                          device_id);
-    *num_out = r < 0 ? -1 : r;
-}
-
-extern "C" int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id) {
-    return nms_host_impl(dets_host, n, 5, thresh, FRCNN_NMS_GE_DOUBLE, 0, keep_out_host, device_id);
 }
 
 // Debug / profiling hook (not part of the drop-in surface): device buffer of 8 int64 that receives the

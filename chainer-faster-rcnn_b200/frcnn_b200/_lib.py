@@ -35,9 +35,18 @@ SIGNATURES = {
                                 c_void_p]),
     "frcnn_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "frcnn_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "frcnn_linear": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "frcnn_conv2d_set_tile": (None, [c_int, c_int, c_int]),
     "frcnn_conv2d_set_cta_group": (None, [c_int]),
     "frcnn_conv2d_set_max_ctas": (None, [c_int]),
+    "frcnn_set_programmatic_launch": (None, [c_int]),
+    "frcnn_host_alloc": (c_void_p, [c_size_t]),
+    "frcnn_host_free": (c_int, [c_void_p]),
+    "frcnn_memcpy_h2d_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_memcpy_d2h_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frcnn_stream_synchronize": (c_int, [c_void_p]),
     "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "frcnn_pack_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -118,15 +118,37 @@ class ForwardPlan(object):
         self.fh, self.fw = h, w_
         self.rpn_mid = act(h, w_, weights.rpn3[0].shape[1])
         self.rpn_out = torch.empty((h * w_, weights.rpn_ld), dtype=torch.float32, device=dev)
-        self.prop = ops.ProposalWorkspace(A, h, w_, pre_n, post_n, dev, debug=keep_rpn_debug)
+        # every per-image result lives in ONE device block (4-byte words) so that a host caller gets all of it with a
+        # single D2H transfer: [count | prob | boxes | rois | scores | keep_count | conf_count | keep_idx]
+        NC = weights.num_classes
+        sizes = [("count", 4), ("prob", post_n * NC), ("boxes", post_n * 4 * NC), ("rois", post_n * 4), ("scores", post_n),
+                 ("keep_count", NC - 1), ("conf_count", NC - 1), ("keep_idx", (NC - 1) * post_n)]
+        self.result_layout, off = {}, 0
+        for name, n_ in sizes:
+            self.result_layout[name] = (off, n_)
+            off += (n_ + 3) // 4 * 4
+        self.result_words_nodetect = self.result_layout["keep_count"][0]
+        self.result = torch.zeros((off,), dtype=torch.int32, device=dev)
+        rf = self.result.view(torch.float32)
+        seg = lambda t, name: t[self.result_layout[name][0]: self.result_layout[name][0] + self.result_layout[name][1]]   # noqa: E731
+        self.prop = ops.ProposalWorkspace(A, h, w_, pre_n, post_n, dev, debug=keep_rpn_debug,
+                                          outputs=(seg(rf, "rois").view(post_n, 4), seg(rf, "scores"), seg(self.result, "count")[:1]))
         C = self.acts[-1].hi.shape[2]
         self.pool5 = act(1, post_n, 49 * C)
         self.fc6 = act(1, post_n, 4096)
         self.fc7 = act(1, post_n, 4096)
         self.head_out = torch.empty((post_n, weights.head_ld), dtype=torch.float32, device=dev)
-        self.prob = torch.zeros((post_n, weights.num_classes), dtype=torch.float32, device=dev)
-        self.boxes = torch.zeros((post_n, 4 * weights.num_classes), dtype=torch.float32, device=dev)
-        self.det = None
+        # split-K slabs of the swapped-operand head GEMMs (ops.linear); one buffer sized for the largest layer
+        nc5 = 5 * weights.num_classes
+        self.fc_work = ops.linear_workspace(post_n, 49 * C, 4096, dev)
+        for k_, c_ in ((4096, 4096), (4096, nc5)):
+            wk = ops.linear_workspace(post_n, k_, c_, dev)
+            if wk.numel() > self.fc_work.numel():
+                self.fc_work = wk
+        self.prob = seg(rf, "prob").view(post_n, NC)
+        self.boxes = seg(rf, "boxes").view(post_n, 4 * NC)
+        self.det = (seg(self.result, "keep_idx").view(NC - 1, post_n), seg(self.result, "keep_count"), seg(self.result, "conf_count"))
+        self._host = None
         self.graph = None
         self.use_graph = use_graph
         self.im_h, self.im_w = H, W
@@ -191,17 +213,18 @@ class ForwardPlan(object):
         n += 2 + 5          # rpn 3x3, rpn heads; decode, select, rank/scatter, IoU mask, mask scan
         ops.roi_pool(feat, self.prop.rois, self.prop.count, 7, 7, 1.0 / self.feat_stride, out=self.pool5)
         hi, lo, b = w.fc6
-        ops.conv2d(self.pool5, hi, lo, b, 1, True, out=self.fc6, m_valid=self.prop.count)
+        ops.linear(self.pool5, hi, lo, b, True, m_valid=self.prop.count, out=self.fc6, work=self.fc_work)
         hi, lo, b = w.fc7
-        ops.conv2d(self.fc6, hi, lo, b, 1, True, out=self.fc7, m_valid=self.prop.count)
+        ops.linear(self.fc6, hi, lo, b, True, m_valid=self.prop.count, out=self.fc7, work=self.fc_work)
         hi, lo, b = w.head
-        ops.conv2d(self.fc7, hi, lo, b, 1, False, out_act=False, ld_f32=w.head_ld, out_f32=self.head_out,
-                   m_valid=self.prop.count)
+        ops.linear(self.fc7, hi, lo, b, False, m_valid=self.prop.count, out_f32=self.head_out, ld_f32=w.head_ld,
+                   work=self.fc_work, want_act=False)
+        n += 3          # each head layer = the split-K GEMM + its reduction
         ops.head_decode(self.head_out, w.head_ld, self.prop.rois, self.prop.count, w.num_classes, self.im_h, self.im_w,
                         out_prob=self.prob, out_boxes=self.boxes)
         n += 5
         if self.with_detect:
-            self.det = ops.detect(self.prob, self.boxes, self.prop.count, self.det_nms_thresh, self.det_conf)
+            ops.detect(self.prob, self.boxes, self.prop.count, self.det_nms_thresh, self.det_conf, out=self.det)
             n += 1
         self.n_launches = n
 
@@ -217,6 +240,47 @@ class ForwardPlan(object):
         if (im_h, im_w) != (self.im_h, self.im_w):
             self.im_h, self.im_w = int(im_h), int(im_w)
             self.graph = None
+
+    # -- host-array front end (the reference's model-input interface: a float32 (3,H,W) HOST array in, host results out)
+    def result_words(self):
+        return int(self.result.numel()) if self.with_detect else int(self.result_words_nodetect)
+
+    def host_io(self):
+        """Pinned staging for one synchronous host call at a time: the input image and a mirror of the result block."""
+        if self._host is None:
+            dev = self.x_in.device
+            self._host = dict(x=ops.PinnedBlock(tuple(self.x_in.shape), np.float32),
+                              res=ops.PinnedBlock((int(self.result.numel()),), np.int32),
+                              stream=torch.cuda.Stream(device=dev))
+        return self._host
+
+    def forward_host(self, x_np):
+        """x_np: float32 (3,H,W) (or (1,3,H,W)) numpy array.  Copies it into pinned staging (multi-threaded host copy),
+        uploads, replays the graph and brings the whole result block back with ONE D2H; blocks until it is there.
+        Returns a dict of numpy VIEWS into the pinned mirror (valid until the next forward_host on this plan)."""
+        io = self.host_io()
+        io["x"].t.copy_(torch.from_numpy(x_np).reshape(io["x"].shape))     # pageable -> pinned on the host cores
+        n = self.result_words()
+        st = io["stream"]
+        io["x"].h2d(self.x_in, st)                                 # H2D (cudaMemcpyAsync from the library's pinned block)
+        with torch.cuda.stream(st):
+            self.forward(None)
+        io["res"].d2h(self.result, st, nbytes=4 * n)               # D2H: everything the caller can ask for, one transfer
+        ops.stream_synchronize(st)
+        return self.unpack_result(io["res"].np)
+
+    def unpack_result(self, words):
+        """numpy int32 words of a result block -> dict of views (count int, prob [R,NC], boxes [R,4NC], rois, scores, detect lists)."""
+        L, post_n, NC = self.result_layout, self.post_n, self.w.num_classes
+        f = words.view(np.float32)
+        R = int(words[L["count"][0]])
+        sl = lambda a, name: a[L[name][0]: L[name][0] + L[name][1]]          # noqa: E731
+        out = dict(count=R, prob=sl(f, "prob").reshape(post_n, NC)[:R], boxes=sl(f, "boxes").reshape(post_n, 4 * NC)[:R],
+                   rois=sl(f, "rois").reshape(post_n, 4)[:R], scores=sl(f, "scores")[:R])
+        if self.with_detect:
+            out.update(keep_idx=sl(words, "keep_idx").reshape(NC - 1, post_n), keep_count=sl(words, "keep_count"),
+                       conf_count=sl(words, "conf_count"))
+        return out
 
     def forward(self, x_chw=None):
         """Run one image.  x_chw: (3,H,W) float32 CUDA tensor (copied into the static input) or None
@@ -309,24 +373,22 @@ class StreamRunner(object):
             self.stage = [torch.empty((src_hw[0], src_hw[1], 3), dtype=torch.uint8, device=dev) for _ in range(D)]
         self.h2d_done = [torch.cuda.Event() for _ in range(D)]
         self.step_done = [torch.cuda.Event() for _ in range(D)]
-        nc = plan.w.num_classes
-        self.res = [dict(prob=torch.empty((plan.post_n, nc), dtype=torch.float32).pin_memory(),
-                         boxes=torch.empty((plan.post_n, 4 * nc), dtype=torch.float32).pin_memory(),
-                         count=torch.zeros((1,), dtype=torch.int32).pin_memory()) for _ in range(D)]
+        self.n_words = plan.result_words()
+        self.res = [ops.PinnedBlock((self.n_words,), np.int32) for _ in range(D)]
         self.h2d_bytes = self.stage[0].numel() * self.stage[0].element_size()
-        self.d2h_bytes = (plan.post_n * nc + plan.post_n * 4 * nc) * 4 + 4
+        self.d2h_bytes = 4 * self.n_words
 
     def _deliver(self, i, counts, on_result):
         s = i % self.depth
         self.step_done[s].synchronize()
-        counts.append(int(self.res[s]["count"][0]))
+        counts.append(int(self.res[s].np[self.plan.result_layout["count"][0]]))
         if on_result is not None:
-            on_result(i, self.res[s])
+            on_result(i, self.plan.unpack_result(self.res[s].np))
 
     def run(self, host_images, on_result=None):
         """host_images: sequence of pinned host tensors ((3,H,W) float32, or (h0,w0,3) uint8 with src_hw).
-        Calls on_result(i, res) in order with the pinned result dict of image i (valid until image i+depth is
-        submitted).  Returns the proposal counts."""
+        Calls on_result(i, res) in order with the unpacked result of image i (ForwardPlan.unpack_result: numpy views
+        into the pinned block, valid until image i+depth is submitted).  Returns the proposal counts."""
         n, D, L = len(host_images), self.depth, len(self.pool)
         self.pool.fork()
         counts = []
@@ -335,9 +397,15 @@ class StreamRunner(object):
             plan, cur = self.pool.plans[i % L], self.pool.streams[i % L]
             if i >= D:
                 self._deliver(i - D, counts, on_result)         # slot reuse: image i-D must be finished and handed over
-            with torch.cuda.stream(self.copy_stream):
-                self.stage[s].copy_(host_images[i], non_blocking=True)          # H2D, overlaps earlier images' graphs
-                self.h2d_done[s].record(self.copy_stream)
+            # H2D on the copy stream (overlaps earlier images' graphs): cudaMemcpyAsync straight from the caller's buffer
+            # -- asynchronous when that buffer is pinned (ops.PinnedBlock, tensor.pin_memory()), staged by the driver if not
+            src = host_images[i]
+            src = src.t if isinstance(src, ops.PinnedBlock) else (torch.from_numpy(src) if isinstance(src, np.ndarray) else src)
+            if src.numel() * src.element_size() != self.h2d_bytes or not src.is_contiguous():
+                raise FrcnnError("StreamRunner: host image %d has %d bytes, expected %d contiguous" %
+                                 (i, src.numel() * src.element_size(), self.h2d_bytes))
+            ops.memcpy_h2d_async(self.stage[s], src.data_ptr(), self.h2d_bytes, self.copy_stream)
+            self.h2d_done[s].record(self.copy_stream)
             with torch.cuda.stream(cur):
                 cur.wait_event(self.h2d_done[s])
                 if self.src_hw is None:
@@ -349,10 +417,8 @@ class StreamRunner(object):
                     else:
                         preprocess.img_preprocessing(self.stage[s], self.pixel_means, out=plan.x_in)
                 plan.forward(None)
-                r = self.res[s]
-                r["prob"].copy_(plan.prob, non_blocking=True)
-                r["boxes"].copy_(plan.boxes, non_blocking=True)
-                r["count"].copy_(plan.prop.count, non_blocking=True)
+                # ONE D2H: count, class probabilities, boxes, proposals (+ the per-class NMS keep lists and counts)
+                self.res[s].d2h(plan.result, cur, nbytes=4 * self.n_words)
                 self.step_done[s].record(cur)
         for i in range(max(0, n - D), n):
             self._deliver(i, counts, on_result)
@@ -370,6 +436,8 @@ class Engine(object):
         self.anchors, self.feat_stride = anchors, feat_stride
         self.plan_kwargs = plan_kwargs
         self.plans = {}
+        import threading
+        self._tls, self._lock = threading.local(), threading.Lock()
 
     def plan(self, H, W, **overrides):
         kw = dict(self.plan_kwargs)
@@ -378,6 +446,37 @@ class Engine(object):
         if key not in self.plans:
             self.plans[key] = ForwardPlan(self.weights, H, W, anchors=self.anchors, feat_stride=self.feat_stride, **kw)
         return self.plans[key]
+
+    def thread_plan(self, H, W, **overrides):
+        """A ForwardPlan private to the calling thread (buffers, graph, stream over the shared weights): several host
+        threads may call the model concurrently, one image each, and their graphs overlap on the GPU."""
+        kw = dict(self.plan_kwargs)
+        kw.update(overrides)
+        key = (H, W, tuple(sorted(kw.items())))
+        cache = self._tls.__dict__.setdefault("plans", {})
+        p = cache.get(key)
+        if p is None:
+            with self._lock:
+                base = self.plan(H, W, **overrides)
+                owner = getattr(base, "_owner_thread", None)
+                import threading
+                me = threading.get_ident()
+                if owner is None or owner == me:
+                    base._owner_thread = me
+                    p = base
+                else:
+                    p = base.clone()
+                    p._owner_thread = me
+            cache[key] = p
+        return p
+
+    def call_host(self, x_np, img_info=None, **overrides):
+        """Host-array call: x_np float32 (3,H,W) numpy -> dict of numpy results (ForwardPlan.forward_host)."""
+        H, W = int(x_np.shape[-2]), int(x_np.shape[-1])
+        p = self.thread_plan(H, W, **overrides)
+        if img_info is not None:
+            p.set_clip(int(img_info[0]), int(img_info[1]))
+        return p.forward_host(x_np), p
 
     def __call__(self, x_chw, img_info=None, **overrides):
         _, H, W = x_chw.shape

@@ -140,6 +140,38 @@ def conv2d(x, w_hi, w_lo, bias, ksize, relu, out_act=True, ld_f32=0, m_valid=Non
     return y, y32
 
 
+def linear_workspace(R_cap, K, Cout, device):
+    n = _lib.load().frcnn_linear_workspace_bytes(int(R_cap), int(K), int(Cout))
+    if n == 0:
+        raise FrcnnError("frcnn_linear_workspace_bytes: bad shape R_cap=%d K=%d Cout=%d" % (R_cap, K, Cout))
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def linear(x, w_hi, w_lo, bias, relu, m_valid=None, out=None, out_f32=None, ld_f32=0, work=None, want_act=True):
+    """frcnn_linear: x Act [1,R_cap,K] (one RoI per row); w [1,Cout,K] packed planes; bias fp32 [>= Cout].
+    Returns (Act [1,R_cap,Cout] or None, fp32 [R_cap, ld_f32] or None).  `work`: uint8 workspace (linear_workspace)."""
+    _, R_cap, K = x.hi.shape
+    taps, Cout, kw = w_hi.shape
+    if taps != 1 or kw != K:
+        raise FrcnnError("linear: weight shape %s does not match K = %d" % (tuple(w_hi.shape), K))
+    if (x.lo is None) != (w_lo is None):
+        raise FrcnnError("linear: activation and weight precision modes differ")
+    dev = x.hi.device
+    y = out
+    if want_act and y is None:
+        yh = torch.empty((1, R_cap, Cout), dtype=torch.bfloat16, device=dev)
+        y = Act(yh, torch.empty_like(yh) if x.lo is not None else None)
+    y32 = out_f32
+    if ld_f32 and y32 is None:
+        y32 = torch.empty((R_cap, ld_f32), dtype=torch.float32, device=dev)
+    if work is None:
+        work = linear_workspace(R_cap, K, Cout, dev)
+    check(_lib.load().frcnn_linear(_p(x.hi), _p(x.lo), R_cap, K, _p(w_hi), _p(w_lo), _p(bias), Cout, 1 if relu else 0,
+                                   _p(m_valid), _p(y.hi) if y else None, _p(y.lo) if y else None, _p(y32), int(ld_f32),
+                                   _p(work), work.numel(), _stream()), "frcnn_linear")
+    return y, y32
+
+
 def conv2d_res(x, w_hi, w_lo, bias, ksize, relu, res, out=None):
     """frcnn_conv2d_res: y = act(conv(x) + bias + res); res an Act of the output shape (ResNet shortcut add)."""
     H, W, Cin = x.hi.shape
@@ -208,6 +240,57 @@ def set_conv_cta_group(cta_group=0):
     _lib.load().frcnn_conv2d_set_cta_group(cta_group)
 
 
+class PinnedBlock(object):
+    """A pinned host block owned by the library (frcnn_host_alloc), exposed as a numpy array and a CPU torch tensor that
+    share its memory.  Uploads / downloads go through h2d() / d2h(): cudaMemcpyAsync on the given torch stream."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        lib = _lib.load()
+        self.ptr = lib.frcnn_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise FrcnnError("frcnn_host_alloc(%d) failed: %s" % (self.nbytes, _lib.last_error()))
+        buf = (ctypes.c_char * self.nbytes).from_address(self.ptr)
+        self.np = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+        self.t = torch.from_numpy(self.np)
+
+    def h2d(self, dst, stream, nbytes=None):
+        check(_lib.load().frcnn_memcpy_h2d_async(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(self.ptr),
+                                                 int(self.nbytes if nbytes is None else nbytes),
+                                                 ctypes.c_void_p(stream.cuda_stream)), "frcnn_memcpy_h2d_async")
+
+    def d2h(self, src, stream, nbytes=None):
+        check(_lib.load().frcnn_memcpy_d2h_async(ctypes.c_void_p(self.ptr), ctypes.c_void_p(src.data_ptr()),
+                                                 int(self.nbytes if nbytes is None else nbytes),
+                                                 ctypes.c_void_p(stream.cuda_stream)), "frcnn_memcpy_d2h_async")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.np = self.t = None
+                _lib.load().frcnn_host_free(ctypes.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:          # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def memcpy_h2d_async(dst, src_ptr, nbytes, stream):
+    """cudaMemcpyAsync(dst tensor <- host pointer) on a torch stream."""
+    check(_lib.load().frcnn_memcpy_h2d_async(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(int(src_ptr)), int(nbytes),
+                                             ctypes.c_void_p(stream.cuda_stream)), "frcnn_memcpy_h2d_async")
+
+
+def stream_synchronize(stream):
+    check(_lib.load().frcnn_stream_synchronize(ctypes.c_void_p(stream.cuda_stream)), "frcnn_stream_synchronize")
+
+
+def set_programmatic_launch(on=-1):
+    """Programmatic dependent launch of the forward-path kernels for the calling thread: 1 on, 0 off, -1 = the
+    FRCNN_PDL environment default (on).  Read at launch time, i.e. baked into a CUDA graph at capture."""
+    _lib.load().frcnn_set_programmatic_launch(int(on))
+
+
 def set_conv_max_ctas(max_ctas=0):
     """Cap the persistent grid of later conv launches (0 = all SMs); baked into CUDA graphs at capture time."""
     _lib.load().frcnn_conv2d_set_max_ctas(int(max_ctas))
@@ -265,12 +348,16 @@ def bbox_decode(boxes, trans, clip_to=None, min_size=None):
     return out, flags
 
 
-def detect(prob, boxes, count=None, nms_thresh=0.3, conf=0.8):
+def detect(prob, boxes, count=None, nms_thresh=0.3, conf=0.8, out=None):
+    """frcnn_detect.  out: optional pre-allocated (keep_idx [NC-1,R_cap], keep_count [NC-1], conf_count [NC-1]) int32."""
     R_cap, NC = prob.shape
     dev = prob.device
-    keep_idx = torch.empty((NC - 1, R_cap), dtype=torch.int32, device=dev)
-    keep_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
-    conf_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
+    if out is not None:
+        keep_idx, keep_count, conf_count = out
+    else:
+        keep_idx = torch.empty((NC - 1, R_cap), dtype=torch.int32, device=dev)
+        keep_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
+        conf_count = torch.empty((NC - 1,), dtype=torch.int32, device=dev)
     check(_lib.load().frcnn_detect(_p(prob), _p(boxes), _p(count), R_cap, NC, float(nms_thresh), ctypes.c_float(conf),
                                    _p(keep_idx), _p(keep_count), _p(conf_count), _stream()), "frcnn_detect")
     return keep_idx, keep_count, conf_count
@@ -279,14 +366,19 @@ def detect(prob, boxes, count=None, nms_thresh=0.3, conf=0.8):
 class ProposalWorkspace(object):
     """Pre-allocated scratch + outputs of frcnn_proposals for one (A,H,W,pre,post) shape."""
 
-    def __init__(self, A, H, W, pre_n, post_n, device, debug=False):
+    def __init__(self, A, H, W, pre_n, post_n, device, debug=False, outputs=None):
+        """outputs: optional pre-allocated (rois [post_n,4] f32, scores [post_n] f32, count [1] i32) -- e.g. views of one
+        result block that is copied to the host in a single transfer."""
         lib = _lib.load()
         self.shape = (A, H, W, pre_n, post_n)
         nbytes = lib.frcnn_proposals_workspace_bytes(A, H, W, pre_n)
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        self.rois = torch.zeros((post_n, 4), dtype=torch.float32, device=device)
-        self.scores = torch.zeros((post_n,), dtype=torch.float32, device=device)
-        self.count = torch.zeros((1,), dtype=torch.int32, device=device)
+        if outputs is not None:
+            self.rois, self.scores, self.count = outputs
+        else:
+            self.rois = torch.zeros((post_n, 4), dtype=torch.float32, device=device)
+            self.scores = torch.zeros((post_n,), dtype=torch.float32, device=device)
+            self.count = torch.zeros((1,), dtype=torch.int32, device=device)
         k_cap = min(pre_n, A * H * W)
         self.dbg_dets = torch.zeros((k_cap, 5), dtype=torch.float32, device=device) if debug else None
         self.dbg_idx = torch.zeros((k_cap,), dtype=torch.int32, device=device) if debug else None
@@ -340,7 +432,7 @@ def cpu_nms_host(dets_np, thresh, device_id=0):
                                        keep.ctypes.data_as(ctypes.c_void_p), device_id)
     if r < 0:
         raise FrcnnError("frcnn_cpu_nms_host failed (status %d): %s" % (r, _lib.last_error()))
-    return [int(v) for v in keep[:r]]
+    return keep[:r].tolist()
 
 
 def gpu_nms_host(sorted_dets_np, thresh, device_id=0):

@@ -126,11 +126,21 @@ class FasterRCNN(links.Link):
             d["loss_cls"], d["loss_bbox"], d["cls_accuracy"], d["loss_rcnn"] = [Variable(v) for v in vals]
             return self.loss_rcnn
         fam = arrays.family(x)
-        t = arrays.to_device(x)
         hw = arrays.to_host_ints(img_info)
         pl = self.RPN.proposal_layer
-        prob, boxes, plan = self.engine()(t[0], img_info=(int(hw[0]), int(hw[1])), pre_n=pl._pre_nms_top_n,
-                                          post_n=pl._post_nms_top_n, nms_thresh=pl._nms_thresh, min_size=pl._min_size)
+        kw = dict(pre_n=pl._pre_nms_top_n, post_n=pl._post_nms_top_n, nms_thresh=pl._nms_thresh, min_size=pl._min_size)
+        if fam == arrays.NUMPY:
+            # the reference's CPU-mode call (forward.py:88-94): a HOST float32 image in, host arrays out.  One pinned
+            # upload, the graph, ONE download of the whole result block; thread-safe (a plan per calling thread).
+            import numpy as np
+            xd = arrays.raw(x)
+            xd = xd if xd.dtype == np.float32 and xd.flags.c_contiguous else np.ascontiguousarray(xd, dtype=np.float32)
+            res, plan = self.engine().call_host(xd[0], img_info=(int(hw[0]), int(hw[1])), **kw)
+            self.__dict__["rpn_proposals"] = res["rois"].copy()
+            self.__dict__["rpn_probs"] = res["scores"].reshape(-1, 1).copy()
+            return Variable(res["prob"].copy()), res["boxes"].copy()
+        t = arrays.to_device(x)
+        prob, boxes, plan = self.engine()(t[0], img_info=(int(hw[0]), int(hw[1])), **kw)
         R = prob.shape[0]
         self.__dict__["rpn_proposals"] = arrays.from_device(plan.prop.rois[:R].clone(), fam)
         self.__dict__["rpn_probs"] = arrays.from_device(plan.prop.scores[:R].reshape(R, 1).clone(), fam)

@@ -115,6 +115,21 @@ void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w);
 /* 0 = automatic (CTA pairs / cta_group::2 for N tiles >= 128), 1 = force single-CTA MMAs, 2 = force pairs
  * where the tile allows it.  Process-wide; for tests and A/B timing. */
 void frcnn_conv2d_set_cta_group(int cta_group);
+/* Host staging for callers that hold HOST arrays (forward.py:88-99 uploads a float32 image and reads the results back):
+ * pinned blocks owned by the library and explicit asynchronous copies on the caller's stream.  frcnn_host_alloc returns
+ * NULL on failure (see frcnn_last_error). */
+void* frcnn_host_alloc(size_t bytes);
+int frcnn_host_free(void* p);
+int frcnn_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream);
+int frcnn_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes, void* stream);
+int frcnn_stream_synchronize(void* stream);
+
+/* Programmatic dependent launch for the forward-path kernels (per calling thread; default on, or the FRCNN_PDL
+ * environment variable "0"/"1"): a kernel's CTAs may become resident and run their prologue while the previous kernel of
+ * the stream drains; every such kernel waits (griddepcontrol.wait) before it touches global memory.  on < 0 restores the
+ * environment default.  Read when a launch is enqueued, i.e. fixed inside a captured graph. */
+void frcnn_set_programmatic_launch(int on);
+
 /* Cap on the persistent grid of subsequent frcnn_conv2d launches (0 = all SMs).  With several independent images in
  * flight on different streams, launches that each take a share of the SMs run side by side instead of queueing behind
  * each other's 148-CTA grids, and a smaller grid quantises a layer's tile count into fuller waves.  The value is baked
@@ -158,6 +173,18 @@ int frcnn_maxpool2x2_ceil(const void* x_hi, const void* x_lo, int H, int W, int 
 int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois,
                    const int* count, int R_cap, int outh, int outw, float scale, void* out_hi, void* out_lo,
                    float* out_f32, void* stream);
+
+/* L.Linear (+ F.relu) for a small number of rows: fc6 / fc7 / cls_score|bbox_pred over the R <= post_nms_top_n RoIs
+ * (models/faster_rcnn.py:33-36,127-134).  y[r, c] = act(sum_k x[r,k] * w[c,k] + bias[c]) for r < R_cap, c < Cout.
+ * Operands swapped on the tensor cores (weight rows = the M side, RoIs = the N side) and K split over the SMs; the
+ * fp32 partial slabs live in `workspace` (frcnn_linear_workspace_bytes) and are summed in fixed order (deterministic).
+ *   x_hi/x_lo [R_cap, K] bf16 planes (x_lo NULL = single-pass bf16), K % 64 == 0; w_hi/w_lo [Cout, K] as
+ *   frcnn_pack_conv_weights produces them (taps = 1); bias [Cout] fp32; m_valid (optional, device): rows >= *m_valid are 0.
+ *   y_hi/y_lo [R_cap, Cout] bf16 planes and/or y_f32 [R_cap, ld_f32] fp32 (columns [Cout, ld_f32) are written as 0). */
+size_t frcnn_linear_workspace_bytes(int R_cap, int K, int Cout);
+int frcnn_linear(const void* x_hi, const void* x_lo, int R_cap, int K, const void* w_hi, const void* w_lo,
+                 const float* bias, int Cout, int relu, const int* m_valid, void* y_hi, void* y_lo, float* y_f32,
+                 int ld_f32, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Head tail (models/faster_rcnn.py:175-178): softmax over num_classes scores + per-class
  * bbox_transform_inv + clip_boxes.  scores element (r,c) at scores[r*ld + c], deltas (r,j) at

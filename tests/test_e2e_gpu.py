@@ -151,10 +151,19 @@ def test_stream_runner_host_to_host_matches_direct_forward(params):
         want.append((p.cpu().clone(), b.cpu().clone(), int(c.item())))
     got = []
     runner = StreamRunner(plan)
-    counts = runner.run(imgs, on_result=lambda i, r: got.append((i, r["prob"].clone(), r["boxes"].clone(), int(r["count"][0]))))
+    counts = runner.run(imgs, on_result=lambda i, r: got.append((i, r["prob"].copy(), r["boxes"].copy(), r["count"], r["rois"].copy())))
     assert counts == [w[2] for w in want] and [g[0] for g in got] == list(range(5))
-    for (i, p, b, c), (wp, wb, wc) in zip(got, want):
-        assert c == wc and torch.equal(p, wp) and torch.equal(b, wb)
+    for (i, p, b, c, rois), (wp, wb, wc) in zip(got, want):
+        # one D2H of the result block per image: rows [0, count) of (prob, boxes, proposals)
+        assert c == wc and p.shape == (wc, 21) and np.array_equal(p, wp.numpy()[:wc]) and np.array_equal(b, wb.numpy()[:wc])
+        assert rois.shape == (wc, 4)
+    # numpy sources (pageable) and library-pinned blocks are accepted as well
+    from frcnn_b200 import ops as _ops
+    blk = _ops.PinnedBlock((3, H, W), np.float32)
+    blk.np[...] = imgs[2].numpy()
+    got2 = []
+    runner.run([imgs[2].numpy(), blk], on_result=lambda i, r: got2.append(r["prob"].copy()))
+    assert np.array_equal(got2[0], want[2][0].numpy()[:want[2][2]]) and np.array_equal(got2[1], got2[0])
 
 
 def test_lanes_in_flight_are_bit_identical_to_single_lane(params):
@@ -183,10 +192,10 @@ def test_lanes_in_flight_are_bit_identical_to_single_lane(params):
             assert torch.equal(pl.prob.cpu(), want[i][0]) and torch.equal(pl.boxes.cpu(), want[i][1])
     got = []
     runner = StreamRunner(pool, depth=4)
-    counts = runner.run(imgs, on_result=lambda i, r: got.append((i, r["prob"].clone(), r["boxes"].clone())))
+    counts = runner.run(imgs, on_result=lambda i, r: got.append((i, r["prob"].copy(), r["boxes"].copy())))
     assert counts == [w[2] for w in want] and [g[0] for g in got] == list(range(7))
     for (i, p, b), (wp, wb, wc) in zip(got, want):
-        assert torch.equal(p, wp) and torch.equal(b, wb)
+        assert np.array_equal(p, wp.numpy()[:wc]) and np.array_equal(b, wb.numpy()[:wc])
 
 
 def test_bf16_fast_mode_runs_and_is_close(params):

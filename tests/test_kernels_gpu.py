@@ -439,3 +439,60 @@ def test_long_k_gemm_rotating_accumulators_exact(ops, x3):
         y, y32 = ops.conv2d(xa, hi, lo, ops.pad_bias(b, N), 1, False, out_act=False, ld_f32=N)
         want = (x[0].double() @ w.double().T + b.double()).float()
         assert torch.equal(y32, want), (K, x3, float((y32 - want).abs().max()))
+
+
+# ------------------------------------------------------------------------------- head linears, swapped operands + split-K
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("shape", [(300, 1024, 105, 171, False),      # cls_score|bbox_pred: one 128-row weight tile, fp32 out
+                                   (300, 4096, 4096, 300, True),       # fc7
+                                   (300, 25088, 512, 233, True),       # fc6's K (392 k-blocks: 2 splits x 2 accumulators)
+                                   (77, 192, 96, 50, True),            # ragged everything: R_cap < one N tile, 3 k-blocks
+                                   (1000, 512, 256, 999, True)])       # config #4's RoI count (N tiles of 256)
+def test_linear_swapab_vs_float64(ops, precision, shape):
+    """frcnn_linear (weights on the M side, RoIs on the N side, K split over the SMs, fixed-order reduction) against the
+    float64 product of the identical 16-bit-split operands; rows >= *m_valid are zero."""
+    R, K, N, valid, relu = shape
+    rng = np.random.default_rng(R + K + N)
+    x = rng.standard_normal((R, K)).astype(f32)
+    w = (rng.standard_normal((N, K)) * (1.0 / K) ** 0.5).astype(f32)
+    b = (rng.standard_normal(N) * 0.1).astype(f32)
+    q = _quant16 if precision == "bf16x3" else _bf16
+    ref = q(x).astype(np.float64) @ q(w).astype(np.float64).T + b
+    if relu:
+        ref = np.maximum(ref, 0)
+    xt = dev(x)[None]                                         # [1,R,K]
+    hi = xt.to(torch.bfloat16)
+    act = ops.Act(hi, (xt - hi.float()).to(torch.bfloat16) if precision == "bf16x3" else None)
+    wh, wl = ops.pack_conv_weights(dev(w), precision=precision)
+    m_valid = torch.tensor([valid], dtype=torch.int32, device="cuda")
+    ld = (N + 31) // 32 * 32
+    y, y32 = ops.linear(act, wh, wl, ops.pad_bias(dev(b), ld), relu, m_valid=m_valid, ld_f32=ld)
+    y2, y32b = ops.linear(act, wh, wl, ops.pad_bias(dev(b), ld), relu, m_valid=m_valid, ld_f32=ld)
+    torch.cuda.synchronize()
+    got = y32.cpu().numpy()
+    scale = np.abs(ref).max()
+    err = np.abs(got[:valid, :N] - ref[:valid]).max() / scale
+    assert err < 3e-5, err
+    assert not got[valid:].any() and not got[:, N:].any()
+    assert torch.equal(y32, y32b) and torch.equal(y.hi, y2.hi)                    # deterministic reduction
+    val = y.hi[0].float() + (y.lo[0].float() if y.lo is not None else 0)
+    err_act = np.abs(val.cpu().numpy()[:valid] - ref[:valid]).max() / scale
+    assert err_act < (5e-5 if precision == "bf16x3" else 6e-3), err_act
+    assert not val[valid:].any().item()
+
+
+@pytest.mark.parametrize("x3", [True, False])
+def test_linear_swapab_long_k_exact_on_integers(ops, x3):
+    """Small-integer operands: every partial sum is exact in fp32, so split-K + rotating accumulators + the fixed-order
+    reduction must reproduce the integer GEMM exactly (fc6's K = 25,088 and a short K)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for K in (25088, 4096, 128):
+        R, N = 300, 256
+        x = torch.randint(-2, 3, (1, R, K), device="cuda", generator=g).float()
+        w = torch.randint(-2, 3, (N, K), device="cuda", generator=g).float()
+        b = torch.randint(-5, 6, (N,), device="cuda", generator=g).float()
+        xa = ops.Act(x.to(torch.bfloat16), torch.zeros_like(x, dtype=torch.bfloat16) if x3 else None)
+        hi, lo = ops.pack_conv_weights(w, precision="bf16x3" if x3 else "bf16")
+        _, y32 = ops.linear(xa, hi, lo, ops.pad_bias(b, N), False, ld_f32=N, want_act=False)
+        want = (x[0].double() @ w.double().T + b.double()).float()
+        assert torch.equal(y32, want), (K, x3, float((y32 - want).abs().max()))

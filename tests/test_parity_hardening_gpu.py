@@ -1,0 +1,349 @@
+"""GPU parity tests added in round 2 (VERDICT r01 "missing" #5/#6 and "weak" #1/#2):
+
+  * BASELINE config #1 end to end on the GPU: 600x800 image with img_info = (600, 600) exactly as forward.py:93 passes it
+    (SURVEY Q7), engine vs the CPU oracle stage-wise (bit-exact integer stages) AND pure end to end (matched fraction);
+  * pure end-to-end vs the fp32 oracle AT the headline size (600x1000) for seeds 0-4: matched-proposal fraction, box and
+    probability errors PER ELEMENT (not only max-norm), printed and asserted;
+  * the reference's interface: models.faster_rcnn.FasterRCNN.__call__ fed HOST float32 arrays (one pinned upload, one
+    download) returns bit for bit what the device path returns, also from several caller threads at once;
+  * the reference's own test files executed unchanged (when /root/reference is present -- it is not on the GPU box);
+  * the training path's NCCL all-reduce as a pytest (skipped under 2 GPUs).
+
+Tolerance readings ("within 1e-4 relative", BASELINE north_star):
+  max-norm      |got - want|.max() / |want|.max()                                       asserted < 1e-4 (stage-wise)
+  boxes / elem  |got - want| / max(width, height of THAT box, 1 px)                     asserted < 1e-4 (stage-wise)
+  probs / elem  |got - want| / want for want >= 1e-3                                    asserted < 5e-4, printed
+Note on "bit-exact": integer/index stages are bit-exact against the ORACLE, whose exp() is the same fixed IEEE operation
+sequence as the device's (oracle_c.c); against NumPy's exp the decode differs by <= 2 ulp (tests/test_oracle_cpu.py pins the
+oracle to the reference's golden vectors with atol 1e-3), so a keep-list flip at |IoU - thresh| < 1e-6 is possible in
+principle; none occurs on the 13 golden NMS cases and 7 golden ProposalLayer cases.
+"""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import frcnn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+ANCHORS = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def params():
+    return orc.make_params(seed=1234)
+
+
+def _engine(params, **kw):
+    from frcnn_b200.engine import Engine
+    return Engine(params, precision="bf16x3", anchors=ANCHORS, keep_rpn_debug=True, **kw)
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _box_err_per_element(got, want):
+    """|d| / max(box width, box height, 1) per coordinate, boxes laid out [R, 4K]."""
+    g, w = got.reshape(-1, 4).astype(np.float64), want.reshape(-1, 4).astype(np.float64)
+    size = np.maximum(np.maximum(w[:, 2] - w[:, 0] + 1, w[:, 3] - w[:, 1] + 1), 1.0)
+    return float((np.abs(g - w) / size[:, None]).max())
+
+
+def _prob_err_per_element(got, want, floor=1e-3):
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    m = want >= floor
+    return float((np.abs(got - want)[m] / want[m]).max()), int(m.sum())
+
+
+def _match(rois_dev, rois_ref, scale):
+    d = np.abs(rois_dev[:, None, :] - rois_ref[None, :, :]).max(-1)
+    j = d.argmin(1)
+    ok = d[np.arange(len(j)), j] < 1e-4 * scale
+    return ok, j
+
+
+def _stagewise(plan, prob, boxes, x, params, info_hw, fh, fw):
+    """Stage-wise identical-input checks; returns a dict of the measured errors."""
+    R = prob.shape[0]
+    info = np.array([list(info_hw)], np.int32)
+    feat_dev = plan.acts[-1].to_chw_f32().cpu().numpy()[None]
+    e_feat = _rel(feat_dev, orc.vgg16_forward(x, params))
+    rpn = plan.rpn_out.cpu().numpy()
+    logits = rpn[:, :18].T.reshape(1, 18, fh, fw)
+    deltas = rpn[:, 18:54].T.reshape(1, 36, fh, fw)
+    want_rois, want_fg = orc.proposal_layer(orc.softmax_axis1(logits), deltas, info)
+    assert R == len(want_rois) and R > 0
+    assert np.array_equal(plan.prop.rois.cpu().numpy()[:R], want_rois)                       # bit-exact
+    assert np.array_equal(plan.prop.scores.cpu().numpy()[:R], want_fg.ravel())
+    rois_dev = plan.prop.rois.cpu().numpy()[:R]
+    cls_ref, box_ref, aux = orc.head_forward(feat_dev, rois_dev, params, info)
+    pool_dev = (plan.pool5.hi.float() + plan.pool5.lo.float()).cpu().numpy().reshape(-1, 7, 7, 512)[:R]
+    assert np.array_equal(pool_dev.transpose(0, 3, 1, 2), aux["pool5"])                      # RoI pooling exact
+    p, b = prob.cpu().numpy(), boxes.cpu().numpy()
+    ho = plan.head_out.cpu().numpy()[:R]
+    assert np.array_equal(p, orc.softmax_axis1(ho[:, :21]))                                  # tail bit-exact on identical inputs
+    assert np.array_equal(b, orc.clip_boxes(orc.bbox_transform_inv(rois_dev, ho[:, 21:105]), info_hw))
+    e_fc7 = _rel((plan.fc7.hi.float() + plan.fc7.lo.float()).cpu().numpy()[0, :R], aux["fc7"])
+    e_box_max = _rel(b, box_ref)
+    e_box_el = _box_err_per_element(b, box_ref)
+    e_p_abs = float(np.abs(p - cls_ref).max())
+    e_p_el, n_el = _prob_err_per_element(p, cls_ref)
+    return dict(R=R, feat=e_feat, fc7=e_fc7, box_max=e_box_max, box_el=e_box_el, p_abs=e_p_abs, p_el=e_p_el, n_p=n_el,
+                p=p, b=b, rois=rois_dev)
+
+
+def test_config1_600x800_with_img_info_600_600(params):
+    """BASELINE config #1: forward.py's own case -- a 600x800 image and img_info = (H, H) = (600, 600) (forward.py:93 passes
+    img.shape[2] twice), so proposals and final boxes are clipped to x <= 599 although the image is 800 wide."""
+    H, W = 600, 800
+    x = orc.make_image(H, W, seed=0)
+    eng = _engine(params, with_detect=True, det_conf=0.05)
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda(), img_info=(H, H))
+    assert (plan.fh, plan.fw) == (38, 50)
+    m = _stagewise(plan, prob, boxes, x, params, (H, H), 38, 50)
+    print("config #1 (600x800, img_info 600x600): R=%d conv5_3 %.2e fc7 %.2e boxes max-norm %.2e per-element %.2e "
+          "probs abs %.2e per-element(p>=1e-3, n=%d) %.2e" % (m["R"], m["feat"], m["fc7"], m["box_max"], m["box_el"], m["p_abs"],
+                                                              m["n_p"], m["p_el"]))
+    assert m["feat"] < 1e-4 and m["fc7"] < 1e-4 and m["box_max"] < 1e-4 and m["box_el"] < 1e-4
+    assert m["p_abs"] < 1e-4 and m["p_el"] < 5e-4
+    assert m["b"][:, 0::4].max() <= H - 1 and m["b"][:, 2::4].max() <= H - 1 and m["rois"][:, 2].max() <= H - 1   # the Q7 clip
+    # per-class NMS of the caller (forward.py:48-57) on the device == the oracle's on the same (prob, boxes)
+    keep_idx, keep_count, conf_count = [t.cpu().numpy() for t in plan.det]
+    for c, keep, dets in orc.detect(m["p"], m["b"], 0.3, 0.05):
+        assert keep_idx[c - 1, :conf_count[c - 1]].tolist() == keep.tolist()
+    # pure end to end vs the fp32 oracle pipeline with the same (H, H) img_info
+    cls_ref, box_ref, aux = orc.faster_rcnn_forward(x, params, np.array([[H, H]], np.int32))
+    ok, j = _match(m["rois"], aux["proposals"], max(H, W))
+    print("config #1 pure end to end: matched proposals %.4f (%d of %d), oracle R=%d" % (ok.mean(), ok.sum(), len(ok), len(aux["proposals"])))
+    assert ok.mean() >= 0.97
+    assert np.abs(m["p"][ok] - cls_ref[j[ok]]).max() < 1e-4 * cls_ref.max()
+    assert _box_err_per_element(m["b"][ok], box_ref[j[ok]]) < 3e-4
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_headline_600x1000_pure_end_to_end_seeds(params, seed):
+    """BASELINE config #2, seeds 0-4: the whole device path vs the whole fp32 oracle path -- no stage is fed the
+    device's upstream tensors.  A score perturbation of ~1e-5 may reorder near-ties in the top-k / NMS, so proposals are
+    matched by box; the matched fraction, the errors of the matched rows and the tie-free-ness of the run are printed."""
+    H, W = 600, 1000
+    x = orc.make_image(H, W, seed=seed)
+    eng = _engine(params)
+    prob, boxes, plan = eng(torch.from_numpy(x[0]).cuda())
+    R = prob.shape[0]
+    cls_ref, box_ref, aux = orc.faster_rcnn_forward(x, params, np.array([[H, W]], np.int32))
+    rois_dev = plan.prop.rois.cpu().numpy()[:R]
+    ok, j = _match(rois_dev, aux["proposals"], max(H, W))
+    p, b = prob.cpu().numpy(), boxes.cpu().numpy()
+    fg = orc.softmax_axis1(plan.rpn_out.cpu().numpy()[:, :18].T.reshape(1, 18, 38, 63))[0, 9:].ravel()
+    same_order = bool(R == len(aux["proposals"]) and ok.all() and np.array_equal(j, np.arange(R)))
+    e_p_abs = float(np.abs(p[ok] - cls_ref[j[ok]]).max())
+    e_p_el, n_el = _prob_err_per_element(p[ok], cls_ref[j[ok]])
+    e_b_el = _box_err_per_element(b[ok], box_ref[j[ok]])
+    e_b_max = float(np.abs(b[ok] - box_ref[j[ok]]).max() / max(H, W))
+    print("seed %d 600x1000 pure e2e: R dev/oracle %d/%d matched %.4f identical order %s | unique fg scores %d/%d | probs abs %.2e "
+          "per-element(p>=1e-3, n=%d) %.2e | boxes /image-scale %.2e per-element(/box size) %.2e" %
+          (seed, R, len(aux["proposals"]), ok.mean(), same_order, np.unique(fg).size, fg.size, e_p_abs, n_el, e_p_el, e_b_max, e_b_el))
+    assert ok.mean() >= 0.97
+    assert e_p_abs < 1e-4 * cls_ref.max()
+    assert e_p_el < 1e-3
+    # pure end to end the decode multiplies the (~3e-5 relative) delta error by the box size: bounded at 3e-4 of the box size
+    assert e_b_el < 3e-4 and e_b_max < 3e-4
+
+
+# ------------------------------------------------------------------------------- the reference's interface, host arrays
+@pytest.fixture(scope="module")
+def model(params):
+    from frcnn_b200 import dropin
+    dropin.install()
+    from models.faster_rcnn import FasterRCNN
+    from models.vgg16 import VGG16Prev
+    m = FasterRCNN(trunk_class=VGG16Prev)
+    m.rcnn_train = False
+    m.rpn_train = False
+    named = dict(m.namedparams())
+    for k, v in params.items():
+        named["/" + k].data[...] = v
+    m._params_changed()
+    return m
+
+
+def test_reference_api_host_arrays_equal_device_path_and_threads(model, params):
+    """FasterRCNN.__call__(Variable(host float32 (1,3,H,W)), Variable(img_info)) -- forward.py:88-94 in CPU mode -- goes
+    through one pinned upload, the graph and ONE download; it must return bit for bit what the device-array call returns
+    (chainer.cuda.to_gpu input), keep the rpn_proposals / rpn_probs side outputs, and be callable from several threads."""
+    import chainer
+    from chainer import Variable
+    from models.cpu_nms import cpu_nms
+    H, W = 150, 201
+    xs = [orc.make_image(H, W, seed=60 + i) for i in range(4)]
+    info = Variable(np.array([[H, W]], np.int32))
+    want = []
+    for x in xs:
+        cls, box = model(Variable(chainer.cuda.to_gpu(x, device=0)), info)          # device arrays in, device arrays out
+        want.append((chainer.cuda.cupy.asnumpy(cls.data), chainer.cuda.cupy.asnumpy(box),
+                     chainer.cuda.cupy.asnumpy(model.rpn_proposals), chainer.cuda.cupy.asnumpy(model.rpn_probs)))
+    for x, (wc, wb, wr, wp) in zip(xs, want):
+        cls, box = model(Variable(x), info)                                          # host arrays in, host arrays out
+        assert isinstance(cls.data, np.ndarray) and isinstance(box, np.ndarray)
+        assert np.array_equal(cls.data, wc) and np.array_equal(box, wb)
+        assert np.array_equal(model.rpn_proposals, wr) and np.array_equal(model.rpn_probs, wp)
+        assert cls.data.shape[0] == box.shape[0] > 0
+    # non-contiguous / float64 inputs are converted like the reference's type check allows (float kind)
+    cls, box = model(Variable(xs[0].astype(np.float64)), info)
+    assert np.array_equal(box, want[0][1])
+    # four caller threads, each its own image, 3 rounds: identical results, per-class NMS through models.cpu_nms too
+    errs, got = [], {}
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            for _ in range(3):
+                cls, box = model(Variable(xs[k]), info)
+                keeps = []
+                for c in (1, 7, 20):
+                    dets = np.hstack((box[:, 4 * c:4 * c + 4], cls.data[:, c][:, np.newaxis]))
+                    keeps.append(cpu_nms(dets, 0.3))
+                got[k] = (cls.data.copy(), box.copy(), keeps)
+        except Exception as exc:          # noqa: BLE001
+            errs.append(repr(exc))
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for k in range(4):
+        assert np.array_equal(got[k][0], want[k][0]) and np.array_equal(got[k][1], want[k][1])
+        for c, keep in zip((1, 7, 20), got[k][2]):
+            dets = np.hstack((want[k][1][:, 4 * c:4 * c + 4], want[k][0][:, c][:, np.newaxis]))
+            assert keep == orc.cpu_nms(dets, 0.3)
+
+
+def test_cpu_nms_host_small_and_large_paths_and_threads():
+    """models.cpu_nms.cpu_nms on host arrays: n <= 2048 runs as ONE kernel on mapped pinned memory, larger n through the
+    chip-wide pipeline; both must equal the oracle (= the reference's cpu_nms.pyx on the golden cases), repeatedly (the
+    per-thread context is reused) and from several threads."""
+    import golden_inputs as gi
+    from frcnn_b200 import ops
+    cases = []
+    for n, seed in ((1, 1), (63, 2), (64, 3), (65, 4), (300, 5), (2048, 6), (2049, 7), (5000, 8)):
+        d = gi._clustered_dets(n, seed)
+        cases.append((d, 0.3 if n <= 300 else 0.7))
+    want = [orc.cpu_nms(d, t) for d, t in cases]
+    for _ in range(2):
+        for (d, t), w in zip(cases, want):
+            assert ops.cpu_nms_host(d, t) == w
+    assert ops.cpu_nms_host(np.zeros((0, 5), f32), 0.5) == []
+    # heavy ties: the pinned tie rule (lower index first) in the one-kernel path
+    rng = np.random.default_rng(3)
+    d = gi._clustered_dets(500, 77)
+    d[:, 4] = rng.integers(0, 8, size=500).astype(f32) / 8
+    assert ops.cpu_nms_host(d, 0.7) == orc.cpu_nms(d, 0.7)
+    # `_nms` (models/gpu_nms.hpp:9-10): pre-sorted rows, float `>`
+    order = np.argsort(-cases[4][0][:, 4], kind="stable")
+    got = ops.gpu_nms_host(cases[4][0][order], 0.3)
+    assert order[got].tolist() == want[4]
+    errs = []
+
+    def worker():
+        try:
+            for (d, t), w in zip(cases[:6], want[:6]):
+                for _ in range(5):
+                    assert ops.cpu_nms_host(d, t) == w
+        except Exception as exc:          # noqa: BLE001
+            errs.append(repr(exc))
+    ths = [threading.Thread(target=worker) for _ in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+
+
+# ------------------------------------------------------------------------------- the reference's own test files, unchanged
+REF = "/root/reference"
+
+
+def _run_reference_test_file(rel, only=None):
+    """Load /root/reference/<rel> as a module (unchanged source) after dropin.install() and run its unittest cases."""
+    import importlib.util
+    import unittest
+    from frcnn_b200 import dropin
+    dropin.install()
+    path = os.path.join(REF, rel)
+    name = "ref_" + os.path.basename(rel)[:-3]
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+
+    def flatten(s):
+        for t in s:
+            if isinstance(t, unittest.TestSuite):
+                for u in flatten(t):
+                    yield u
+            else:
+                yield t
+    tests = [t for t in flatten(suite) if only is None or only in t.id()]
+    assert tests, "no test cases found in %s" % rel
+    res = unittest.TextTestRunner(verbosity=0).run(unittest.TestSuite(tests))
+    assert res.wasSuccessful(), (res.failures, res.errors)
+    return len(tests)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is not present on this box (it never is on the GPU box)")
+@pytest.mark.parametrize("rel,only", [("tests/test_proposal_layer.py", None), ("tests/test_region_proposal_network.py", None),
+                                      ("tests/test_generate_anchors.py", None), ("tests/test_faster_rcnn.py", "test_forward_whole")])
+def test_reference_test_files_run_unchanged(rel, only):
+    """The reference's own tests executed as files against this build's `models` package (dropin.install()); test_faster_rcnn.py
+    needs datasets.pascal_voc_dataset.VOC -> the synthetic stand-in in chainer-faster-rcnn_b200/datasets/."""
+    assert _run_reference_test_file(rel, only) > 0
+
+
+def test_reference_test_faster_rcnn_statements_with_the_voc_stand_in():
+    """tests/test_faster_rcnn.py:29-62 re-typed (the file itself cannot travel to the GPU box): setUp with VOC('train')[1] from the
+    synthetic stand-in, then test_forward_whole for both trunks and the three train switches."""
+    import chainer
+    import cupy as cp
+    from chainer import Variable
+    from frcnn_b200 import dropin
+    dropin.install()
+    from datasets.pascal_voc_dataset import VOC
+    from models.faster_rcnn import FasterRCNN
+    from models.vgg16 import VGG16, VGG16Prev
+    for trunk in (VGG16Prev, VGG16):
+        for train in ((True, False), (False, True), (False, False)):
+            chainer.set_debug(True)
+            np.random.seed(0)
+            img, im_info, bbox = VOC('train')[1]
+            x, info = Variable(img[None, ...]), Variable(im_info[None, ...])
+            model = FasterRCNN(trunk, 512, 512, 16, [0.5, 1, 2], [8, 16, 32], 21)
+            model.rpn_train, model.rcnn_train = train
+            model.to_gpu(0)
+            x.to_gpu(0)
+            x.volatile = True
+            assert model.xp is cp and model.trunk.xp is cp
+            ret = model(x, info)
+            assert len(ret) == 2 and isinstance(ret[0], chainer.Variable) and isinstance(ret[1], (cp.ndarray, np.ndarray))
+            R = ret[0].data.shape[0]
+            assert ret[0].data.shape == (R, 21) and ret[1].shape == (R, 84) and R > 0
+
+
+# ------------------------------------------------------------------------------- training collective (NCCL), as a pytest
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (the NCCL all-reduce of the train_rpn.py step)")
+def test_train_rpn_gradient_allreduce_two_ranks_nccl():
+    """train_rpn.py:169-174 (ParallelUpdater): 2 ranks, each back-propagates its own image, gradients are ADDED with one
+    all-reduce, identical update on both.  tests/gpu_train_ddp_check.py asserts bucket == g(image0) + g(image1) exactly and
+    bit-identical replicas."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tests", "gpu_train_ddp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
