@@ -620,6 +620,7 @@ def run_train_arm(args, rank, local_rank, world):
     anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
     params = orc.make_params(seed=1234)
     tr = RpnTrainer(params, H_IMG, W_IMG, anchors, precision=args.precision, subsample="device")
+    tr.set_grad_exchange(args.grad_dtype, overlap=not args.no_overlap)
     imgs = [torch.from_numpy(orc.make_image(H_IMG, W_IMG, seed=shard.image_seed(rank, i))[0]).cuda() for i in range(4)]
     gt = torch.tensor([[100, 120, 400, 380, 3], [500, 200, 900, 560, 7], [50, 50, 200, 180, 1], [600, 30, 780, 150, 5]],
                       dtype=torch.float32).cuda()
@@ -645,6 +646,14 @@ def run_train_arm(args, rank, local_rank, world):
     ms = shard.max_over_ranks(e0.elapsed_time(e1), device="cuda")
     clocks = sampler.stop() if rank == 0 else None
     losses = [float(v) for v in tr.last_losses.cpu().numpy()]
+    # exposed gradient exchange: per step, the time between "backward enqueued work done" (compute stream) and "all-reduce
+    # done" (communication stream), CUDA events, 8 extra steps with a sync after each; max over ranks of the median
+    exposed = []
+    for i in range(8):
+        tr.step(imgs[i % 4], gt)
+        torch.cuda.synchronize()
+        exposed.append(tr.last_exposed_exchange_ms())
+    exposed_ms = shard.max_over_ranks(sorted(exposed)[len(exposed) // 2], device="cuda") if world > 1 else 0.0
     if rank == 0:
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -664,7 +673,11 @@ def run_train_arm(args, rank, local_rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "train_rpn.py step, VGG16 trunk + RPN trainable, one 600x1000 image per GPU per step, "
-                                   "all-reduce(SUM) of the flat fp32 gradient bucket (config #5; secondary workload)",
+                                   "all-reduce(SUM) of the gradient bucket (config #5; secondary workload)",
+                       "gradient_exchange": {"dtype": args.grad_dtype, "bucket_bytes": int(tr.g_flat.numel()) * (2 if args.grad_dtype == "bf16" else 4),
+                                             "buckets": "deep layers (conv4_1..heads) reduced on a side stream during the rest of "
+                                                        "backward; shallow layers after it" if not args.no_overlap else "one all-reduce after backward",
+                                             "exposed_ms_median_max_over_ranks": exposed_ms},
                        "last_losses_cls_bbox_acc_total": losses},
             "clocks": clocks, "cpu_baseline": cpu_baseline}), flush=True)
     if world > 1:
@@ -801,6 +814,9 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
+    ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="train_rpn workload: dtype of the all-reduced gradient bucket (BASELINE config #5 says bf16)")
+    ap.add_argument("--no-overlap", action="store_true", help="train_rpn workload: one all-reduce after backward instead of bucket overlap")
     ap.add_argument("--api-threads", type=int, default=4, help="caller threads of the reference-interface e2e leg")
     ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")

@@ -30,6 +30,11 @@ void set_error(const char* fmt, ...);
 
 #define FRCNN_LAUNCH_OK() FRCNN_CUDA_OK(cudaGetLastError())
 
+// First statement of every entry point: drop a stale, non-sticky error that an EARLIER runtime call of this host thread
+// (the framework's, another library's) may have left behind -- cudaGetLastError() after a <<<>>> launch reports the last
+// error of the calling thread, whoever caused it.
+#define FRCNN_ENTRY() ((void)cudaGetLastError())
+
 // ------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  The forward path is a chain of ~35 dependent kernels; launched with the
 // programmatic-stream-serialization attribute a kernel's CTAs may become resident while the previous kernel drains
@@ -59,6 +64,18 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// launch without the attribute; the launch status comes back directly (no cudaGetLastError involved)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                       Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -885,6 +885,7 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
 extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
                             const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
                             void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_) {
+    FRCNN_ENTRY();
     return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, fuse_pool2x2, y_hi, y_lo, y_f32, ld_f32,
                        m_valid, stream_, nullptr);
 }
@@ -892,12 +893,14 @@ extern "C" int frcnn_conv2d(const void* x_hi, const void* x_lo, int H, int W, in
 extern "C" int frcnn_conv2d_res(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi, const void* w_lo,
                                 const float* bias, int Cout, int ksize, int relu, const void* res_hi, const void* res_lo,
                                 void* y_hi, void* y_lo, void* stream_) {
+    FRCNN_ENTRY();
     ResExtra re{res_hi, res_lo};
     return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, 0, y_hi, y_lo, nullptr, 0, nullptr, stream_,
                        nullptr, &re);
 }
 
 extern "C" int frcnn_gemm_nt_splitk_splits(int K, int splits) {
+    FRCNN_ENTRY();
     const int kb = cdiv(K, 64), per = cdiv(kb, splits < 1 ? 1 : splits);
     return cdiv(kb, per);
 }
@@ -905,6 +908,7 @@ extern "C" int frcnn_gemm_nt_splitk_splits(int K, int splits) {
 extern "C" int frcnn_gemm_nt_splitk(const void* a_hi, const void* a_lo, int M, int K, const void* b_hi, const void* b_lo,
                                     int N, int groups, int row_stride, int splits, const float* zero_bias, float* parts,
                                     int ld, void* stream_) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(groups == 1 || groups == 9, "gemm_nt_splitk: groups must be 1 or 9 (got %d)", groups);
     FRCNN_REQUIRE(M > 0 && N > 0 && K > 0 && K % 64 == 0, "gemm_nt_splitk: bad shape M=%d N=%d K=%d (K %% 64 == 0)", M, N, K);
     FRCNN_REQUIRE(splits >= 1 && parts && zero_bias, "gemm_nt_splitk: splits >= 1, parts and a zero bias vector of ld floats are required");

@@ -90,6 +90,7 @@ int check_config(const frcnn_forward_config* c) {
 extern "C" {
 
 size_t frcnn_forward_workspace_bytes(const frcnn_forward_config* config) {
+    FRCNN_ENTRY();
     if (check_config(config) != FRCNN_OK) return 0;
     return carve(*config, nullptr).total;
 }
@@ -97,6 +98,7 @@ size_t frcnn_forward_workspace_bytes(const frcnn_forward_config* config) {
 int frcnn_forward_vgg16(const frcnn_forward_config* config, const frcnn_vgg16_weights* wts, const float* image_chw, int im_h,
                         int im_w, void* workspace, size_t workspace_bytes, float* out_prob, float* out_boxes, int* out_count,
                         void* stream) {
+    FRCNN_ENTRY();
     int rc = check_config(config);
     if (rc != FRCNN_OK) return rc;
     const frcnn_forward_config& c = *config;

@@ -35,7 +35,7 @@ __device__ __forceinline__ float hn_iou(const float4 a, const float4 b) {     //
 // out[2..] = keep list (original indices, descending score).
 __global__ void __launch_bounds__(kSmallThreads) nms_small_kernel(const float* __restrict__ dets, int n, int dim, int presorted,
                                                                   double thr_d, float thr_f, int mode, volatile int* out,
-                                                                  int ticket) {
+                                                                  int ticket, int use_mask) {
     extern __shared__ __align__(16) unsigned char sm[];
     float4* sbox = reinterpret_cast<float4*>(sm);               // [n] boxes by rank
     float4* rbox = sbox + n;                                    // [n] boxes by row
@@ -43,10 +43,28 @@ __global__ void __launch_bounds__(kSmallThreads) nms_small_kernel(const float* _
     int* order = reinterpret_cast<int*>(sc + n);                // [n] row by rank
     unsigned char* dead = reinterpret_cast<unsigned char*>(order + n);
     const int tid = threadIdx.x;
-    for (int r = tid; r < n; r += kSmallThreads) {
-        const float* d = dets + (size_t)r * dim;
-        rbox[r] = make_float4(d[0], d[1], d[2], d[3]);
-        sc[r] = presorted ? 0.0f : d[4];
+    // the rows live in MAPPED HOST memory: read the dense [n*dim] floats once, coalesced (consecutive lanes = consecutive
+    // words -> few, large PCIe reads), into shared memory, then regroup
+    float* flat = reinterpret_cast<float*>(sbox);            // sbox [n] float4 is not live yet: n*dim <= n*5 floats fit in 2n float4
+    for (int k = tid; k < n * dim; k += kSmallThreads) flat[k] = dets[k];
+    __syncthreads();
+    float4 my_box[(kSmallMax + kSmallThreads - 1) / kSmallThreads];
+    float my_sc[(kSmallMax + kSmallThreads - 1) / kSmallThreads];
+    {
+        int q = 0;
+        for (int r = tid; r < n; r += kSmallThreads, ++q) {
+            const float* d = flat + (size_t)r * dim;
+            my_box[q] = make_float4(d[0], d[1], d[2], d[3]);
+            my_sc[q] = presorted ? 0.0f : d[4];
+        }
+    }
+    __syncthreads();
+    {
+        int q = 0;
+        for (int r = tid; r < n; r += kSmallThreads, ++q) {
+            rbox[r] = my_box[q];
+            sc[r] = my_sc[q];
+        }
     }
     __syncthreads();
     for (int r = tid; r < n; r += kSmallThreads) {
@@ -64,6 +82,43 @@ __global__ void __launch_bounds__(kSmallThreads) nms_small_kernel(const float* _
         dead[rank] = 0;
     }
     __syncthreads();
+    if (use_mask) {
+        // suppression bitmask in shared memory (row i = the later ranks box i suppresses, upper triangle), then ONE warp walks
+        // the ranks with the `removed` words in registers: no block-wide barrier on the greedy chain
+        const int nw = (n + 63) >> 6;
+        unsigned long long* mask = reinterpret_cast<unsigned long long*>(dead + ((n + 15) & ~15));
+        for (int it = tid; it < n * nw; it += kSmallThreads) {
+            const int i = it / nw, w = it - i * nw;
+            unsigned long long bits = 0ull;
+            if (w >= (i >> 6)) {
+                const float4 a = sbox[i];
+                const int j0 = w << 6, j1 = min(n, j0 + 64);
+                for (int j = max(j0, i + 1); j < j1; ++j) {
+                    const float ovr = hn_iou(a, sbox[j]);
+                    if (mode == FRCNN_NMS_GE_DOUBLE ? ((double)ovr >= thr_d) : (ovr > thr_f)) bits |= 1ull << (j - j0);
+                }
+            }
+            mask[(size_t)i * nw + w] = bits;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned long long removed = 0ull;            // lane w: ranks [64w, 64w + 64)
+            int nk = 0;
+            for (int i = 0; i < n; ++i) {
+                const unsigned long long word = __shfl_sync(0xffffffffu, removed, i >> 6);
+                if ((word >> (i & 63)) & 1ull) continue;
+                if (tid == 0) out[2 + nk] = order[i];
+                ++nk;
+                if (tid < nw) removed |= mask[(size_t)i * nw + tid];
+            }
+            if (tid == 0) {
+                out[1] = nk;
+                __threadfence_system();                // keep list + count visible to the host before the flag
+                out[0] = ticket;
+            }
+        }
+        return;
+    }
     int nk = 0;
     for (int i = 0; i < n; ++i) {
         if (dead[i]) continue;                      // uniform: dead[] is only written ahead of a barrier
@@ -95,6 +150,7 @@ struct HostNmsCtx {
     char* d_ws = nullptr;           // device scratch of the large-n path
     size_t ws_bytes = 0;
     int ticket = 0;
+    size_t smem_attr = 48 * 1024;   // largest dynamic shared-memory size set on nms_small_kernel by this thread so far
     ~HostNmsCtx() {                 // thread exit: best effort (the CUDA context may already be gone)
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
@@ -164,11 +220,16 @@ static int nms_host_impl(const float* dets_host, int n, int dim, double thresh, 
                 for (int j = 0; j < sd; ++j) ctx.h_in[(size_t)sd * i + j] = dets_host[(size_t)dim * i + j];
         }
         const int ticket = ++ctx.ticket == 0 ? ++ctx.ticket : ctx.ticket;
-        const size_t smem = (size_t)n * (2 * sizeof(float4) + sizeof(float) + sizeof(int) + 1) + 16;
-        FRCNN_CUDA_OK(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_small_kernel<<<1, kSmallThreads, smem, ctx.stream>>>(ctx.d_in, n, sd, presorted, thresh, (float)thresh, mode,
-                                                                  ctx.d_out, ticket);
-        FRCNN_LAUNCH_OK();
+        size_t smem = (size_t)n * (2 * sizeof(float4) + sizeof(float) + sizeof(int)) + ((n + 15) & ~15) + 16;
+        const size_t mask_bytes = (size_t)n * ((n + 63) / 64) * 8;
+        const int use_mask = smem + mask_bytes <= 160 * 1024;
+        if (use_mask) smem += mask_bytes;
+        if (smem > ctx.smem_attr) {                      // raise the kernel's dynamic shared-memory limit only when needed
+            FRCNN_CUDA_OK(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx.smem_attr = smem;
+        }
+        FRCNN_CUDA_OK(launch_plain(nms_small_kernel, dim3(1), dim3(kSmallThreads), smem, ctx.stream, (const float*)ctx.d_in, n, sd,
+                                   presorted, thresh, (float)thresh, mode, (volatile int*)ctx.d_out, ticket, use_mask));
         // poll the completion flag in mapped memory; if it does not show up soon, fall back to a stream sync (which also
         // surfaces an execution error)
         volatile int* flag = ctx.h_out;
@@ -214,12 +275,14 @@ using namespace frcnn;
 
 extern "C" void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, int boxes_dim,
                      float nms_overlap_thresh, int device_id) {
+    FRCNN_ENTRY();
     int r = nms_host_impl(boxes_host, boxes_num, boxes_dim, (double)nms_overlap_thresh, FRCNN_NMS_GT_FLOAT, 1, keep_out,
                           device_id);
     *num_out = r < 0 ? -1 : r;
 }
 
 extern "C" int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id) {
+    FRCNN_ENTRY();
     return nms_host_impl(dets_host, n, 5, thresh, FRCNN_NMS_GE_DOUBLE, 0, keep_out_host, device_id);
 }
 
@@ -239,23 +302,27 @@ extern "C" void* frcnn_host_alloc(size_t bytes) {
 }
 
 extern "C" int frcnn_host_free(void* p) {
+    FRCNN_ENTRY();
     if (p != nullptr) FRCNN_CUDA_OK(cudaFreeHost(p));
     return FRCNN_OK;
 }
 
 extern "C" int frcnn_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(dst_device && src_host, "frcnn_memcpy_h2d_async: NULL pointer");
     FRCNN_CUDA_OK(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
     return FRCNN_OK;
 }
 
 extern "C" int frcnn_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(dst_host && src_device, "frcnn_memcpy_d2h_async: NULL pointer");
     FRCNN_CUDA_OK(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     return FRCNN_OK;
 }
 
 extern "C" int frcnn_stream_synchronize(void* stream) {
+    FRCNN_ENTRY();
     FRCNN_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return FRCNN_OK;
 }

@@ -38,7 +38,15 @@ __global__ void __launch_bounds__(kRedThreads) linear_reduce_kernel(const float*
         float v = 0.0f;
         if (c < Cout && r < R) {
             const float* src = parts + (long)c * ld + r;
-            for (int s = 0; s < S; ++s) v = __fadd_rn(v, src[(long)s * part_stride]);       // fixed order: deterministic
+            int s = 0;
+            for (; s + 8 <= S; s += 8) {                     // 8 independent loads in flight, then the adds in order
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = src[(long)(s + u) * part_stride];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v = __fadd_rn(v, t[u]);
+            }
+            for (; s < S; ++s) v = __fadd_rn(v, src[(long)s * part_stride]);       // fixed order: deterministic
             v = __fadd_rn(v, bias[c]);
             if (relu) v = fmaxf(v, 0.0f);
         }
@@ -115,6 +123,7 @@ static LinearPlan plan_linear(int R_cap, int K, int Cout) {
 using namespace frcnn;
 
 extern "C" size_t frcnn_linear_workspace_bytes(int R_cap, int K, int Cout) {
+    FRCNN_ENTRY();
     if (R_cap <= 0 || K <= 0 || Cout <= 0 || K % 64 != 0) return 0;
     return align_up(plan_linear(R_cap, K, Cout).parts_bytes, 256);
 }
@@ -122,6 +131,7 @@ extern "C" size_t frcnn_linear_workspace_bytes(int R_cap, int K, int Cout) {
 extern "C" int frcnn_linear(const void* x_hi, const void* x_lo, int R_cap, int K, const void* w_hi, const void* w_lo,
                             const float* bias, int Cout, int relu, const int* m_valid, void* y_hi, void* y_lo, float* y_f32,
                             int ld_f32, void* workspace, size_t workspace_bytes, void* stream_) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(x_hi && w_hi && bias && workspace, "frcnn_linear: x_hi, w_hi, bias and workspace are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_linear: x_lo and w_lo must both be given (bf16x3) or both NULL");
     FRCNN_REQUIRE(R_cap > 0 && Cout > 0 && K > 0 && K % 64 == 0, "frcnn_linear: bad shape R_cap=%d K=%d Cout=%d (K %% 64 == 0)", R_cap, K, Cout);

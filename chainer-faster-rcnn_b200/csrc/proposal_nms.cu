@@ -561,6 +561,7 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
 using namespace frcnn;
 
 extern "C" size_t frcnn_proposals_workspace_bytes(int A, int H, int W, int pre_nms_top_n) {
+    FRCNN_ENTRY();
     if (A <= 0 || H <= 0 || W <= 0 || pre_nms_top_n <= 0) return 0;
     const long n_all = (long)A * H * W;
     const int k_cap = (int)(pre_nms_top_n < n_all ? pre_nms_top_n : n_all);
@@ -573,6 +574,7 @@ extern "C" int frcnn_proposals(const float* cls, long cls_chan_stride, long cls_
                                int pre_nms_top_n, int post_nms_top_n, double nms_thresh, float* out_rois,
                                float* out_scores, int* out_count, float* dbg_sorted_dets, int* dbg_sorted_anchor_idx,
                                int* dbg_num_sorted, void* ws, size_t ws_bytes, void* stream_) {
+    FRCNN_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(cls && bbox && anchors && out_rois && out_count && ws, "frcnn_proposals: NULL argument");
     FRCNN_REQUIRE(A > 0 && A <= 32 && H > 0 && W > 0, "frcnn_proposals: bad shape A=%d H=%d W=%d", A, H, W);
@@ -600,12 +602,14 @@ extern "C" int frcnn_proposals(const float* cls, long cls_chan_stride, long cls_
 }
 
 extern "C" size_t frcnn_nms_workspace_bytes(int n) {
+    FRCNN_ENTRY();
     if (n <= 0) return 256;
     return carve(nullptr, n, n).total;
 }
 
 extern "C" int frcnn_nms(const float* dets, int n, double thresh, int mode, int max_keep, int* keep_out,
                          int* num_out, void* ws, size_t ws_bytes, void* stream_) {
+    FRCNN_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(num_out != nullptr, "frcnn_nms: num_out is NULL");
     FRCNN_REQUIRE(n >= 0 && n <= 16384, "frcnn_nms: n must be in [0,16384] (got %d)", n);

@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(1024) rcnn_loss_kernel(const float* __restrict
         if (dhead)
             for (int c = lane; c < num_classes; c += 32)
                 dhead[(size_t)r * ld + c] = (float)((exp((double)z[c] - lse) - (c == t ? 1.0 : 0.0)) * grad_scale / n);
-        if (lane == 0) { s_ce[i] = lse - (double)z[t]; s_hub[i] = hub; s_ok[i] = am == t ? 1.0 : 0.0; }
+        // a ground-truth class outside [0, num_classes) (a dataset with another class count, a NaN label) must not index the
+        // score row: its loss becomes NaN -- loud in the reported loss, the caller's check -- instead of a silently wrong value
+        const bool t_ok = t >= 0 && t < num_classes;
+        if (lane == 0) { s_ce[i] = t_ok ? lse - (double)z[t] : nan(""); s_hub[i] = hub; s_ok[i] = am == t ? 1.0 : 0.0; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -234,6 +237,7 @@ extern "C" {
 
 int frcnn_roi_overlaps(const float* rois, const int* count, int R_cap, const float* gt_boxes, int n_gt, double* max_overlaps,
                        int* argmax, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(rois && gt_boxes && max_overlaps && argmax && R_cap > 0 && n_gt > 0, "roi_overlaps: bad arguments");
     roi_overlaps_kernel<<<cdiv(R_cap, 128), 128, 0, (cudaStream_t)stream>>>(rois, count, R_cap, gt_boxes, n_gt, max_overlaps, argmax);
     FRCNN_LAUNCH_OK();
@@ -242,6 +246,7 @@ int frcnn_roi_overlaps(const float* rois, const int* count, int R_cap, const flo
 
 int frcnn_roi_targets(const float* rois, const float* gt_boxes, const int* argmax, const int* keep_inds, int n, int num_classes,
                       float* use_gt_boxes, float* bbox_reg_targets, int* labels, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(rois && gt_boxes && argmax && keep_inds && use_gt_boxes && bbox_reg_targets && labels && n >= 0 && num_classes > 0,
                   "roi_targets: bad arguments");
     if (n == 0) return FRCNN_OK;
@@ -252,6 +257,7 @@ int frcnn_roi_targets(const float* rois, const float* gt_boxes, const int* argma
 }
 
 int frcnn_bbox_transform(const float* ex_rois, const float* gt_rois, int gt_stride, int n, float* out, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(n >= 0 && gt_stride >= 4, "bbox_transform: bad arguments");
     if (n == 0) return FRCNN_OK;
     FRCNN_REQUIRE(ex_rois && gt_rois && out, "bbox_transform: null pointer");
@@ -261,6 +267,7 @@ int frcnn_bbox_transform(const float* ex_rois, const float* gt_rois, int gt_stri
 }
 
 int frcnn_keep_inside(const float* boxes, int n, int im_h, int im_w, unsigned char* flags, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(n >= 0, "keep_inside: bad arguments");
     if (n == 0) return FRCNN_OK;
     FRCNN_REQUIRE(boxes && flags, "keep_inside: null pointer");
@@ -272,6 +279,7 @@ int frcnn_keep_inside(const float* boxes, int n, int im_h, int im_w, unsigned ch
 int frcnn_rcnn_loss(const float* head_out, int ld, int R_cap, const int* keep_inds, int n, const int* labels,
                     const float* bbox_reg_targets, int num_classes, double delta, double grad_scale, float* losses, float* dhead,
                     void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(head_out && keep_inds && labels && bbox_reg_targets && losses && R_cap > 0 && ld >= 5 * num_classes,
                   "rcnn_loss: bad arguments");
     FRCNN_REQUIRE(n >= 1 && n <= 128, "rcnn_loss: 1 <= kept rows <= 128 (ROIS_PER_IMAGE), got %d", n);
@@ -283,6 +291,7 @@ int frcnn_rcnn_loss(const float* head_out, int ld, int R_cap, const int* keep_in
 }
 
 int frcnn_dropout(void* x_hi, void* x_lo, const unsigned char* mask, long n, float scale, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(x_hi && mask && n >= 0, "dropout: bad arguments");
     if (n == 0) return FRCNN_OK;
     dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x_hi, (__nv_bfloat16*)x_lo, mask, n, scale);
@@ -295,6 +304,7 @@ size_t frcnn_roi_pool_backward_workspace_bytes(int H, int W, int C) { return (si
 int frcnn_roi_pool_backward(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois, const int* count,
                             int R_cap, int outh, int outw, float scale, const void* g_hi, const void* g_lo, float* dfeat,
                             void* workspace, size_t workspace_bytes, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(feat_hi && rois && g_hi && dfeat && workspace && H > 0 && W > 0 && C > 0 && C % 8 == 0 && R_cap > 0,
                   "roi_pool_backward: bad arguments");
     if (workspace_bytes < frcnn_roi_pool_backward_workspace_bytes(H, W, C)) {

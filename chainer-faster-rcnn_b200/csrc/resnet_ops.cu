@@ -137,6 +137,7 @@ extern "C" {
 
 int frcnn_pack_image_im2col(const float* x_chw, int C, int H, int W, int ksize, int stride, int pad, int K_pad, void* y_hi,
                             void* y_lo, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(x_chw && y_hi && C > 0 && H > 0 && W > 0 && ksize > 0 && stride > 0 && pad >= 0, "pack_image_im2col: bad arguments");
     FRCNN_REQUIRE(K_pad % 8 == 0 && K_pad >= ksize * ksize * C, "pack_image_im2col: K_pad must be a multiple of 8 and >= ksize^2*C");
     const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
@@ -150,6 +151,7 @@ int frcnn_pack_image_im2col(const float* x_chw, int C, int H, int W, int ksize, 
 
 int frcnn_pack_conv_weights_im2col(const float* w_oihw, const float* scale, int Cout, int Cin, int ksize, int K_pad, void* w_hi,
                                    void* w_lo, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && ksize > 0 && K_pad % 8 == 0 && K_pad >= ksize * ksize * Cin,
                   "pack_conv_weights_im2col: bad arguments");
     pack_weights_im2col_general_kernel<<<cdiv(Cout * K_pad, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -159,6 +161,7 @@ int frcnn_pack_conv_weights_im2col(const float* w_oihw, const float* scale, int 
 }
 
 int frcnn_maxpool3x3s2_ceil(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(x_hi && y_hi && H >= 3 && W >= 3 && C > 0 && C % 8 == 0, "maxpool3x3s2_ceil: bad arguments (H=%d W=%d C=%d)", H, W, C);
     FRCNN_REQUIRE((x_lo == nullptr) == (y_lo == nullptr), "maxpool3x3s2_ceil: lo planes must both be given or both NULL");
     const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;            // ceil((H-3)/2) + 1
@@ -170,6 +173,7 @@ int frcnn_maxpool3x3s2_ceil(const void* x_hi, const void* x_lo, int H, int W, in
 }
 
 int frcnn_subsample2x(const void* x_hi, const void* x_lo, int H, int W, int C, void* y_hi, void* y_lo, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(x_hi && y_hi && H > 0 && W > 0 && C > 0 && C % 8 == 0, "subsample2x: bad arguments");
     FRCNN_REQUIRE((x_lo == nullptr) == (y_lo == nullptr), "subsample2x: lo planes must both be given or both NULL");
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;

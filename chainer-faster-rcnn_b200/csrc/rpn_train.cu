@@ -390,6 +390,7 @@ using namespace frcnn;
 extern "C" {
 
 int frcnn_bbox_overlaps(const double* boxes, int n, const double* query, int k, double* out, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(n >= 0 && k >= 0, "bbox_overlaps: negative size");
     if (n == 0 || k == 0) return FRCNN_OK;
     FRCNN_REQUIRE(boxes && query && out, "bbox_overlaps: null pointer");
@@ -400,6 +401,7 @@ int frcnn_bbox_overlaps(const double* boxes, int n, const double* query, int k, 
 }
 
 size_t frcnn_anchor_targets_workspace_bytes(int n_all, int n_gt) {
+    FRCNN_ENTRY();
     if (n_all < 0 || n_gt < 0) return 0;
     return align_up((size_t)n_all * sizeof(double), 256) + align_up((size_t)n_all * sizeof(int), 256) +
            align_up((size_t)(n_gt > 0 ? n_gt : 1) * sizeof(unsigned long long), 256);
@@ -410,6 +412,7 @@ int frcnn_anchor_targets(const double* anchors, int A, int feat_h, int feat_w, i
                          int subsample_mode, unsigned long long seed, const int* disable_pos, int n_disable,
                          int* labels_full, float* targets_full, int* inds_inside, int* counts, void* workspace,
                          size_t workspace_bytes, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(A > 0 && feat_h > 0 && feat_w > 0 && feat_stride > 0, "anchor_targets: bad geometry A=%d H=%d W=%d", A, feat_h, feat_w);
     FRCNN_REQUIRE(n_gt > 0, "anchor_targets: needs at least one ground-truth box (the reference's argmax over an empty axis raises)");
     FRCNN_REQUIRE(anchors && gt_boxes && labels_full && targets_full && inds_inside && counts && workspace, "anchor_targets: null pointer");
@@ -442,6 +445,7 @@ int frcnn_anchor_targets(const double* anchors, int A, int feat_h, int feat_w, i
 }
 
 size_t frcnn_rpn_loss_workspace_bytes(int n_all) {
+    FRCNN_ENTRY();
     if (n_all < 0) return 0;
     return (size_t)cdiv(n_all > 0 ? n_all : 1, 256) * 4 * sizeof(double);
 }
@@ -451,6 +455,7 @@ int frcnn_rpn_loss(const float* score, long score_cs, long score_ps, const float
                    const int* labels_full, const float* targets_full, const int* counts, double delta, double loss_lambda,
                    double grad_scale, float* losses, float* dscore, float* dbbox, void* workspace, size_t workspace_bytes,
                    void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(A > 0 && feat_h > 0 && feat_w > 0 && feat_stride > 0, "rpn_loss: bad geometry");
     FRCNN_REQUIRE(score && bbox && anchors && labels_full && targets_full && counts && losses && workspace, "rpn_loss: null pointer");
     FRCNN_REQUIRE(aligned(targets_full, 16), "rpn_loss: targets_full must be 16-byte aligned");

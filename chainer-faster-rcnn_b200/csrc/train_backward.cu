@@ -268,6 +268,32 @@ __global__ void sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ v
     w[i] = __fadd_rn(w[i], vi);
 }
 
+// bf16 gradient bucket (BASELINE config #5: "bf16, NCCL grad allreduce"): the fp32 gradients of a bucket are rounded to bf16
+// for the all-reduce (half the bytes on the wire), the fp32 masters / momentum are updated from the reduced bf16 values.
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);            // src + i is 16-B aligned (bucket starts are)
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&a);
+        o.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
+    }
+}
+
+__global__ void sgd_momentum_bf16g_kernel(float* __restrict__ w, float* __restrict__ v, const __nv_bfloat16* __restrict__ g, long n,
+                                          float lr, float momentum, float weight_decay) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = __fmaf_rn(weight_decay, w[i], __bfloat162float(g[i]));
+    const float vi = __fsub_rn(__fmul_rn(momentum, v[i]), __fmul_rn(lr, gi));
+    v[i] = vi;
+    w[i] = __fadd_rn(w[i], vi);
+}
+
 // ------------------------------------------------------------------------------------------ dgrad weight packing
 // out[t][ci][co] (bf16 hi/lo, co padded to Cout_pad) = W[co][ci][kh-1-r][kw-1-s], t = r*kw + s: the data gradient of a
 // stride-1 "same" convolution is the convolution of dY with the 180-degree rotated, in/out-swapped filter.
@@ -305,6 +331,7 @@ long frcnn_padded_pixels(int H, int W, int* row_pitch) { return padded_pixels(H,
 int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, int ld_f32, const void* y_hi, const void* y_lo,
                        const void* p_hi, const void* p_lo, int H, int W, int C, void* o_hi, void* o_lo, void* t_hi, void* t_lo,
                        int planes, int times2, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(H > 0 && W > 0 && C > 0 && C % 8 == 0, "grad_prepare: bad shape H=%d W=%d C=%d (C %% 8 == 0)", H, W, C);
     FRCNN_REQUIRE((g_hi != nullptr) != (g_f32 != nullptr), "grad_prepare: give the source as bf16 planes OR fp32");
     FRCNN_REQUIRE(!g_f32 || (ld_f32 >= 1 && !p_hi), "grad_prepare: fp32 source needs ld_f32 and no pooling");
@@ -337,6 +364,7 @@ int frcnn_grad_prepare(const void* g_hi, const void* g_lo, const float* g_f32, i
 
 int frcnn_wgrad_reduce(const float* parts, int groups, int splits, int M_parts, int M, int ld, int N, float scale, float* dw,
                        void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(parts && dw && groups >= 1 && splits >= 1 && M > 0 && M_parts >= M && N > 0 && ld >= N, "wgrad_reduce: bad arguments");
     const long total = (long)M * N * groups;
     wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(parts, groups, splits, M_parts, M, ld, N, dw, scale);
@@ -345,6 +373,7 @@ int frcnn_wgrad_reduce(const float* parts, int groups, int splits, int M_parts, 
 }
 
 int frcnn_bias_grad(const void* t_hi, const void* t_lo, int C, long Kp, float scale, float* db, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(t_hi && db && C > 0 && Kp > 0 && Kp % 64 == 0, "bias_grad: bad arguments");
     bias_grad_kernel<<<C, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)t_hi, (const __nv_bfloat16*)t_lo, Kp, db, scale);
     FRCNN_LAUNCH_OK();
@@ -352,6 +381,7 @@ int frcnn_bias_grad(const void* t_hi, const void* t_lo, int C, long Kp, float sc
 }
 
 int frcnn_sgd_momentum(float* w, float* v, const float* g, long n, float lr, float momentum, float weight_decay, void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(w && v && g && n >= 0, "sgd_momentum: bad arguments");
     if (n == 0) return FRCNN_OK;
     sgd_momentum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, v, g, n, lr, momentum, weight_decay);
@@ -359,8 +389,32 @@ int frcnn_sgd_momentum(float* w, float* v, const float* g, long n, float lr, flo
     return FRCNN_OK;
 }
 
+int frcnn_cast_f32_bf16(const float* src, void* dst_bf16, long n, void* stream) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(src && dst_bf16 && n >= 0, "cast_f32_bf16: bad arguments");
+    FRCNN_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0,
+                  "cast_f32_bf16: src must be 16-byte and dst 8-byte aligned");
+    if (n == 0) return FRCNN_OK;
+    const long threads = (n + 3) / 4;
+    cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst_bf16, n);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+int frcnn_sgd_momentum_bf16g(float* w, float* v, const void* g_bf16, long n, float lr, float momentum, float weight_decay,
+                             void* stream) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(w && v && g_bf16 && n >= 0, "sgd_momentum_bf16g: bad arguments");
+    if (n == 0) return FRCNN_OK;
+    sgd_momentum_bf16g_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, v, (const __nv_bfloat16*)g_bf16, n, lr,
+                                                                                              momentum, weight_decay);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
 int frcnn_pack_conv_weights_dgrad(const float* w_oihw, int Cout, int Cin, int kh, int kw, int Cout_pad, void* w_hi, void* w_lo,
                                   void* stream) {
+    FRCNN_ENTRY();
     FRCNN_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && Cout_pad >= Cout && Cout_pad % 8 == 0,
                   "pack_conv_weights_dgrad: bad arguments");
     const long total = (long)kh * kw * Cin * Cout_pad;

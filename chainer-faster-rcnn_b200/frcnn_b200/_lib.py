@@ -53,6 +53,7 @@ SIGNATURES = {
     "frcnn_preprocess_bgr8": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int, c_int,
                                       c_void_p, c_void_p]),
     "frcnn_pack_image_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_pack_image_im2col3x3_strided": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p]),
     "frcnn_pack_conv_weights_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_unpack_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "frcnn_maxpool2x2_ceil": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -80,6 +81,8 @@ SIGNATURES = {
     "frcnn_wgrad_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "frcnn_bias_grad": (c_int, [c_void_p, c_void_p, c_int, c_long, c_float, c_void_p, c_void_p]),
     "frcnn_sgd_momentum": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_void_p]),
+    "frcnn_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_long, c_void_p]),
+    "frcnn_sgd_momentum_bf16g": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_void_p]),
     "frcnn_pack_conv_weights_dgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_conv2d_res": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -25,6 +25,10 @@ import torch
 from . import ops
 from ._lib import FrcnnError
 
+import threading
+
+_CAPTURE_LOCK = threading.Lock()
+
 VGG16_LAYERS = [
     ("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool",
     ("conv2_1", 64, 128), ("conv2_2", 128, 128), "pool",
@@ -92,11 +96,14 @@ class ForwardPlan(object):
 
     def __init__(self, weights, H, W, pre_n=6000, post_n=300, nms_thresh=0.7, min_size=16, feat_stride=16,
                  anchors=None, with_detect=False, det_nms_thresh=0.3, det_conf=0.8, use_graph=True, keep_rpn_debug=False,
-                 fuse_pool=True):
+                 fuse_pool=True, hwc_input=False):
         self.w, self.H, self.W = weights, H, W
         self._ctor = dict(pre_n=pre_n, post_n=post_n, nms_thresh=nms_thresh, min_size=min_size, feat_stride=feat_stride,
                           anchors=anchors, with_detect=with_detect, det_nms_thresh=det_nms_thresh, det_conf=det_conf,
-                          use_graph=use_graph, keep_rpn_debug=keep_rpn_debug, fuse_pool=fuse_pool)
+                          use_graph=use_graph, keep_rpn_debug=keep_rpn_debug, fuse_pool=fuse_pool, hwc_input=hwc_input)
+        # hwc_input: the static input buffer holds the bytes of a dense (H,W,3) float32 image (what a forward.py-style caller's
+        # `img.transpose(2,0,1).astype(np.float32)` really is in memory); the first kernel reads it with HWC strides
+        self.hwc_input = bool(hwc_input)
         dev = weights.device
         x3 = weights.precision == "bf16x3"
         self.pre_n, self.post_n, self.nms_thresh, self.min_size, self.feat_stride = pre_n, post_n, nms_thresh, min_size, feat_stride
@@ -182,7 +189,7 @@ class ForwardPlan(object):
         w = self.w
         n = 0
         x = self.acts[0]
-        ops.pack_image_im2col(self.x_in, out=x)
+        ops.pack_image_im2col(self.x_in, out=x, hwc_memory=self.hwc_input)
         n += 1
         i = 0
         for name, fused, pool_after in self.trunk_steps:
@@ -259,7 +266,7 @@ class ForwardPlan(object):
         uploads, replays the graph and brings the whole result block back with ONE D2H; blocks until it is there.
         Returns a dict of numpy VIEWS into the pinned mirror (valid until the next forward_host on this plan)."""
         io = self.host_io()
-        io["x"].t.copy_(torch.from_numpy(x_np).reshape(io["x"].shape))     # pageable -> pinned on the host cores
+        io["x"].t.view(-1).copy_(torch.from_numpy(x_np).reshape(-1))       # pageable -> pinned on the host cores (dense bytes)
         n = self.result_words()
         st = io["stream"]
         io["x"].h2d(self.x_in, st)                                 # H2D (cudaMemcpyAsync from the library's pinned block)
@@ -291,12 +298,15 @@ class ForwardPlan(object):
             self._run()
         else:
             if self.graph is None:
-                self._run()                       # warm-up outside capture (func attributes, lazy init)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run()
-                self.graph = g
+                # one capture at a time in the process (torch's capture stream is shared), and thread-local capture mode so
+                # that other host threads (each running its own plan) may keep calling CUDA meanwhile
+                with _CAPTURE_LOCK:
+                    self._run()                   # warm-up outside capture (func attributes, lazy init)
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._run()
+                    self.graph = g
             self.graph.replay()
         return self.prob, self.boxes, self.prop.count
 
@@ -401,9 +411,13 @@ class StreamRunner(object):
             # -- asynchronous when that buffer is pinned (ops.PinnedBlock, tensor.pin_memory()), staged by the driver if not
             src = host_images[i]
             src = src.t if isinstance(src, ops.PinnedBlock) else (torch.from_numpy(src) if isinstance(src, np.ndarray) else src)
-            if src.numel() * src.element_size() != self.h2d_bytes or not src.is_contiguous():
-                raise FrcnnError("StreamRunner: host image %d has %d bytes, expected %d contiguous" %
+            if src.numel() * src.element_size() != self.h2d_bytes:
+                raise FrcnnError("StreamRunner: host image %d has %d bytes, expected %d" %
                                  (i, src.numel() * src.element_size(), self.h2d_bytes))
+            if not src.is_contiguous():
+                src = src.contiguous()             # a strided view (e.g. an HWC->CHW transpose): densify on the host first
+                host_images = list(host_images)
+                host_images[i] = src               # keep it alive until the copy has been consumed
             ops.memcpy_h2d_async(self.stage[s], src.data_ptr(), self.h2d_bytes, self.copy_stream)
             self.h2d_done[s].record(self.copy_stream)
             with torch.cuda.stream(cur):
@@ -429,6 +443,7 @@ class StreamRunner(object):
 
 class Engine(object):
     """Weights + per-shape plans.  `engine(x)` -> (prob [R,21], boxes [R,84]) device tensors, R synced."""
+    supports_hwc_input = True          # the VGG16 plan's first kernel takes source strides (ForwardPlan(hwc_input=True))
 
     def __init__(self, params, precision="bf16x3", device="cuda", anchors=None, num_classes=21, n_anchors=9,
                  feat_stride=16, **plan_kwargs):
@@ -471,8 +486,21 @@ class Engine(object):
         return p
 
     def call_host(self, x_np, img_info=None, **overrides):
-        """Host-array call: x_np float32 (3,H,W) numpy -> dict of numpy results (ForwardPlan.forward_host)."""
+        """Host-array call: x_np float32 (3,H,W) numpy -> dict of numpy results (ForwardPlan.forward_host).  A C-contiguous
+        array is uploaded as it is; so is the transposed view of a dense (H,W,3) array (forward.py:45 produces exactly that:
+        `img.transpose([2, 0, 1]).astype(np.float32)` keeps the HWC memory) -- the first kernel then reads it with HWC
+        strides; any other striding is densified on the host first."""
         H, W = int(x_np.shape[-2]), int(x_np.shape[-1])
+        if x_np.dtype != np.float32:
+            x_np = np.ascontiguousarray(x_np, dtype=np.float32)
+        if x_np.flags.c_contiguous:
+            dense = x_np
+        elif self.supports_hwc_input and x_np.ndim == 3 and x_np.transpose(1, 2, 0).flags.c_contiguous:
+            dense = x_np.transpose(1, 2, 0)             # the (H,W,3) memory itself, no copy
+            overrides = dict(overrides, hwc_input=True)
+        else:
+            dense = np.ascontiguousarray(x_np)
+        x_np = dense
         p = self.thread_plan(H, W, **overrides)
         if img_info is not None:
             p.set_clip(int(img_info[0]), int(img_info[1]))

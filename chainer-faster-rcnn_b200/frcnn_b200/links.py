@@ -6,10 +6,25 @@ import numpy as np
 
 
 class Param(object):
-    def __init__(self, data):
-        self.data = data
+    """One named array.  ASSIGNING `param.data = array` (what chainer.serializers.load_npz and most callers do) marks the
+    owning link as changed, so that packed device copies are rebuilt; mutating the array IN PLACE
+    (`param.data[...] = v`) cannot be seen from here -- call `link._params_changed()` afterwards."""
 
-    shape = property(lambda s: s.data.shape)
+    def __init__(self, data, owner=None):
+        object.__setattr__(self, "_data", data)
+        object.__setattr__(self, "_owner", owner)
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        object.__setattr__(self, "_data", value)
+        if self._owner is not None:
+            self._owner._bump()
+
+    shape = property(lambda s: s._data.shape)
 
 
 class Link(object):
@@ -21,7 +36,7 @@ class Link(object):
 
     def add_param(self, name, array):
         self._param_names.append(name)
-        object.__setattr__(self, name, Param(np.ascontiguousarray(array, dtype=np.float32)))
+        object.__setattr__(self, name, Param(np.ascontiguousarray(array, dtype=np.float32), owner=self))
 
     def add_link(self, name, link):
         self._child_names.append(name)
@@ -40,10 +55,19 @@ class Link(object):
     def param_dict(self, prefix=""):
         return {k.lstrip("/"): p.data for k, p in self.namedparams(prefix)}
 
-    def _params_changed(self):
+    def _bump(self):
         object.__setattr__(self, "_version", self._version + 1)
+
+    def _params_changed(self):
+        """Declare that parameter arrays of this link or of any link below it were modified in place."""
+        self._bump()
         for c in self._child_names:
             getattr(self, c)._params_changed()
+
+    def version_key(self):
+        """Changes whenever this link OR ANY DESCENDANT changed (a bump on a sub-link -- load_npz(path, model.trunk),
+        rpn._params_changed(), param.data = ... -- is therefore seen by every cache held further up)."""
+        return (self._version,) + tuple(getattr(self, c).version_key() for c in self._child_names)
 
     # -- device placement: the math always runs on the GPU; these only record the caller's intent so
     #    `xp` and the returned array family behave like the reference's links.

@@ -80,16 +80,19 @@ def pack_conv_weights(w, cin_pad=None, precision="bf16x3", perm_chw=None):
     return hi, lo
 
 
-def pack_image_im2col(x_chw, precision="bf16x3", out=None):
-    """(C<=3,H,W) float32 CUDA image -> Act [H,W,32]: every pixel's zero-padded 3x3xC neighbourhood."""
+def pack_image_im2col(x_chw, precision="bf16x3", out=None, hwc_memory=False):
+    """(C<=3,H,W) float32 CUDA image -> Act [H,W,32]: every pixel's zero-padded 3x3xC neighbourhood.
+    hwc_memory: `x_chw` is a (C,H,W)-shaped buffer whose BYTES are the dense (H,W,C) image (a host caller's transposed
+    view uploaded as it was); the kernel reads it with (1, W*C, C) strides."""
     _need_cuda(x_chw)
     x = x_chw.contiguous().float()
     C, H, W = x.shape
     if out is None:
         hi = torch.empty((H, W, 32), dtype=torch.bfloat16, device=x.device)
         out = Act(hi, torch.empty_like(hi) if precision == "bf16x3" else None)
-    check(_lib.load().frcnn_pack_image_im2col3x3(_p(x), C, H, W, _p(out.hi), _p(out.lo), _stream()),
-          "frcnn_pack_image_im2col3x3")
+    sc, sh, sw = (1, W * C, C) if hwc_memory else (H * W, W, 1)
+    check(_lib.load().frcnn_pack_image_im2col3x3_strided(_p(x), C, H, W, sc, sh, sw, _p(out.hi), _p(out.lo), _stream()),
+          "frcnn_pack_image_im2col3x3_strided")
     return out
 
 

@@ -125,6 +125,7 @@ class ResNetForwardPlan(ForwardPlan):
 
 class ResNetEngine(Engine):
     """`Engine` for FasterRCNN(trunk_class=ResNet, rpn_in_ch=2048, feat_stride=32)."""
+    supports_hwc_input = False         # the 7x7 first layer's im2col kernel reads dense (C,H,W) only
 
     def __init__(self, params, n_layers=101, precision="bf16x3", device="cuda", anchors=None, num_classes=21, n_anchors=9,
                  feat_stride=32, **plan_kwargs):
@@ -132,6 +133,8 @@ class ResNetEngine(Engine):
         self.anchors, self.feat_stride = anchors, feat_stride
         self.plan_kwargs = plan_kwargs
         self.plans = {}
+        import threading
+        self._tls, self._lock = threading.local(), threading.Lock()
 
     def plan(self, H, W, **overrides):
         kw = dict(self.plan_kwargs)

@@ -92,6 +92,18 @@ class _ConvTrainer(object):
         self._acts, self._tbufs = {}, {}
         self.packed = {}
         self.last_losses = None
+        # ---- multi-GPU gradient exchange (train_rpn.py:169-174): "fp32" = one exact SUM of the fp32 bucket (the parity
+        # mode: bucket == sum of the per-image gradients bit for bit); "bf16" = BASELINE config #5: the bucket is rounded
+        # to bf16 for the all-reduce (half the bytes), masters / momentum stay fp32.  The exchange runs on its own stream
+        # in two buckets: the deep layers (conv4_1 ... heads, 90 % of the parameters) are reduced while conv3_3 ... conv1_1
+        # still back-propagate; only the small shallow bucket is exposed.
+        self.grad_dtype = "fp32"
+        self.g_bf16 = None
+        self.comm_stream = None
+        self._comm_done = None
+        self._bucket_lo = None              # flat offset where the early (deep-layer) bucket starts
+        self.n_updates = 0                  # optimizer steps taken (the drop-in model syncs its Link params when this moves)
+        self._ev_bwd = self._ev_comm = None
 
 
 class RpnTrainer(_ConvTrainer):
@@ -298,6 +310,7 @@ class RpnTrainer(_ConvTrainer):
                 train_ops.grad_prepare(h, w, ci, g=x, tbuf=xT)
                 self._wgrad(dyT, xT, co, ci, 9, self.grads(L["name"] + "/W"))
             train_ops.bias_grad(dyT, co, self.grads(L["name"] + "/b"))
+            self._early_exchange(L["name"])
             if not first:
                 _, _, (dhi, dlo) = self.packed[L["name"]]
                 g = self._gact(h, w, ci, tag=1)
@@ -314,12 +327,71 @@ class RpnTrainer(_ConvTrainer):
         prev = self.layers[i - 1]
         return prev["p"] if prev["pool"] else prev["y"]
 
-    # ---------------------------------------------------------------- optimizer
+    # ---------------------------------------------------------------- gradient exchange + optimizer
+    def set_grad_exchange(self, grad_dtype="fp32", overlap=True):
+        """grad_dtype "fp32" (exact) or "bf16" (config #5); overlap: reduce the deep-layer bucket during the rest of backward."""
+        if grad_dtype not in ("fp32", "bf16"):
+            raise FrcnnError("grad_dtype must be fp32 or bf16")
+        self.grad_dtype = grad_dtype
+        if grad_dtype == "bf16" and self.g_bf16 is None:
+            self.g_bf16 = torch.zeros(self.g_flat.shape, dtype=torch.bfloat16, device=self.device)
+        self._overlap = bool(overlap)
+
+    def _multi(self):
+        return shard.dist.is_available() and shard.dist.is_initialized() and shard.dist.get_world_size(self.pg) > 1
+
+    def _exchange(self, lo, hi):
+        """All-reduce(SUM) of g_flat[lo:hi] on the communication stream, after everything queued so far on the compute stream."""
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            if self.grad_dtype == "bf16":
+                train_ops.cast_f32_bf16(self.g_flat[lo:hi], self.g_bf16[lo:hi])
+                shard.allreduce_sum_(self.g_bf16[lo:hi], self.pg)
+            else:
+                shard.allreduce_sum_(self.g_flat[lo:hi], self.pg)
+
+    def _early_exchange(self, layer_name):
+        """Called from the backward chain right after `layer_name`'s gradients are enqueued."""
+        if not getattr(self, "_overlap", True) or not self._multi() or layer_name != "trunk/conv4_1":
+            return
+        lo = self.index["trunk/conv4_1/W"][0]
+        if lo % 4 != 0:
+            return
+        self._bucket_lo = lo
+        self._exchange(lo, self.g_flat.numel())
+
     def update(self):
         """[all-reduce SUM over ranks, like ParallelUpdater's addgrads] + WeightDecay + MomentumSGD, then repack."""
-        shard.allreduce_sum_(self.g_flat, self.pg)
-        train_ops.sgd_momentum(self.w_flat, self.v_flat, self.g_flat, self.lr, self.momentum, self.weight_decay)
+        if self._multi():
+            hi = self._bucket_lo if self._bucket_lo is not None else self.g_flat.numel()
+            self._ev_bwd = torch.cuda.Event(enable_timing=True)
+            self._ev_bwd.record()                                  # backward fully enqueued on the compute stream
+            self._exchange(0, hi)
+            self._ev_comm = torch.cuda.Event(enable_timing=True)
+            self._ev_comm.record(self.comm_stream)
+            torch.cuda.current_stream().wait_event(self._ev_comm)
+            self._bucket_lo = None
+        if self.grad_dtype == "bf16" and self._multi():
+            train_ops.sgd_momentum_bf16g(self.w_flat, self.v_flat, self.g_bf16, self.lr, self.momentum, self.weight_decay)
+        else:
+            train_ops.sgd_momentum(self.w_flat, self.v_flat, self.g_flat, self.lr, self.momentum, self.weight_decay)
         self.repack()
+        self.n_updates += 1
+
+    def last_exposed_exchange_ms(self):
+        """Time between "backward done" on the compute stream and "exchange done" on the communication stream for the last
+        step (what the optimizer had to wait for); call after a synchronize.  0 if the exchange finished first."""
+        if self._ev_bwd is None or self._ev_comm is None:
+            return 0.0
+        return max(0.0, self._ev_bwd.elapsed_time(self._ev_comm))
+
+    def export_params(self):
+        """Trainable parameters as numpy arrays under the reference's names (checkpoint / write-back into the Links)."""
+        return {n: self.weights(n).detach().cpu().numpy().copy() for n in self.index}
 
     def step(self, x_chw, gt_boxes, im_info=None, disable_pos=None):
         losses = self.forward(x_chw, gt_boxes, im_info, disable_pos)

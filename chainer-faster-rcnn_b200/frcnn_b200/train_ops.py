@@ -109,7 +109,7 @@ def rpn_loss(score, bbox, anchors, A, H, W, feat_stride, im_h, im_w, work, delta
                                      int(im_h), int(im_w), _p(work.labels_full), _p(work.targets_full), _p(work.counts),
                                      float(delta), float(loss_lambda), float(grad_scale), _p(work.losses), ds_ptr, db_ptr,
                                      _p(work.loss_ws), work.loss_ws.numel(), _stream()), "frcnn_rpn_loss")
-    return work.losses, ds, db
+    return work.losses.clone(), ds, db          # a fresh tensor per call: the workspace buffer is overwritten by the next step
 
 
 def split_bf16(x):
@@ -198,6 +198,16 @@ def bias_grad(tbuf, C, db, scale=1.0):
 def sgd_momentum(w, v, g, lr, momentum, weight_decay):
     check(_lib.load().frcnn_sgd_momentum(_p(w), _p(v), _p(g), w.numel(), float(lr), float(momentum), float(weight_decay),
                                          _stream()), "frcnn_sgd_momentum")
+
+
+def cast_f32_bf16(src, dst):
+    """frcnn_cast_f32_bf16: round a (16-byte aligned) slice of the fp32 gradient bucket into the bf16 bucket."""
+    check(_lib.load().frcnn_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "frcnn_cast_f32_bf16")
+
+
+def sgd_momentum_bf16g(w, v, g_bf16, lr, momentum, weight_decay):
+    check(_lib.load().frcnn_sgd_momentum_bf16g(_p(w), _p(v), _p(g_bf16), w.numel(), float(lr), float(momentum),
+                                               float(weight_decay), _stream()), "frcnn_sgd_momentum_bf16g")
 
 
 def pack_conv_weights_dgrad(w, cout_pad=None, x3=True):

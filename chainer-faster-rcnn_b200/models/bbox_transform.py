@@ -53,6 +53,9 @@ def keep_inside(anchors, img_info):
     hw = arrays.to_host_ints(img_info)
     flags = train_ops.keep_inside_flags(a[:, :4], int(hw[0]), int(hw[1]))
     idx = torch.nonzero(flags, as_tuple=False).reshape(-1)
+    if fam == arrays.NUMPY:                     # rows come back in the caller's dtype (the reference keeps float64 anchors)
+        idx_np = idx.cpu().numpy()
+        return idx_np, arrays.raw(anchors)[idx_np]
     return arrays.from_device(idx, fam), arrays.from_device(a[idx], fam)
 
 

@@ -76,9 +76,28 @@ class FasterRCNN(links.Link):
             assert gt_boxes.shape[0] == 1 and gt_boxes.shape[1] > 0 and gt_boxes.shape[2] == 5
             assert arrays.dtype_kind(gt_boxes) == 'f'
 
+    # -- parameters learnt by the device-side trainer flow back into the Link params before anyone reads them
+    def _sync_trained_params(self):
+        tr = self.__dict__.get("rcnn_trainer")
+        if tr is None or self.__dict__.get("_rcnn_synced_updates", 0) == tr.n_updates:
+            return
+        named = dict(links.Link.namedparams(self))
+        for k, v in tr.export_params().items():              # fc6/W comes back in the reference's (c, h, w) column order
+            named["/" + k]._data[...] = v
+        self._params_changed()
+        self.__dict__["_rcnn_synced_updates"] = tr.n_updates
+        shape_key = self.__dict__.get("_rcnn_trainer_key")
+        if shape_key is not None:                              # the trainer already holds these weights: keep it
+            self.__dict__["_rcnn_trainer_key"] = (shape_key[0], self.version_key())
+
+    def namedparams(self, prefix=""):
+        """serializers.save_npz / param_dict / the inference engine all read the parameters through here."""
+        self._sync_trained_params()
+        return links.Link.namedparams(self, prefix)
+
     def engine(self):
         eng, ver = self._engine
-        if eng is None or ver != self._version:
+        if eng is None or ver != self.version_key():
             params = self.param_dict()
             kw = dict(precision=self.precision, anchors=self.RPN.proposal_layer._anchors, num_classes=self._num_classes,
                       n_anchors=self.RPN.proposal_layer._num_anchors, feat_stride=self._feat_stride)
@@ -88,7 +107,7 @@ class FasterRCNN(links.Link):
                 eng = ResNetEngine(params, n_layers, **kw)
             else:
                 eng = Engine(params, **kw)
-            self.__dict__["_engine"] = (eng, self._version)
+            self.__dict__["_engine"] = (eng, self.version_key())
         return eng
 
     def __call__(self, x, img_info, gt_boxes=None):
@@ -113,13 +132,20 @@ class FasterRCNN(links.Link):
             hw = arrays.to_host_ints(img_info)
             pl = self.RPN.proposal_layer
             tr = self.__dict__.get("rcnn_trainer")
-            key = (tuple(t.shape[2:]), self._version)
+            self._sync_trained_params()                       # weights a previous trainer learnt -> the Link params
+            key = (tuple(t.shape[2:]), self.version_key())
             if tr is None or self.__dict__.get("_rcnn_trainer_key") != key:
+                # a new image shape (VOC images vary in size) or externally changed parameters: the new trainer starts from
+                # the CURRENT parameters (synced above) and inherits the momentum of the one it replaces
+                old = tr
                 tr = RcnnTrainer(self.param_dict(), int(t.shape[2]), int(t.shape[3]), pl._anchors, precision=self.precision,
                                  feat_stride=self._feat_stride, num_classes=self._num_classes, delta=float(self._rcnn_delta),
                                  post_n=pl._post_nms_top_n, pre_n=pl._pre_nms_top_n, nms_thresh=pl._nms_thresh,
                                  min_size=pl._min_size, device=t.device)
+                if old is not None and old.index == tr.index:
+                    tr.v_flat.copy_(old.v_flat)
                 self.__dict__["rcnn_trainer"], self.__dict__["_rcnn_trainer_key"] = tr, key
+                self.__dict__["_rcnn_synced_updates"] = tr.n_updates
             losses = tr.forward(t[0], arrays.to_device(gt_boxes)[0], im_info=(int(hw[0]), int(hw[1])))
             vals = list(losses.cpu().numpy()) if fam == arrays.NUMPY else [arrays.from_device(losses[i].clone(), fam) for i in range(4)]
             d = self.__dict__
@@ -134,7 +160,8 @@ class FasterRCNN(links.Link):
             # upload, the graph, ONE download of the whole result block; thread-safe (a plan per calling thread).
             import numpy as np
             xd = arrays.raw(x)
-            xd = xd if xd.dtype == np.float32 and xd.flags.c_contiguous else np.ascontiguousarray(xd, dtype=np.float32)
+            if xd.dtype != np.float32:
+                xd = xd.astype(np.float32)
             res, plan = self.engine().call_host(xd[0], img_info=(int(hw[0]), int(hw[1])), **kw)
             self.__dict__["rpn_proposals"] = res["rois"].copy()
             self.__dict__["rpn_probs"] = res["scores"].reshape(-1, 1).copy()

@@ -82,11 +82,14 @@ class ProposalLayer(object):
         _, H, W = pred_chw.shape
         if self._anchors_dev is None or self._anchors_dev.device != prob_chw.device:
             self._anchors_dev = torch.from_numpy(np.ascontiguousarray(self._anchors, dtype=np.float64)).to(prob_chw.device)
-        if self._pre_nms_top_n <= 0 or self._post_nms_top_n <= 0:
-            raise ops.FrcnnError("ProposalLayer: pre/post_nms_top_n must be positive in this build")
+        # the reference treats a limit <= 0 as "take all" (models/proposal_layer.py:164-165,189-190); the device pipeline
+        # sorts at most 16384 candidates and returns at most 2048 rows, so "all" maps to those limits
+        pre_n = self._pre_nms_top_n if self._pre_nms_top_n > 0 else min(A * H * W, 16384)
+        post_n = self._post_nms_top_n if self._post_nms_top_n > 0 else 2048
+        if A * H * W > 16384 and self._pre_nms_top_n <= 0:
+            raise ops.FrcnnError("ProposalLayer: 'no limit' pre_nms_top_n with %d anchors exceeds the device sort's 16384" % (A * H * W))
         self._work = ops.proposals(prob_chw, pred_chw, self._anchors_dev, A, H, W, self._feat_stride, im_h, im_w,
-                                   self._min_size, self._pre_nms_top_n, self._post_nms_top_n, self._nms_thresh,
-                                   layout="nchw", work=self._work)
+                                   self._min_size, pre_n, post_n, self._nms_thresh, layout="nchw", work=self._work)
         return self._work
 
     # -- kept for callers that ask for the explicit anchor grid (tests/test_anchor_target_layer.py:38)

@@ -61,7 +61,7 @@ class RegionProposalNetwork(links.Link):
 
     def _weights(self, device):
         packed, ver = self._packed
-        if packed is None or ver != self._version:
+        if packed is None or ver != self.version_key():
             T = lambda a: torch.from_numpy(a).to(device)
             hi3, lo3 = ops.pack_conv_weights(T(self.rpn_conv_3x3.W.data), precision=self.precision)
             b3 = ops.pad_bias(T(self.rpn_conv_3x3.b.data), self.rpn_conv_3x3.b.data.size)
@@ -70,7 +70,7 @@ class RegionProposalNetwork(links.Link):
             ld = ops.round_up(wh.shape[0], 32)
             hih, loh = ops.pack_conv_weights(wh, precision=self.precision)
             packed = dict(c3=(hi3, lo3, b3), heads=(hih, loh, ops.pad_bias(bh, ld)), ld=ld)
-            self.__dict__["_packed"] = (packed, self._version)
+            self.__dict__["_packed"] = (packed, self.version_key())
         return packed
 
     def forward_device(self, feat, im_h, im_w):

@@ -76,8 +76,8 @@ class ResNet(links.Link):
         """(3,H,W) CUDA float32 -> ops.Act [h,w,2048] through a trunk-only plan (no RPN / head weights needed)."""
         from frcnn_b200 import resnet_engine as re_
         pk, ver = self._engine
-        if pk is None or ver != self._version:
+        if pk is None or ver != self.version_key():
             params = {"trunk/" + k.lstrip("/"): p.data for k, p in self.namedparams()}
             pk = re_.TrunkOnly(params, self.n_layers, self.precision, x_chw.device)
-            self.__dict__["_engine"] = (pk, self._version)
+            self.__dict__["_engine"] = (pk, self.version_key())
         return pk.run(x_chw)

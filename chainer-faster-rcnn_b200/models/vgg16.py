@@ -36,7 +36,7 @@ class VGG16Prev(links.Link):
 
     def _weights(self, device):
         packed, ver = self._packed
-        if packed is None or ver != self._version:
+        if packed is None or ver != self.version_key():
             packed = {}
             for item in _PLAN:
                 if item is None:
@@ -49,7 +49,7 @@ class VGG16Prev(links.Link):
                 else:
                     hi, lo = ops.pack_conv_weights(w, cin_pad=cin, precision=self.precision)
                 packed[name] = (hi, lo, ops.pad_bias(torch.from_numpy(l.b.data).to(device), l.b.data.size))
-            self.__dict__["_packed"] = (packed, self._version)
+            self.__dict__["_packed"] = (packed, self.version_key())
         return packed
 
     def forward_device(self, x_chw):

@@ -157,6 +157,11 @@ int frcnn_preprocess_bgr8(const unsigned char* img_hwc, int h0, int w0, double m
  * OIHW (Cout,Cin<=3,3,3) -> [1,Cout,32].  conv1_1 (models/vgg16.py:39) is then frcnn_conv2d with ksize = 1,
  * Cin = 32: one 64-byte-row k-block per pixel tile instead of nine 32-byte-row blocks. */
 int frcnn_pack_image_im2col3x3(const float* x_chw, int C, int H, int W, void* y_hi, void* y_lo, void* stream);
+/* Same with an explicit source layout: element (c, h, w) is x[c*stride_c + h*stride_h + w*stride_w] (in floats).
+ * (H*W, W, 1) = dense (C,H,W); (1, W*C, C) = dense (H,W,C) memory, which is what forward.py:45's
+ * `img.transpose([2, 0, 1]).astype(np.float32)` hands to the model (astype keeps the transposed strides). */
+int frcnn_pack_image_im2col3x3_strided(const float* x, int C, int H, int W, long stride_c, long stride_h, long stride_w,
+                                       void* y_hi, void* y_lo, void* stream);
 int frcnn_pack_conv_weights_im2col3x3(const float* w_oihw, int Cout, int Cin, void* w_hi, void* w_lo, void* stream);
 /* [H,W,C] bf16 hi(/lo) -> (C,H,W) fp32 (the reference's feature-map layout); for inspection/tests. */
 int frcnn_unpack_nhwc(const void* x_hi, const void* x_lo, int H, int W, int C, float* y_chw, void* stream);
@@ -407,6 +412,13 @@ int frcnn_bias_grad(const void* t_hi, const void* t_lo, int C, long Kp, float sc
 /* chainer.optimizer.WeightDecay(rate) hook + optimizers.MomentumSGD(lr, momentum) (train_rpn.py:165-167) on float32
  * master weights: g' = g + rate*w; v = momentum*v - lr*g'; w += v. */
 int frcnn_sgd_momentum(float* w, float* v, const float* g, long n, float lr, float momentum, float weight_decay, void* stream);
+
+/* bf16 gradient bucket for the multi-GPU step (train_rpn.py:169-174 ParallelUpdater; BASELINE config #5 "bf16, NCCL grad
+ * allreduce"): frcnn_cast_f32_bf16 rounds a bucket of fp32 gradients to bf16 for the all-reduce (src 16-byte, dst 8-byte
+ * aligned), frcnn_sgd_momentum_bf16g is frcnn_sgd_momentum reading the reduced bf16 gradient (fp32 masters / momentum). */
+int frcnn_cast_f32_bf16(const float* src, void* dst_bf16, long n, void* stream);
+int frcnn_sgd_momentum_bf16g(float* w, float* v, const void* g_bf16, long n, float lr, float momentum, float weight_decay,
+                             void* stream);
 
 /* Weights of the data-gradient convolution: out[t][ci][co] = W[co][ci][kh-1-r][kw-1-s] (t = r*kw+s), bf16 hi/lo, co
  * zero-padded to Cout_pad -- feed to frcnn_conv2d with Cin := Cout_pad, Cout := Cin. */
