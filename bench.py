@@ -227,7 +227,13 @@ def conv_layer_table(plan, torch, reps=3, spin=True):
         Cout = w_hi.shape[1]
         return bracket(lambda: orig_lin(x, w_hi, w_lo, bias, relu, **kw), 2.0 * R * Cout * K / 1e9,
                        "linear %dx%d->%d" % (R, K, Cout))
-    ops.conv2d, ops.linear = timed_conv, timed_lin
+    orig_c8 = ops.conv3x3_c8
+
+    def timed_c8(x_c8, H, W, w_hi, w_lo, bias, relu=True, out=None):
+        Cout = w_hi.shape[1]
+        return bracket(lambda: orig_c8(x_c8, H, W, w_hi, w_lo, bias, relu, out=out), 2.0 * H * W * Cout * 27 / 1e9,
+                       "%dx%dx3->%d k3 (compact image, K=3x32)" % (H, W, Cout))
+    ops.conv2d, ops.linear, ops.conv3x3_c8 = timed_conv, timed_lin, timed_c8
     acc = {}
     try:
         for _ in range(reps):
@@ -237,7 +243,7 @@ def conv_layer_table(plan, torch, reps=3, spin=True):
             for i, (ev, gf, name) in enumerate(rows):
                 acc.setdefault(i, [name, gf, []])[2].append(ev[0].elapsed_time(ev[1]))
     finally:
-        ops.conv2d, ops.linear = orig_conv, orig_lin
+        ops.conv2d, ops.linear, ops.conv3x3_c8 = orig_conv, orig_lin, orig_c8
     return [(v[0], min(v[2]), v[1]) for _, v in sorted(acc.items())]
 
 
@@ -320,6 +326,9 @@ def run_b200_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     anchors = orc.generate_anchors(ratios=(0.5, 1, 2), scales=(8, 16, 32))
     params = orc.make_params(seed=1234)
+    if args.smem_reserve_kb:
+        from frcnn_b200 import ops as _o
+        _o.set_conv_smem_reserve(1024 * args.smem_reserve_kb)
     # the whole north_star path: the caller's per-class NMS (forward.py:48-57, thresholds of :75-76) runs inside the graph
     eng = Engine(params, precision=args.precision, anchors=anchors, use_graph=True, with_detect=True,
                  det_nms_thresh=0.3, det_conf=0.8)
@@ -407,6 +416,13 @@ def run_b200_arm(args, rank, local_rank, world):
             seed_rates[str(sd)] = {"images_per_s": 20e3 / e0.elapsed_time(e1), "proposals": int(plan.prop.count.item())}
     barrier()
 
+    # The e2e legs run Python per image.  A full (generation-2) garbage collection in a process that has imported torch walks
+    # ~1M objects and takes 70-80 ms (measured: the "periodic stall" of round 1 and the 81 ms outliers of
+    # profiles/r02_host_api_profile.txt); a serving process moves its start-up objects out of the collector's way once.
+    import gc
+    gc.collect()
+    gc.freeze()
+
     # ---------------- e2e (1): the public streaming call -- host image in, host result out, every step
     runner = StreamRunner(pool)
     seq = [imgs_host[i % n_img] for i in range(args.steps)]
@@ -438,6 +454,20 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---------------- e2e (2): the REFERENCE's interface -- models.faster_rcnn.FasterRCNN.__call__ fed a host float32
     # (1,3,600,1000) chainer.Variable + img_info, then the caller's 20 models.cpu_nms.cpu_nms calls (forward.py:88-99,48-57)
     import threading
+
+    def cgroup_cpu():
+        out = {}
+        for name in ("cpu.max", "cpu.stat"):
+            try:
+                with open("/sys/fs/cgroup/" + name) as f:
+                    out[name] = f.read().split()
+            except OSError:
+                pass
+        st = out.get("cpu.stat", [])
+        d = {st[i]: int(st[i + 1]) for i in range(0, len(st) - 1, 2) if st[i + 1].isdigit()}
+        return {"cpu_max": " ".join(out.get("cpu.max", [])) or None, "nr_throttled": d.get("nr_throttled"),
+                "throttled_usec": d.get("throttled_usec")}
+    cg0 = cgroup_cpu()
     model = build_reference_api_model(params)
     model.precision = args.precision
     from chainer import Variable
@@ -447,10 +477,23 @@ def run_b200_arm(args, rank, local_rank, world):
     for i in range(3):
         reference_api_image(model, x_vars[i % n_img], info_var, ref_nms, np)
     barrier()
+    from frcnn_b200 import engine as _engine_mod
+    _engine_mod.HOST_PROFILE = []
+    per_image = []
     t0 = time.perf_counter()
     for i in range(args.steps):
+        ta = time.perf_counter()
         r_api = reference_api_image(model, x_vars[i % n_img], info_var, ref_nms, np)
+        per_image.append(1e3 * (time.perf_counter() - ta))
     t_api = time.perf_counter() - t0
+    phases = np.array(_engine_mod.HOST_PROFILE)
+    _engine_mod.HOST_PROFILE = None
+    per_image = np.array(per_image)
+    api_phases = {"upload_pageable_to_device_ms_median": float(np.median(phases[:, 1])),
+                  "graph_replay_enqueue_ms_median": float(np.median(phases[:, 2])), "d2h_and_wait_ms_median": float(np.median(phases[:, 3])),
+                  "forward_host_ms_mean": float(phases.sum(1).mean()), "forward_host_ms_max": float(phases.sum(1).max()),
+                  "per_image_ms_median": float(np.median(per_image)), "per_image_ms_mean": float(per_image.mean()),
+                  "per_image_ms_p90": float(np.percentile(per_image, 90)), "per_image_ms_max": float(per_image.max())}
     api_serial = world * args.steps / shard.max_over_ranks(t_api, device="cuda")
     # the model call alone (no caller NMS), serial: where the time of the serial number goes
     t0 = time.perf_counter()
@@ -466,6 +509,8 @@ def run_b200_arm(args, rank, local_rank, world):
     def worker(k, n_local, sync):
         try:
             torch.cuda.set_device(local_rank)
+            if args.smem_reserve_kb:
+                _ops.set_conv_smem_reserve(1024 * args.smem_reserve_kb)
             for i in range(2):
                 reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)     # per-thread plan + graph
             sync.wait()
@@ -493,6 +538,12 @@ def run_b200_arm(args, rank, local_rank, world):
         raise RuntimeError("reference-API worker failed: %s" % errs[0])
     api_threads = world * args.steps / shard.max_over_ranks(t_thr, device="cuda")
     link = host_link_probe(torch) if rank == 0 else None
+    cg1 = cgroup_cpu()
+    cgroup = {"cpu_max": cg1["cpu_max"],
+              "throttled_periods_during_api_legs": None if cg1["nr_throttled"] is None or cg0["nr_throttled"] is None
+              else cg1["nr_throttled"] - cg0["nr_throttled"],
+              "throttled_ms_during_api_legs": None if cg1["throttled_usec"] is None or cg0["throttled_usec"] is None
+              else (cg1["throttled_usec"] - cg0["throttled_usec"]) / 1e3}
 
     if rank != 0:
         if world > 1:
@@ -508,7 +559,7 @@ def run_b200_arm(args, rank, local_rank, world):
     peak_sus = pk.get("bf16_tflops_sustained", 1421.6)
     peak_hbm = pk.get("hbm_gbs", 6571.9)
     peak_src = "MEASURED_PEAKS.json" if pk else "fallback (B200_PROFILING.md)"
-    conv_rows = [r for r in table if " k3" in r[0] or "->64 k1" in r[0]]   # trunk + RPN convs (3x3, conv1_1, the twin 1x1)
+    conv_rows = [r for r in table if " k3" in r[0] or "->64 k1" in r[0]]   # trunk + RPN convs (3x3 incl. conv1_1, the twin 1x1)
     conv_ms = sum(r[1] for r in conv_rows)
     all_ms = sum(r[1] for r in table)
     exec_mult = 3.0 if args.precision == "bf16x3" else 1.0
@@ -587,7 +638,7 @@ def run_b200_arm(args, rank, local_rank, world):
                 "mode": "models.faster_rcnn.FasterRCNN.__call__(Variable float32 (1,3,600,1000) HOST, img_info) + 20 x "
                         "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads" % T,
                 "reference_api_one_thread": {"value": api_serial, "unit": "images/s", "ms_per_image": 1e3 / (api_serial / world),
-                                             "model_call_only_ms": api_model_only_ms, "last": list(r_api)},
+                                             "model_call_only_ms": api_model_only_ms, "last": list(r_api), "phases": api_phases},
                 "reference_api_threads": T,
                 "stream_runner_raw_uint8": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
                                             "d2h_bytes_per_step": runner8.d2h_bytes,
@@ -596,7 +647,7 @@ def run_b200_arm(args, rank, local_rank, world):
                                                     "NMS + one D2H of (prob, boxes, proposals, keep lists), ring of %d slots" % runner8.depth},
                 "stream_runner_float32": {"value": e2e_f32_val, "unit": "images/s", "h2d_bytes_per_step": runner.h2d_bytes,
                                           "d2h_bytes_per_step": runner.d2h_bytes},
-                "host_link": link},
+                "host_link": link, "host_cgroup_cpu": cgroup},
         "gpu_launches": plan.n_launches * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -817,6 +868,8 @@ def main():
     ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="train_rpn workload: dtype of the all-reduced gradient bucket (BASELINE config #5 says bf16)")
     ap.add_argument("--no-overlap", action="store_true", help="train_rpn workload: one all-reduce after backward instead of bucket overlap")
+    ap.add_argument("--smem-reserve-kb", type=int, default=0,
+                    help="shared memory per SM the conv kernels leave to other streams' small kernels (tuning experiment)")
     ap.add_argument("--api-threads", type=int, default=4, help="caller threads of the reference-interface e2e leg")
     ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")

@@ -40,6 +40,7 @@ namespace frcnn {
 struct ConvParams {
     int H, W, Cout;
     int taps, ksize, cin_blocks;
+    int kw, pad_h, pad_w;                // tap -> (r, s) = (tap / kw, tap % kw); A box origin (w0 + s - pad_w, h0 + r - pad_h)
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
     int num_stages, a_stages, x3, relu, pool;
     int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
@@ -214,7 +215,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     grid_dep_wait();
 
     const int num_kb = p.taps * p.cin_blocks;
-    const int pad = (p.ksize - 1) / 2;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -257,15 +257,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const int tap = kb / p.cin_blocks;
                     const int btap = bplane >= 0 ? bplane : tap;
                     const int cb = kb - tap * p.cin_blocks;
-                    const int r = tap / p.ksize, s = tap - r * p.ksize;
+                    const int r = tap / p.kw, s = tap - r * p.kw;
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = ring + (size_t)stage * stage_bytes;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * CG));
-                    tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], ka + cb * BK, w0 + s - pad, h0 + r - pad);
+                    tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], ka + cb * BK, w0 + s - p.pad_w, h0 + r - p.pad_h);
                     tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], kboff + cb * BK, n0, btap);
                     if (p.x3) {
                         uint8_t* st2 = st + C::A_BYTES + C::B_BYTES;
-                        tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], ka + cb * BK, w0 + s - pad, h0 + r - pad);
+                        tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], ka + cb * BK, w0 + s - p.pad_w, h0 + r - p.pad_h);
                         tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], kboff + cb * BK, n0, btap);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -566,8 +566,11 @@ static TmapCache* tmap_cache() {
 }
 
 static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
-                        uint32_t b1, uint32_t b2) {
-    const TmapKey key{base, d0, d1, d2, b0, b1, b2};
+                        uint32_t b1, uint32_t b2, uint64_t stride1_bytes = 0, uint64_t stride2_bytes = 0) {
+    // stride1_bytes / stride2_bytes != 0: explicit byte strides of dimensions 1 and 2 (a SLIDING-WINDOW map when stride1 is
+    // smaller than the dimension-0 extent: neighbouring "rows" overlap in memory -- verified on B200 by
+    // tests/experiments/tma_overlap_probe.cu); the cache key folds them into d1 / d2's upper bits
+    const TmapKey key{base, d0, d1 | (stride1_bytes << 32), d2 | (stride2_bytes << 32), b0, b1, b2};
     uint64_t hsh = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull;
     hsh ^= (d0 * 31 + d1) * 0xC2B2AE3D27D4EB4Full + d2 * 0x165667B19E3779F9ull + b0 * 131 + b1 * 17 + b2;
     const int slot = (int)((hsh >> 20) % kTmapCacheSlots);
@@ -582,7 +585,7 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
         return FRCNN_ERR_CUDA;
     }
     cuuint64_t dims[3] = {d0, d1, d2};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint64_t strides[2] = {stride1_bytes ? stride1_bytes : d0 * 2, stride2_bytes ? stride2_bytes : d0 * d1 * 2};
     cuuint32_t box[3] = {b0, b1, b2};
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMapSwizzle sw = (b0 * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -603,7 +606,7 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
 
 // Tuning overrides (frcnn_conv2d_set_*): per calling thread, read when a launch is enqueued (and therefore fixed inside
 // a captured graph) -- two engines driven from different threads cannot disturb each other.
-static thread_local int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0;
+static thread_local int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0, g_smem_reserve = 0;
 
 static int device_sm_count() {
     static int sms = 0;
@@ -622,13 +625,17 @@ static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream)
     const int planes = p.x3 ? 2 : 1;
     const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
     const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0);
+    // shared-memory budget of the persistent CTA: everything by default; frcnn_conv2d_set_smem_reserve leaves a slice of
+    // every SM to other kernels, so that the small kernels of ANOTHER image in flight (decode, NMS, RoI pooling, a host
+    // caller's per-class NMS) can become resident next to a convolution instead of waiting for one of its CTAs to retire
+    const int smem_budget = 227 * 1024 - g_smem_reserve;
     int a_stages = 0, a_bytes = 0;
     if (HALO) {
         // two halo slots when at least 3 weight slots still fit, else one
-        a_stages = ((227 * 1024 - fixed - 2 * planes * kHaloBytes) / stage_bytes >= 3) ? 2 : 1;
+        a_stages = ((smem_budget - fixed - 2 * planes * kHaloBytes) / stage_bytes >= 3) ? 2 : 1;
         a_bytes = a_stages * planes * kHaloBytes;
     }
-    int stages = (227 * 1024 - fixed - a_bytes) / stage_bytes;
+    int stages = (smem_budget - fixed - a_bytes) / stage_bytes;
     if (stages > 20) stages = 20;
     if (stages < 2) {
         set_error("conv tile BN=%d BK=%d halo=%d does not fit 2 pipeline stages", BN, BK, (int)HALO);
@@ -696,6 +703,8 @@ extern "C" void frcnn_conv2d_set_cta_group(int cta_group) { g_force_cg = cta_gro
 
 extern "C" void frcnn_conv2d_set_max_ctas(int max_ctas) { g_max_ctas = max_ctas; }
 
+extern "C" void frcnn_conv2d_set_smem_reserve(int bytes) { g_smem_reserve = bytes < 0 ? 0 : (bytes > 96 * 1024 ? 96 * 1024 : bytes); }
+
 extern "C" void frcnn_conv2d_set_tile(int block_n, int tile_h, int tile_w) {
     g_force_bn = block_n;
     g_force_th = tile_h;
@@ -712,12 +721,15 @@ struct GemmExtra {          // split-K GEMM mode of the same kernel (frcnn_gemm_
 struct ResExtra {           // residual input of frcnn_conv2d_res
     const void *hi, *lo;
 };
+struct WinExtra {           // frcnn_conv3x3_c8: 3x3 convolution over a compact [H][W+2][8] image through a sliding-window map
+    int row_pixels;         // pixels per stored row (W + 2: one zero column on each side)
+};
 }  // namespace
 
 static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin, const void* w_hi,
                        const void* w_lo, const float* bias, int Cout, int ksize, int relu, int fuse_pool2x2,
                        void* y_hi, void* y_lo, float* y_f32, int ld_f32, const int* m_valid, void* stream_,
-                       const GemmExtra* ge, const ResExtra* re = nullptr) {
+                       const GemmExtra* ge, const ResExtra* re = nullptr, const WinExtra* we = nullptr) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     FRCNN_REQUIRE(x_hi && w_hi && (bias || ge), "frcnn_conv2d: x_hi, w_hi and bias are required");
     FRCNN_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "frcnn_conv2d: x_lo and w_lo must both be given (bf16x3) or both NULL");
@@ -739,7 +751,7 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     int TH = 8, TW = 16;
     const bool forced_tile = g_force_th > 0 && g_force_tw > 0 && g_force_th * g_force_tw == kTileM;
     // HALO (shared halo patch for the 9 taps) needs the 16x8 tile; a forced other tile selects the per-tap path
-    const bool halo = ksize == 3 && BK == 64 && (!forced_tile || (g_force_th == kHaloTH && g_force_tw == kHaloTW));
+    const bool halo = ksize == 3 && BK == 64 && !we && (!forced_tile || (g_force_th == kHaloTH && g_force_tw == kHaloTW));
     if (halo) {
         TH = kHaloTH;
         TW = kHaloTW;
@@ -789,6 +801,13 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     ConvParams p;
     p.H = H; p.W = W; p.Cout = Cout;
     p.ksize = ksize; p.taps = ksize * ksize; p.cin_blocks = cdiv(Cin, BK);
+    p.kw = ksize; p.pad_h = p.pad_w = (ksize - 1) / 2;
+    if (we != nullptr) {
+        // K = 3 image rows x (4 pixels x 8 channels): one k-block of 32 per row r, its A box starting at stored pixel w0 of row
+        // h0 + r - 1 (the left zero column is stored, rows -1 and H are the TMA unit's out-of-bounds zero fill)
+        FRCNN_REQUIRE(Cin == 32 && ksize == 3 && !fuse_pool2x2 && !m_valid && !ge && !re, "conv3x3_c8: bad configuration");
+        p.taps = 3; p.kw = 1; p.pad_h = 1; p.pad_w = 0;
+    }
     p.TH = TH; p.TW = TW; p.tiles_h = tiles_h; p.tiles_w = tiles_w;
     p.n_tiles = cdiv(cout_cover, BN);
     // CTA pairs (cta_group::2) for the wide-N tiles of layers with at least two pixel tiles
@@ -832,11 +851,12 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     CUtensorMap tm[6];
     int rc;
     const int abw = halo ? kHaloW : TW, abh = halo ? kHaloH : TH;     // A box: the tile, or the tile + 1-pixel halo
-    if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
+    const uint64_t as1 = we ? 16 : 0, as2 = we ? (uint64_t)we->row_pixels * 16 : 0;     // sliding window: one pixel (8 ch) per step
+    if ((rc = make_tmap_3d(&tm[0], x_hi, Cin, W, H, BK, abw, abh, as1, as2)) != FRCNN_OK) return rc;
     const int b_planes = (ge != nullptr && ge->groups == 9) ? 3 : p.taps;
     if ((rc = make_tmap_3d(&tm[2], w_hi, Cin, Cout, b_planes, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     if (p.x3) {
-        if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, abw, abh)) != FRCNN_OK) return rc;
+        if ((rc = make_tmap_3d(&tm[1], x_lo, Cin, W, H, BK, abw, abh, as1, as2)) != FRCNN_OK) return rc;
         if ((rc = make_tmap_3d(&tm[3], w_lo, Cin, Cout, b_planes, BK, BN / CG, 1)) != FRCNN_OK) return rc;
     } else {
         tm[1] = tm[0];
@@ -897,6 +917,14 @@ extern "C" int frcnn_conv2d_res(const void* x_hi, const void* x_lo, int H, int W
     ResExtra re{res_hi, res_lo};
     return conv2d_impl(x_hi, x_lo, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, relu, 0, y_hi, y_lo, nullptr, 0, nullptr, stream_,
                        nullptr, &re);
+}
+
+extern "C" int frcnn_conv3x3_c8(const void* x_hi, const void* x_lo, int H, int W, const void* w_hi, const void* w_lo,
+                                const float* bias, int Cout, int relu, void* y_hi, void* y_lo, void* stream_) {
+    FRCNN_ENTRY();
+    WinExtra we{W + 2};
+    return conv2d_impl(x_hi, x_lo, H, W, 32, w_hi, w_lo, bias, Cout, 3, relu, 0, y_hi, y_lo, nullptr, 0, nullptr, stream_, nullptr,
+                       nullptr, &we);
 }
 
 extern "C" int frcnn_gemm_nt_splitk_splits(int K, int splits) {

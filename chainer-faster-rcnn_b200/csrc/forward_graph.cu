@@ -48,7 +48,7 @@ int round32(int v) { return (v + 31) / 32 * 32; }
 Layout carve(const frcnn_forward_config& c, void* workspace) {
     Layout L;
     Carver k{(char*)workspace, 0, c.x3 != 0};
-    L.x_col = k.act((long)c.H * c.W * 32);
+    L.x_col = k.act((long)frcnn_image_c8_elems(c.H, c.W));          // compact first-layer input [H][W+2][8]
     int h = c.H, w = c.W;
     for (int i = 0; i < 13; ++i) {
         if (kVgg[i][2]) { h = (h + 1) / 2; w = (w + 1) / 2; }          // the pool is fused into this conv's epilogue
@@ -111,14 +111,18 @@ int frcnn_forward_vgg16(const frcnn_forward_config* config, const frcnn_vgg16_we
     const bool x3 = c.x3 != 0;
     for (int i = 0; i < 13; ++i)
         FRCNN_REQUIRE(wts->conv[i].hi && wts->conv[i].bias && (!x3 || wts->conv[i].lo), "frcnn_forward: trunk layer %d weights missing", i);
-    // ---- trunk: conv1_1 as a K = 32 GEMM over the im2col-packed image, then 12 shared-halo 3x3 convolutions
-    if ((rc = frcnn_pack_image_im2col3x3(image_chw, 3, c.H, c.W, L.x_col.hi, L.x_col.lo, stream)) != FRCNN_OK) return rc;
+    // ---- trunk: conv1_1 as a K = 3 x 32 GEMM over the compact image (sliding-window tensor map), then 12 shared-halo 3x3 convs
+    if ((rc = frcnn_pack_image_c8(image_chw, 3, c.H, c.W, (long)c.H * c.W, c.W, 1, L.x_col.hi, L.x_col.lo, stream)) != FRCNN_OK) return rc;
     Plane x = L.x_col;
     int h = c.H, w = c.W, cin = 32;
     for (int i = 0; i < 13; ++i) {
         const frcnn_packed_layer& l = wts->conv[i];
-        if ((rc = frcnn_conv2d(x.hi, x.lo, h, w, cin, l.hi, l.lo, l.bias, kVgg[i][1], i == 0 ? 1 : 3, 1, kVgg[i][2], L.act[i].hi,
-                               L.act[i].lo, nullptr, 0, nullptr, stream)) != FRCNN_OK) return rc;
+        if (i == 0)
+            rc = frcnn_conv3x3_c8(x.hi, x.lo, h, w, l.hi, l.lo, l.bias, kVgg[0][1], 1, L.act[0].hi, L.act[0].lo, stream);
+        else
+            rc = frcnn_conv2d(x.hi, x.lo, h, w, cin, l.hi, l.lo, l.bias, kVgg[i][1], 3, 1, kVgg[i][2], L.act[i].hi, L.act[i].lo, nullptr,
+                              0, nullptr, stream);
+        if (rc != FRCNN_OK) return rc;
         if (kVgg[i][2]) { h = (h + 1) / 2; w = (w + 1) / 2; }
         x = L.act[i];
         cin = kVgg[i][1];

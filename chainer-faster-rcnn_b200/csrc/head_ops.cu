@@ -150,6 +150,44 @@ __global__ void pack_image_im2col_kernel(const float* x, int C, int H, int W, lo
     }
 }
 
+// Compact first-layer input: (C<=3,H,W) fp32 (any strides) -> [H][W+2][8] bf16 hi/lo: 8 channels per pixel (3 used), one
+// zero pixel left and right of every row.  conv1_1 (models/vgg16.py:39) then reads, for output pixel (h, w) and kernel row
+// r, the 32 contiguous values of stored pixels w .. w+3 of row h+r-1 through a SLIDING-WINDOW tensor map (frcnn_conv3x3_c8):
+// 19 MB written here instead of the 77 MB of the [H][W][32] im2col copy, and nothing re-read from HBM four times.
+__global__ void pack_image_c8_kernel(const float* x, int C, int H, int W, long sc, long sh, long sw, __nv_bfloat16* hi,
+                                     __nv_bfloat16* lo, long slack_pixels) {
+    const int WP = W + 2;
+    const long total = (long)H * WP + slack_pixels;
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < total; p += (long)gridDim.x * blockDim.x) {
+        F8 f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f.v[j] = 0.0f;
+        if (p < (long)H * WP) {
+            const int h = (int)(p / WP), wp = (int)(p % WP);
+            if (wp >= 1 && wp <= W) {
+                const long o = h * sh + (long)(wp - 1) * sw;
+                for (int c = 0; c < C; ++c) f.v[c] = x[c * sc + o];
+            }
+        }
+        store8(hi, lo, p * 8, f);
+    }
+}
+
+// conv1_1 weights for frcnn_conv3x3_c8: OIHW (Cout, Cin<=3, 3, 3) -> [3 (kernel row r)][Cout][32], k = dx*8 + c holds
+// W[co][c][r][dx] for dx < 3, c < Cin, zero elsewhere (the 4th pixel of the window and channels 3..7 multiply zeros).
+__global__ void pack_weights_c8_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * Cout * 32) return;
+    const int k = t % 32, co = (t / 32) % Cout, r = t / (32 * Cout);
+    const int dx = k / 8, c = k % 8;
+    float v = 0.0f;
+    if (dx < 3 && c < Cin) v = w[((co * Cin + c) * 3 + r) * 3 + dx];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[t] = h;
+    if (lo) lo[t] = l;
+}
+
 // Caller-side preprocessing (forward.py:34-45, img_preprocessing): uint8 BGR HWC image -> float32(pixel - mean)
 // -> cv.resize(INTER_LINEAR) -> (3,H,W) float32.  One thread per output pixel, all three channels.  OpenCV's
 // float bilinear, restated: coordinate / floor / fraction in double, weight cast to float,
@@ -383,16 +421,37 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, 
         sbox[rank] = reinterpret_cast<const float4*>(boxes)[(long)r * NC + cls];
     }
     __syncthreads();
-    // mask rows: item = (row i, word w) with w >= i/64 (upper triangle); 64 IoUs per item
+    // mask rows: item = (word w, row i) with w >= i/64 (upper triangle), i fastest: the lanes of a warp work on consecutive
+    // rows i against the SAME 64 columns, so sbox[j] is a broadcast read and sbox[i] a conflict-free one (with w fastest the
+    // lanes read 5 different boxes 1 KB apart = the same banks: measured 4x slower).  The decision "iou >= thr" is taken
+    // with products wherever that is provably the same decision as the reference's divide + double compare
+    // (models/cpu_nms.pyx:64-65); only within 1e-5 of the threshold the exact sequence runs (as in nms_mask_kernel).
     const int nw = (R + 63) >> 6;
+    const float thr_f = (float)thr;
+    const float thr_lo = thr_f * (1.0f - 1e-5f), thr_hi = thr_f * (1.0f + 1e-5f);
+    const bool fast_ok = thr_f > 1e-3f;
     for (int it = tid; it < R * nw; it += kDetThreads) {
-        const int i = it / nw, w = it - i * nw;
+        const int w = it / R, i = it - w * R;
         unsigned long long bits = 0ull;
         if (w >= (i >> 6)) {
             const float4 a = sbox[i];
+            const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
             const int j0 = w << 6, j1 = min(R, j0 + 64);
-            for (int j = max(j0, i + 1); j < j1; ++j)
-                if ((double)det_iou(a, sbox[j]) >= thr) bits |= 1ull << (j - j0);
+            for (int j = max(j0, i + 1); j < j1; ++j) {
+                const float4 b = sbox[j];
+                const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+                const float ww = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+                const float hh = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+                const float inter = __fmul_rn(ww, hh);
+                if (fast_ok && inter == 0.0f) continue;
+                const float area_b = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+                const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+                bool sup;
+                if (fast_ok && uni > 0.0f && inter > thr_hi * uni) sup = true;
+                else if (fast_ok && uni > 0.0f && inter < thr_lo * uni) sup = false;
+                else sup = (double)__fdiv_rn(inter, uni) >= thr;
+                if (sup) bits |= 1ull << (j - j0);
+            }
         }
         mask[(size_t)i * words + w] = bits;
     }
@@ -540,6 +599,31 @@ extern "C" int frcnn_pack_image_im2col3x3_strided(const float* x, int C, int H, 
     FRCNN_REQUIRE(stride_c > 0 && stride_h > 0 && stride_w > 0, "frcnn_pack_image_im2col3x3_strided: strides must be positive");
     pack_image_im2col_kernel<<<grid_for((long)H * W, 128), 128, 0, (cudaStream_t)stream>>>(
         x, C, H, W, stride_c, stride_h, stride_w, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" size_t frcnn_image_c8_elems(int H, int W) {
+    return (H > 0 && W > 0) ? ((size_t)H * (W + 2) + 8) * 8 : 0;          // 8 slack pixels behind the last row, zeroed by the pack
+}
+
+extern "C" int frcnn_pack_image_c8(const float* x, int C, int H, int W, long stride_c, long stride_h, long stride_w, void* y_hi,
+                                   void* y_lo, void* stream) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(x && y_hi && C > 0 && C <= 3 && H > 0 && W > 0, "frcnn_pack_image_c8: needs 1 <= C <= 3 (got %d)", C);
+    FRCNN_REQUIRE(stride_c > 0 && stride_h > 0 && stride_w > 0, "frcnn_pack_image_c8: strides must be positive");
+    const long total = (long)H * (W + 2) + 8;
+    pack_image_c8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, C, H, W, stride_c, stride_h, stride_w,
+                                                                                (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, 8);
+    FRCNN_LAUNCH_OK();
+    return FRCNN_OK;
+}
+
+extern "C" int frcnn_pack_conv_weights_c8(const float* w_oihw, int Cout, int Cin, void* w_hi, void* w_lo, void* stream) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(w_oihw && w_hi && Cout > 0 && Cin > 0 && Cin <= 3, "frcnn_pack_conv_weights_c8: needs 1 <= Cin <= 3");
+    pack_weights_c8_kernel<<<cdiv(3 * Cout * 32, 128), 128, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, (__nv_bfloat16*)w_hi,
+                                                                                     (__nv_bfloat16*)w_lo);
     FRCNN_LAUNCH_OK();
     return FRCNN_OK;
 }

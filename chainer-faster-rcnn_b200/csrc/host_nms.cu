@@ -14,6 +14,10 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -87,15 +91,34 @@ __global__ void __launch_bounds__(kSmallThreads) nms_small_kernel(const float* _
         // the ranks with the `removed` words in registers: no block-wide barrier on the greedy chain
         const int nw = (n + 63) >> 6;
         unsigned long long* mask = reinterpret_cast<unsigned long long*>(dead + ((n + 15) & ~15));
+        // item = (word w, row i), i fastest: a warp's lanes test consecutive rows against the same 64 columns (broadcast reads of
+        // sbox[j], conflict-free reads of sbox[i]); product pre-test wherever it provably equals the exact decision
+        const float thr_lo = thr_f * (1.0f - 1e-5f), thr_hi = thr_f * (1.0f + 1e-5f);
+        const bool fast_ok = thr_f > 1e-3f;
         for (int it = tid; it < n * nw; it += kSmallThreads) {
-            const int i = it / nw, w = it - i * nw;
+            const int w = it / n, i = it - w * n;
             unsigned long long bits = 0ull;
             if (w >= (i >> 6)) {
                 const float4 a = sbox[i];
+                const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
                 const int j0 = w << 6, j1 = min(n, j0 + 64);
                 for (int j = max(j0, i + 1); j < j1; ++j) {
-                    const float ovr = hn_iou(a, sbox[j]);
-                    if (mode == FRCNN_NMS_GE_DOUBLE ? ((double)ovr >= thr_d) : (ovr > thr_f)) bits |= 1ull << (j - j0);
+                    const float4 b = sbox[j];
+                    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+                    const float ww = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+                    const float hh = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+                    const float inter = __fmul_rn(ww, hh);
+                    if (fast_ok && inter == 0.0f) continue;
+                    const float area_b = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+                    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+                    bool sup;
+                    if (fast_ok && uni > 0.0f && inter > thr_hi * uni) sup = true;
+                    else if (fast_ok && uni > 0.0f && inter < thr_lo * uni) sup = false;
+                    else {
+                        const float ovr = __fdiv_rn(inter, uni);
+                        sup = mode == FRCNN_NMS_GE_DOUBLE ? ((double)ovr >= thr_d) : (ovr > thr_f);
+                    }
+                    if (sup) bits |= 1ull << (j - j0);
                 }
             }
             mask[(size_t)i * nw + w] = bits;
@@ -103,19 +126,23 @@ __global__ void __launch_bounds__(kSmallThreads) nms_small_kernel(const float* _
         __syncthreads();
         if (tid < 32) {
             unsigned long long removed = 0ull;            // lane w: ranks [64w, 64w + 64)
+            int* s_keep = reinterpret_cast<int*>(rbox);   // rbox is dead: the keep list is collected in shared memory ...
             int nk = 0;
             for (int i = 0; i < n; ++i) {
                 const unsigned long long word = __shfl_sync(0xffffffffu, removed, i >> 6);
                 if ((word >> (i & 63)) & 1ull) continue;
-                if (tid == 0) out[2 + nk] = order[i];
+                if (tid == 0) s_keep[nk] = order[i];
                 ++nk;
                 if (tid < nw) removed |= mask[(size_t)i * nw + tid];
             }
-            if (tid == 0) {
-                out[1] = nk;
-                __threadfence_system();                // keep list + count visible to the host before the flag
-                out[0] = ticket;
-            }
+            __syncwarp();
+            // ... and leaves for the host in a few wide PCIe writes (one 4-byte system-memory store per kept box from a single
+            // lane was the most expensive part of this kernel)
+            for (int k = tid; k < nk; k += 32) out[2 + k] = s_keep[k];
+            if (tid == 0) out[1] = nk;
+            __threadfence_system();                        // keep list + count visible to the host before the flag
+            __syncwarp();
+            if (tid == 0) out[0] = ticket;
         }
         return;
     }
@@ -324,5 +351,88 @@ extern "C" int frcnn_memcpy_d2h_async(void* dst_host, const void* src_device, si
 extern "C" int frcnn_stream_synchronize(void* stream) {
     FRCNN_ENTRY();
     FRCNN_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return FRCNN_OK;
+}
+
+// Pageable -> pinned staging copy on a few host threads that SLEEP between jobs (condition variable, no spinning).  The
+// first version used the framework's parallel copy: 64 OpenMP workers that spin for milliseconds after every parallel
+// region; with one such region per image the process ran into ~70 ms stalls (CPU-quota throttling on the GPU boxes,
+// profiles/r02_host_api_profile.txt).  4 workers move the 7.2 MB image in ~0.15-0.2 ms and cost nothing when idle.
+namespace frcnn {
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool();          // leaked on purpose: worker threads must not be joined at exit
+        return *p;
+    }
+    void copy(char* dst, const char* src, size_t bytes) {
+        const int parts = kWorkers + 1;
+        const size_t chunk = ((bytes / parts) + 4095) & ~size_t(4095);
+        if (bytes < (1u << 20) || chunk == 0) { memcpy(dst, src, bytes); return; }
+        std::unique_lock<std::mutex> run(run_mu_);      // one job at a time (callers from several threads queue here)
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            dst_ = dst; src_ = src; bytes_ = bytes; chunk_ = chunk;
+            pending_ = kWorkers;
+            ++job_;
+        }
+        cv_.notify_all();
+        const size_t o = (size_t)kWorkers * chunk;       // the caller copies the last part itself
+        if (o < bytes) memcpy(dst + o, src + o, bytes - o);
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [&] { return pending_ == 0; });
+    }
+
+  private:
+    static constexpr int kWorkers = 3;
+    CopyPool() {
+        for (int i = 0; i < kWorkers; ++i) std::thread([this, i] { work(i); }).detach();
+    }
+    void work(int i) {
+        unsigned long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [&] { return job_ != seen; });
+            seen = job_;
+            char* d = dst_; const char* s = src_;
+            const size_t bytes = bytes_, chunk = chunk_;
+            g.unlock();
+            const size_t o = (size_t)i * chunk;
+            if (o < bytes) memcpy(d + o, s + o, o + chunk <= bytes ? chunk : bytes - o);
+            g.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_;
+    char* dst_ = nullptr; const char* src_ = nullptr;
+    size_t bytes_ = 0, chunk_ = 0;
+    int pending_ = 0;
+    unsigned long job_ = 0;
+};
+}  // namespace frcnn
+
+extern "C" int frcnn_host_copy(void* dst, const void* src, size_t bytes) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(dst && src, "frcnn_host_copy: NULL pointer");
+    frcnn::CopyPool::get().copy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+    return FRCNN_OK;
+}
+
+// Upload of a PAGEABLE host buffer through a pinned staging block, pipelined: chunk k is copied into the staging block by
+// the calling thread while chunk k-1 is already on the wire (cudaMemcpyAsync on `stream`), so the image costs
+// max(host memcpy, DMA) + one chunk instead of their sum -- and no helper thread is involved (the GPU boxes give the process
+// a 16-CPU quota; a thread pool that wakes for every image costs more than it saves there, profiles/r02_host_api_profile.txt).
+// `staging` must hold `bytes` (the whole image: the chunks of an image never share staging memory, so the host never waits).
+extern "C" int frcnn_upload_pageable(void* dst_device, const void* src_host, void* staging_pinned, size_t bytes, void* stream) {
+    FRCNN_ENTRY();
+    FRCNN_REQUIRE(dst_device && src_host && staging_pinned, "frcnn_upload_pageable: NULL pointer");
+    const size_t chunk = 1u << 20;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t n = bytes - o < chunk ? bytes - o : chunk;
+        memcpy(static_cast<char*>(staging_pinned) + o, static_cast<const char*>(src_host) + o, n);
+        FRCNN_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(dst_device) + o, static_cast<char*>(staging_pinned) + o, n,
+                                      cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    }
     return FRCNN_OK;
 }

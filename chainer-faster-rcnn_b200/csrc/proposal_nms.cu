@@ -379,25 +379,27 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
     const int nb = (n + 63) / 64;
     const int limit = a.max_keep > 0 ? a.max_keep : 0x7fffffff;
     for (int w = tid; w < a.col_blocks; w += blockDim.x) removed[w] = 0ull;
-    // Pre-load every row's DIAGONAL word (the bits inside its own 64-block) into shared memory: the serial
-    // walk below then has no global load on its critical path for the intra-block decisions.
-    unsigned long long* diag = removed + a.col_blocks;          // [n_cap] when a.diag_in_smem
-    if (a.diag_in_smem)
-        for (int r = tid; r < n; r += blockDim.x) diag[r] = a.mask[(long)r * a.col_blocks + (r >> 6)];
     if (tid == 0) s_total = 0;
+    // The diagonal words (the bits inside a row's own 64-block) of the block being resolved are held by warp 0 in
+    // registers -- lane holds rows `lane` and `lane + 32` -- and the NEXT block's are requested before the current block
+    // is resolved, so their L2 latency hides behind the resolve + fold of the current one.  (The first version copied all
+    // n diagonal words to shared memory up front: 6000 scattered loads = 9 us before the first block could start.)
+    unsigned long long nd0 = 0ull, nd1 = 0ull;
+    if (warp == 0 && nb > 0) {
+        const int rows0 = min(64, n);
+        if (lane < rows0) nd0 = a.mask[(long)lane * a.col_blocks];
+        if (lane + 32 < rows0) nd1 = a.mask[(long)(lane + 32) * a.col_blocks];
+    }
     __syncthreads();
 
     for (int blk = 0; blk < nb; ++blk) {
         if (warp == 0) {
             const int rows = min(64, n - blk * 64);
-            // diagonal words of this block's rows: lane holds rows `lane` and `lane+32`
-            unsigned long long d0 = 0ull, d1 = 0ull;
-            if (a.diag_in_smem) {
-                if (lane < rows) d0 = diag[blk * 64 + lane];
-                if (lane + 32 < rows) d1 = diag[blk * 64 + lane + 32];
-            } else {
-                if (lane < rows) d0 = a.mask[(long)(blk * 64 + lane) * a.col_blocks + blk];
-                if (lane + 32 < rows) d1 = a.mask[(long)(blk * 64 + lane + 32) * a.col_blocks + blk];
+            const unsigned long long d0 = nd0, d1 = nd1;
+            if (blk + 1 < nb) {                          // prefetch the next block's diagonal words
+                const int rn = min(64, n - (blk + 1) * 64);
+                nd0 = lane < rn ? a.mask[(long)((blk + 1) * 64 + lane) * a.col_blocks + blk + 1] : 0ull;
+                nd1 = lane + 32 < rn ? a.mask[(long)((blk + 1) * 64 + lane + 32) * a.col_blocks + blk + 1] : 0ull;
             }
             unsigned long long cand = ~removed[blk];
             if (rows < 64) cand &= (1ull << rows) - 1ull;
@@ -422,28 +424,30 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
         __syncthreads();
         const int nk = s_nk;
         if (s_total >= limit) break;
-        // fold the kept rows of this block into `removed` for the blocks still ahead
-        // Thread w owns word w; the kept rows are read 4 at a time with independent loads, so a block pays one
-        // L2 round trip per 4 kept rows instead of one per row (the first version chained every load through
-        // `acc |= ...`).
-        if (nk > 0) {
-            for (int w = blk + 1 + tid; w < nb; w += blockDim.x) {
-                unsigned long long acc = removed[w];
-                const unsigned long long* col = a.mask + (long)(blk * 64) * a.col_blocks + w;
-                int k = 0;
-                for (; k + 4 <= nk; k += 4) {
-                    const unsigned long long m0 = col[(long)s_keep[k] * a.col_blocks];
-                    const unsigned long long m1 = col[(long)s_keep[k + 1] * a.col_blocks];
-                    const unsigned long long m2 = col[(long)s_keep[k + 2] * a.col_blocks];
-                    const unsigned long long m3 = col[(long)s_keep[k + 3] * a.col_blocks];
-                    acc |= (m0 | m1) | (m2 | m3);
+        // Fold the kept rows of this block into `removed` for the blocks still ahead: nk x (nb - blk - 1) mask words, spread
+        // over ALL threads (item = (kept row, word)), 8 independent loads in flight per thread, OR-ed into shared memory
+        // with atomics.  (The first version gave each of the <= 93 words to one thread, which then chained up to 16 L2 round
+        // trips per block: 11 us of the 12 us a block cost.)
+        const int W = nb - blk - 1;
+        const int items = nk * W;
+        const unsigned long long* base = a.mask + (long)(blk * 64) * a.col_blocks + blk + 1;
+        for (int it0 = tid; it0 < items; it0 += 8 * 256) {
+            unsigned long long m[8];
+            int wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int it = it0 + u * 256;
+                m[u] = 0ull;
+                wv[u] = 0;
+                if (it < items) {
+                    const int k = it / W, w = it - k * W;
+                    wv[u] = w;
+                    m[u] = base[(long)s_keep[k] * a.col_blocks + w];
                 }
-                unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull;
-                if (k < nk) t0 = col[(long)s_keep[k] * a.col_blocks];
-                if (k + 1 < nk) t1 = col[(long)s_keep[k + 1] * a.col_blocks];
-                if (k + 2 < nk) t2 = col[(long)s_keep[k + 2] * a.col_blocks];
-                removed[w] = acc | t0 | t1 | t2;
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (m[u] != 0ull) atomicOr(&removed[blk + 1 + wv[u]], m[u]);
         }
         __syncthreads();
     }
@@ -548,10 +552,8 @@ static int run_sort_nms(const NmsWs& w, int n_all, int top_k, double thresh, int
     sc.keep_out = keep_out; sc.num_out = num_out;
     sc.sorted_boxes = w.sorted_boxes; sc.sorted_scores = w.sorted_scores;
     sc.out_rois = out_rois; sc.out_scores = out_scores; sc.out_cap = out_cap;
-    size_t scan_smem = sizeof(unsigned long long) * (size_t)w.col_blocks;
-    sc.diag_in_smem = (scan_smem + sizeof(unsigned long long) * (size_t)k_cap) <= 200 * 1024;
-    if (sc.diag_in_smem) scan_smem += sizeof(unsigned long long) * (size_t)k_cap;
-    FRCNN_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    const size_t scan_smem = sizeof(unsigned long long) * (size_t)w.col_blocks;
+    sc.diag_in_smem = 0;
     FRCNN_CUDA_OK(launch_pdl(nms_scan_kernel, dim3(1), dim3(256), scan_smem, stream, sc));
     return FRCNN_OK;
 }

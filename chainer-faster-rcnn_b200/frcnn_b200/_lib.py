@@ -41,18 +41,26 @@ SIGNATURES = {
     "frcnn_conv2d_set_tile": (None, [c_int, c_int, c_int]),
     "frcnn_conv2d_set_cta_group": (None, [c_int]),
     "frcnn_conv2d_set_max_ctas": (None, [c_int]),
+    "frcnn_conv2d_set_smem_reserve": (None, [c_int]),
     "frcnn_set_programmatic_launch": (None, [c_int]),
     "frcnn_host_alloc": (c_void_p, [c_size_t]),
     "frcnn_host_free": (c_int, [c_void_p]),
     "frcnn_memcpy_h2d_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_memcpy_d2h_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_stream_synchronize": (c_int, [c_void_p]),
+    "frcnn_host_copy": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "frcnn_upload_pageable": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_int, c_int, c_void_p]),
     "frcnn_pack_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_preprocess_bgr8": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_double, c_double, c_int, c_int,
                                       c_void_p, c_void_p]),
     "frcnn_pack_image_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_image_c8_elems": (c_size_t, [c_int, c_int]),
+    "frcnn_pack_image_c8": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p]),
+    "frcnn_pack_conv_weights_c8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frcnn_conv3x3_c8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
     "frcnn_pack_image_im2col3x3_strided": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_void_p, c_void_p, c_void_p]),
     "frcnn_pack_conv_weights_im2col3x3": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frcnn_unpack_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

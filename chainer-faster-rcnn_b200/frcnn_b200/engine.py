@@ -26,8 +26,12 @@ from . import ops
 from ._lib import FrcnnError
 
 import threading
+import time
 
 _CAPTURE_LOCK = threading.Lock()
+# diagnostic hook: a list that receives, per ForwardPlan.forward_host call, the host-side milliseconds of
+# (pageable->pinned copy, H2D enqueue, graph replay enqueue, D2H enqueue + wait for the result); None = off
+HOST_PROFILE = None
 
 VGG16_LAYERS = [
     ("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool",
@@ -79,8 +83,8 @@ class PackedWeights(object):
             name, cin, cout = item
             w = P("trunk/%s/W" % name)
             if cin <= 3:
-                # first layer as a K=32 GEMM over the im2col-packed image (ops.pack_image_im2col)
-                hi, lo = ops.pack_conv_weights_im2col(w, precision=self.precision)
+                # first layer as a K = 3 x 32 GEMM over the compact [H][W+2][8] image (ops.pack_image_c8 / conv3x3_c8)
+                hi, lo = ops.pack_conv_weights_c8(w, precision=self.precision)
                 b = P("trunk/%s/b" % name)
                 self.convs[name] = (hi, lo, ops.pad_bias(b, b.numel()))
             else:
@@ -164,7 +168,9 @@ class ForwardPlan(object):
     def _alloc_trunk(self, H, W):
         """VGG16 activations; returns the feature-map size.  (resnet_engine.ResNetForwardPlan overrides both trunk hooks.)"""
         act, fuse_pool = self._act, self.fuse_pool
-        self.acts = [act(H, W, 32)]          # im2col-packed image: 27 taps*channels + 5 zeros per pixel
+        n_c8 = ops._lib.load().frcnn_image_c8_elems(H, W)          # compact first-layer input: [H][W+2][8] (+ slack), flat planes
+        hi0 = torch.empty((n_c8,), dtype=torch.bfloat16, device=self.x_in.device)
+        self.acts = [ops.Act(hi0, torch.empty_like(hi0) if self.w.precision == "bf16x3" else None)]
         h, w_ = H, W
         self.trunk_steps = []          # (layer name, fuse the following 2x2 pool into the conv epilogue)
         for i, item in enumerate(VGG16_LAYERS):
@@ -189,13 +195,15 @@ class ForwardPlan(object):
         w = self.w
         n = 0
         x = self.acts[0]
-        ops.pack_image_im2col(self.x_in, out=x, hwc_memory=self.hwc_input)
+        ops.pack_image_c8(self.x_in, out=x, hwc_memory=self.hwc_input)
         n += 1
         i = 0
         for name, fused, pool_after in self.trunk_steps:
             hi, lo, b = w.convs[name]
-            ksize = 1 if i == 0 else 3          # conv1_1 runs as a 1x1 over the im2col image
-            ops.conv2d(self.acts[i], hi, lo, b, ksize, True, out=self.acts[i + 1], fuse_pool=fused)
+            if i == 0:                          # conv1_1: sliding-window reads of the compact image, K = 3 x 32
+                ops.conv3x3_c8(self.acts[0], self.H, self.W, hi, lo, b, True, out=self.acts[1])
+            else:
+                ops.conv2d(self.acts[i], hi, lo, b, 3, True, out=self.acts[i + 1], fuse_pool=fused)
             n += 1
             i += 1
             if pool_after:
@@ -266,14 +274,21 @@ class ForwardPlan(object):
         uploads, replays the graph and brings the whole result block back with ONE D2H; blocks until it is there.
         Returns a dict of numpy VIEWS into the pinned mirror (valid until the next forward_host on this plan)."""
         io = self.host_io()
-        io["x"].t.view(-1).copy_(torch.from_numpy(x_np).reshape(-1))       # pageable -> pinned on the host cores (dense bytes)
+        prof = HOST_PROFILE
+        t0 = time.perf_counter() if prof is not None else 0.0
         n = self.result_words()
         st = io["stream"]
-        io["x"].h2d(self.x_in, st)                                 # H2D (cudaMemcpyAsync from the library's pinned block)
+        t1 = t0
+        io["x"].upload(x_np, self.x_in, st)                        # pageable -> pinned -> device, chunk-pipelined (one C call)
+        t2 = time.perf_counter() if prof is not None else 0.0
         with torch.cuda.stream(st):
             self.forward(None)
+        t3 = time.perf_counter() if prof is not None else 0.0
         io["res"].d2h(self.result, st, nbytes=4 * n)               # D2H: everything the caller can ask for, one transfer
         ops.stream_synchronize(st)
+        if prof is not None:
+            t4 = time.perf_counter()
+            prof.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3)))
         return self.unpack_result(io["res"].np)
 
     def unpack_result(self, words):

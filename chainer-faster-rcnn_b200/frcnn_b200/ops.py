@@ -96,6 +96,49 @@ def pack_image_im2col(x_chw, precision="bf16x3", out=None, hwc_memory=False):
     return out
 
 
+def pack_image_c8(x_chw, precision="bf16x3", out=None, hwc_memory=False):
+    """(C<=3,H,W) float32 CUDA image -> compact first-layer input: Act of flat planes holding [H][W+2][8] (+ slack).
+    hwc_memory as in pack_image_im2col."""
+    _need_cuda(x_chw)
+    x = x_chw.contiguous().float()
+    C, H, W = x.shape
+    if out is None:
+        n = _lib.load().frcnn_image_c8_elems(H, W)
+        hi = torch.empty((n,), dtype=torch.bfloat16, device=x.device)
+        out = Act(hi, torch.empty_like(hi) if precision == "bf16x3" else None)
+    sc, sh, sw = (1, W * C, C) if hwc_memory else (H * W, W, 1)
+    check(_lib.load().frcnn_pack_image_c8(_p(x), C, H, W, sc, sh, sw, _p(out.hi), _p(out.lo), _stream()), "frcnn_pack_image_c8")
+    return out
+
+
+def pack_conv_weights_c8(w, precision="bf16x3"):
+    """OIHW (Cout, Cin<=3, 3, 3) float32 -> ([3, Cout, 32] bf16 hi, lo or None) for conv3x3_c8."""
+    _need_cuda(w)
+    w = w.contiguous().float()
+    Cout, Cin, kh, kw = w.shape
+    if (kh, kw) != (3, 3):
+        raise FrcnnError("pack_conv_weights_c8: 3x3 kernels only")
+    hi = torch.empty((3, Cout, 32), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if precision == "bf16x3" else None
+    check(_lib.load().frcnn_pack_conv_weights_c8(_p(w), Cout, Cin, _p(hi), _p(lo), _stream()), "frcnn_pack_conv_weights_c8")
+    return hi, lo
+
+
+def conv3x3_c8(x_c8, H, W, w_hi, w_lo, bias, relu=True, out=None):
+    """frcnn_conv3x3_c8: conv1_1 over the compact image (pack_image_c8) -> Act [H,W,Cout]."""
+    taps, Cout, k = w_hi.shape
+    if (taps, k) != (3, 32):
+        raise FrcnnError("conv3x3_c8: weights must be [3, Cout, 32] (pack_conv_weights_c8)")
+    if (x_c8.lo is None) != (w_lo is None):
+        raise FrcnnError("conv3x3_c8: activation and weight precision modes differ")
+    if out is None:
+        yh = torch.empty((H, W, Cout), dtype=torch.bfloat16, device=x_c8.hi.device)
+        out = Act(yh, torch.empty_like(yh) if x_c8.lo is not None else None)
+    check(_lib.load().frcnn_conv3x3_c8(_p(x_c8.hi), _p(x_c8.lo), H, W, _p(w_hi), _p(w_lo), _p(bias), Cout, 1 if relu else 0,
+                                       _p(out.hi), _p(out.lo), _stream()), "frcnn_conv3x3_c8")
+    return out
+
+
 def pack_conv_weights_im2col(w, precision="bf16x3"):
     """OIHW (Cout, Cin<=3, 3, 3) float32 -> ([1, Cout, 32] bf16 hi, lo or None), K order of pack_image_im2col."""
     _need_cuda(w)
@@ -258,6 +301,21 @@ class PinnedBlock(object):
         self.np = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
         self.t = torch.from_numpy(self.np)
 
+    def fill_from(self, arr):
+        """Copy a C-contiguous numpy array of the same byte size into the block (frcnn_host_copy: a few sleeping worker
+        threads -- no framework thread pool is woken per image)."""
+        if arr.nbytes != self.nbytes or not arr.flags.c_contiguous:
+            raise FrcnnError("PinnedBlock.fill_from: need a C-contiguous array of %d bytes" % self.nbytes)
+        check(_lib.load().frcnn_host_copy(self.ptr, arr.ctypes.data, self.nbytes), "frcnn_host_copy")
+
+    def upload(self, arr, dst, stream):
+        """frcnn_upload_pageable: a C-contiguous numpy array -> device tensor `dst` through this pinned block, the host copy
+        of one 1 MB chunk overlapping the DMA of the previous one."""
+        if arr.nbytes != self.nbytes or not arr.flags.c_contiguous:
+            raise FrcnnError("PinnedBlock.upload: need a C-contiguous array of %d bytes" % self.nbytes)
+        check(_lib.load().frcnn_upload_pageable(dst.data_ptr(), arr.ctypes.data, self.ptr, self.nbytes, stream.cuda_stream),
+              "frcnn_upload_pageable")
+
     def h2d(self, dst, stream, nbytes=None):
         check(_lib.load().frcnn_memcpy_h2d_async(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(self.ptr),
                                                  int(self.nbytes if nbytes is None else nbytes),
@@ -292,6 +350,11 @@ def set_programmatic_launch(on=-1):
     """Programmatic dependent launch of the forward-path kernels for the calling thread: 1 on, 0 off, -1 = the
     FRCNN_PDL environment default (on).  Read at launch time, i.e. baked into a CUDA graph at capture."""
     _lib.load().frcnn_set_programmatic_launch(int(on))
+
+
+def set_conv_smem_reserve(nbytes=0):
+    """Shared memory per SM that later conv launches of this thread leave free for other streams' small kernels."""
+    _lib.load().frcnn_conv2d_set_smem_reserve(int(nbytes))
 
 
 def set_conv_max_ctas(max_ctas=0):
@@ -423,16 +486,26 @@ def nms(dets, thresh, mode=_lib.NMS_GE_DOUBLE, max_keep=0):
     return keep, count
 
 
+_nms_tls = None
+
+
 def cpu_nms_host(dets_np, thresh, device_id=0):
     """Host-array entry (frcnn_cpu_nms_host): numpy f32 [n,5] in, list[int] out -- the drop-in
-    behind models.cpu_nms.cpu_nms (the arithmetic runs on the GPU)."""
-    d = np.ascontiguousarray(dets_np, dtype=np.float32)
+    behind models.cpu_nms.cpu_nms (the arithmetic runs on the GPU).  Called 20 times per image by forward.py's loop, so
+    the wrapper itself is kept lean: a per-thread output buffer, raw addresses instead of ctypes casts."""
+    global _nms_tls
+    d = dets_np if (dets_np.dtype == np.float32 and dets_np.flags.c_contiguous) else np.ascontiguousarray(dets_np, dtype=np.float32)
     if d.ndim != 2 or d.shape[1] != 5:
         raise FrcnnError("cpu_nms: dets must be (N,5), got %s" % (d.shape,))
     n = d.shape[0]
-    keep = np.empty(max(n, 1), dtype=np.int32)
-    r = _lib.load().frcnn_cpu_nms_host(d.ctypes.data_as(ctypes.c_void_p), n, float(thresh),
-                                       keep.ctypes.data_as(ctypes.c_void_p), device_id)
+    if _nms_tls is None:
+        import threading
+        _nms_tls = threading.local()
+    keep = getattr(_nms_tls, "keep", None)
+    if keep is None or keep.shape[0] < n:
+        keep = _nms_tls.keep = np.empty(max(n, 1024), dtype=np.int32)
+        _nms_tls.fn = _lib.load().frcnn_cpu_nms_host
+    r = _nms_tls.fn(d.ctypes.data, n, float(thresh), keep.ctypes.data, device_id)
     if r < 0:
         raise FrcnnError("frcnn_cpu_nms_host failed (status %d): %s" % (r, _lib.last_error()))
     return keep[:r].tolist()

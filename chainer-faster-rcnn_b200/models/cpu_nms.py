@@ -13,7 +13,8 @@ from frcnn_b200 import ops
 
 
 def cpu_nms(dets, thresh):
-    dets = np.asarray(dets)
+    if not isinstance(dets, np.ndarray):
+        dets = np.asarray(dets)
     if dets.ndim != 2 or dets.shape[1] != 5:
         raise ValueError("Buffer has wrong number of dimensions or columns (expected (N, 5), got %s)" % (dets.shape,))
     if dets.dtype != np.float32:

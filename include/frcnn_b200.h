@@ -123,6 +123,12 @@ int frcnn_host_free(void* p);
 int frcnn_memcpy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream);
 int frcnn_memcpy_d2h_async(void* dst_host, const void* src_device, size_t bytes, void* stream);
 int frcnn_stream_synchronize(void* stream);
+/* Upload of a pageable host buffer through a pinned staging block of the same size, 1 MB chunks: the host copy of chunk k
+ * overlaps the DMA of chunk k-1 on `stream`.  Returns when the last chunk is enqueued (the staging block is busy until the
+ * stream reaches that point). */
+int frcnn_upload_pageable(void* dst_device, const void* src_host, void* staging_pinned, size_t bytes, void* stream);
+/* Host memcpy (pageable -> pinned staging) on a small pool of sleeping worker threads; dst and src must not overlap. */
+int frcnn_host_copy(void* dst, const void* src, size_t bytes);
 
 /* Programmatic dependent launch for the forward-path kernels (per calling thread; default on, or the FRCNN_PDL
  * environment variable "0"/"1"): a kernel's CTAs may become resident and run their prologue while the previous kernel of
@@ -135,6 +141,10 @@ void frcnn_set_programmatic_launch(int on);
  * each other's 148-CTA grids, and a smaller grid quantises a layer's tile count into fuller waves.  The value is baked
  * into a CUDA graph at capture time. */
 void frcnn_conv2d_set_max_ctas(int max_ctas);
+/* Shared memory (bytes, 0..96 KB) that subsequent frcnn_conv2d launches of the calling thread leave unused on every SM
+ * (fewer pipeline stages), so that small kernels of other streams can be resident beside the persistent convolution CTAs.
+ * Read at launch time (fixed inside a captured graph). */
+void frcnn_conv2d_set_smem_reserve(int bytes);
 
 /* OIHW fp32 weights (Chainer layout, e.g. trunk/conv1_1/W) -> [kh*kw, Cout, Cin_pad] bf16 hi/lo.
  * For Linear weights (Cout, K) pass kh=kw=1.  `perm_chw_to_hwc` != 0 with (c,h,w) = (pc,ph,pw)
@@ -157,6 +167,19 @@ int frcnn_preprocess_bgr8(const unsigned char* img_hwc, int h0, int w0, double m
  * OIHW (Cout,Cin<=3,3,3) -> [1,Cout,32].  conv1_1 (models/vgg16.py:39) is then frcnn_conv2d with ksize = 1,
  * Cin = 32: one 64-byte-row k-block per pixel tile instead of nine 32-byte-row blocks. */
 int frcnn_pack_image_im2col3x3(const float* x_chw, int C, int H, int W, void* y_hi, void* y_lo, void* stream);
+/* The compact first-layer path (what the whole-graph entry and the engine use): frcnn_pack_image_c8 writes the image as
+ * [H][W+2][8] bf16 planes (3 of 8 channels used, one zero pixel left and right of every row; frcnn_image_c8_elems elements
+ * per plane incl. a few zeroed slack pixels), source element (c,h,w) = x[c*stride_c + h*stride_h + w*stride_w];
+ * frcnn_pack_conv_weights_c8 packs OIHW (Cout, Cin<=3, 3, 3) as [3][Cout][32]; frcnn_conv3x3_c8 is conv1_1
+ * (models/vgg16.py:39-40: 3x3, pad 1, + bias, ReLU) as a K = 3 x 32 GEMM whose A operand is read through a sliding-window
+ * tensor map (pixel stride 16 B, 64-byte rows): the 4x larger im2col copy of frcnn_pack_image_im2col3x3 is never written. */
+size_t frcnn_image_c8_elems(int H, int W);
+int frcnn_pack_image_c8(const float* x, int C, int H, int W, long stride_c, long stride_h, long stride_w, void* y_hi, void* y_lo,
+                        void* stream);
+int frcnn_pack_conv_weights_c8(const float* w_oihw, int Cout, int Cin, void* w_hi, void* w_lo, void* stream);
+int frcnn_conv3x3_c8(const void* x_hi, const void* x_lo, int H, int W, const void* w_hi, const void* w_lo, const float* bias,
+                     int Cout, int relu, void* y_hi, void* y_lo, void* stream);
+
 /* Same with an explicit source layout: element (c, h, w) is x[c*stride_c + h*stride_h + w*stride_w] (in floats).
  * (H*W, W, 1) = dense (C,H,W); (1, W*C, C) = dense (H,W,C) memory, which is what forward.py:45's
  * `img.transpose([2, 0, 1]).astype(np.float32)` hands to the model (astype keeps the transposed strides). */
@@ -235,7 +258,7 @@ typedef struct {                             /* one layer as frcnn_pack_conv_wei
 } frcnn_packed_layer;
 
 typedef struct {
-    frcnn_packed_layer conv[13];             /* conv1_1 (frcnn_pack_conv_weights_im2col3x3) ... conv5_3 */
+    frcnn_packed_layer conv[13];             /* conv1_1 (frcnn_pack_conv_weights_c8) ... conv5_3 */
     frcnn_packed_layer rpn3;                 /* RPN/rpn_conv_3x3 */
     frcnn_packed_layer rpn_heads;            /* rpn_cls_score | rpn_bbox_pred rows concatenated: [1, 6A, 512] */
     frcnn_packed_layer fc6;                  /* K axis permuted (c,h,w) -> (h,w,c) (perm_chw_to_hwc) */

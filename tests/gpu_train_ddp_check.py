@@ -51,6 +51,35 @@ def main():
         print("ranks identical:", same, "| bucket == sum of per-image gradients (exact):", exact,
               "| max |g|", float(g_sum.abs().max()), flush=True)
         ok = ok and exact
+    # ---- BASELINE config #5's exchange: bf16 bucket, deep layers reduced on a side stream while the shallow layers still
+    # back-propagate.  Replicas must stay bit-identical; the update must agree with the exact fp32 exchange to bf16 rounding.
+    tb = RpnTrainer(params, H, W, anchors, subsample="none")
+    tb.set_grad_exchange("bf16", overlap=True)
+    tb.forward(imgs[rank], gts[rank])
+    tb.backward()
+    tb.update()
+    torch.cuda.synchronize()
+    wb = tb.w_flat.clone()
+    ws = [torch.empty_like(wb) for _ in range(world)]
+    dist.all_gather(ws, wb)
+    same_b = all(torch.equal(ws[0], w) for w in ws)
+    # v = -lr * (g + wd * w): compare the momentum buffers (= the applied gradients) of the two exchanges
+    num = float((tb.v_flat - tr.v_flat).abs().max())
+    den = float(tr.v_flat.abs().max())
+    close = num <= 2.0 ** -7 * den                   # each rank's bf16 rounding (2^-9) + the bf16 sum (2^-9), relative to max |g|
+    exposed = tb.last_exposed_exchange_ms()
+    if rank == 0:
+        print("bf16 bucket: ranks identical:", same_b, "| max |dv| / max |v| = %.2e (bound 2^-7)" % (num / max(den, 1e-30)),
+              "| exposed exchange %.3f ms" % exposed, flush=True)
+    ok = ok and same_b and close
+    # ---- fp32 exchange with the overlap on must reproduce the un-overlapped bucket exactly
+    to = RpnTrainer(params, H, W, anchors, subsample="none")
+    to.set_grad_exchange("fp32", overlap=False)
+    to.forward(imgs[rank], gts[rank])
+    to.backward()
+    to.update()
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(to.g_flat, g_sum) and torch.equal(to.w_flat, w_after)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -110,3 +110,26 @@ def test_preprocess_size_rule_matches_oracle_and_opencv():
         out = cv2.resize(np.zeros((h0, w0, 3), np.float32), None, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR)
         assert out.shape[:2] == (H, W), (h0, w0, out.shape, (H, W))
         assert min(H, W) <= 600 + 1 and max(H, W) <= 1000 + 1
+
+
+def test_host_copy_pool_is_a_memcpy():
+    """frcnn_host_copy (the pageable -> pinned staging copy of the host-array front end) is pure host code: sleeping worker
+    threads split the buffer; every byte count, including ragged tails and sizes below the threading threshold, must copy
+    exactly and touch nothing behind the end."""
+    import threading
+    from frcnn_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, size=9_000_001, dtype=np.uint8)
+    for n in (0, 1, 4095, 4096, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 7_200_000, 9_000_001):
+        dst = np.full(src.size + 64, 0xAB, dtype=np.uint8)
+        assert lib.frcnn_host_copy(dst.ctypes.data, src.ctypes.data, n) == 0
+        assert np.array_equal(dst[:n], src[:n]) and (dst[n:] == 0xAB).all()
+    # concurrent callers queue on the pool
+    outs = [np.zeros(7_200_000, np.uint8) for _ in range(4)]
+    ths = [threading.Thread(target=lambda o=o: [lib.frcnn_host_copy(o.ctypes.data, src.ctypes.data, o.size) for _ in range(5)]) for o in outs]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert all(np.array_equal(o, src[:o.size]) for o in outs)

@@ -496,3 +496,36 @@ def test_linear_swapab_long_k_exact_on_integers(ops, x3):
         _, y32 = ops.linear(xa, hi, lo, ops.pad_bias(b, N), False, ld_f32=N, want_act=False)
         want = (x[0].double() @ w.double().T + b.double()).float()
         assert torch.equal(y32, want), (K, x3, float((y32 - want).abs().max()))
+
+
+# ------------------------------------------------------------------------------- compact first layer (sliding-window TMA)
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+@pytest.mark.parametrize("shape", [(37, 45), (600 // 4, 1000 // 4 + 3), (16, 16), (9, 130)])
+def test_conv1_1_compact_image_sliding_window(ops, precision, shape):
+    """conv1_1 as frcnn_pack_image_c8 + frcnn_conv3x3_c8: the A operand of kernel row r is read through a tensor map whose
+    pixel stride (16 B) is smaller than its 64-byte rows (stored pixels w..w+3 of row h+r-1; zero border columns in memory,
+    rows -1 / H by TMA zero fill).  Against torch's conv2d on the identical 16-bit-split operands; the dense (C,H,W) source
+    and the HWC-memory source (forward.py:45's strided view) must give the same bits."""
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    x = (rng.uniform(0, 255, size=(3, H, W)) - 110.0).astype(f32)
+    w = (rng.standard_normal((64, 3, 3, 3)) * (2.0 / 27) ** 0.5).astype(f32)
+    b = (rng.standard_normal(64) * 0.1).astype(f32)
+    q = _quant16 if precision == "bf16x3" else _bf16
+    ref = torch.nn.functional.conv2d(torch.from_numpy(q(x))[None].double(), torch.from_numpy(q(w)).double(),
+                                     torch.from_numpy(b).double(), padding=1)[0].clamp_min(0).numpy()
+    wh, wl = ops.pack_conv_weights_c8(dev(w), precision=precision)
+    bias = ops.pad_bias(dev(b), 64)
+    xc8 = ops.pack_image_c8(dev(x), precision=precision)
+    y = ops.conv3x3_c8(xc8, H, W, wh, wl, bias, True)
+    got = y.to_chw_f32().cpu().numpy()
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < (5e-5 if precision == "bf16x3" else 6e-3), err
+    # HWC memory uploaded as it is: a (3,H,W)-shaped buffer whose bytes are the dense (H,W,3) image
+    hwc_bytes = dev(np.ascontiguousarray(x.transpose(1, 2, 0))).reshape(3, H, W)
+    y2 = ops.conv3x3_c8(ops.pack_image_c8(hwc_bytes, precision=precision, hwc_memory=True), H, W, wh, wl, bias, True)
+    assert torch.equal(y2.hi, y.hi) and (y.lo is None or torch.equal(y2.lo, y.lo))
+    # and the im2col formulation of the same layer agrees to rounding (different summation order inside the MMA)
+    wih, wil = ops.pack_conv_weights_im2col(dev(w), precision=precision)
+    y3, _ = ops.conv2d(ops.pack_image_im2col(dev(x), precision=precision), wih, wil, bias, 1, True)
+    assert np.abs(y3.to_chw_f32().cpu().numpy() - got).max() / np.abs(ref).max() < (2e-5 if precision == "bf16x3" else 6e-3)
