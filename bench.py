@@ -503,6 +503,12 @@ def run_b200_arm(args, rank, local_rank, world):
     # T caller threads, each running the same serial per-image code on its own images (a thread-per-request server):
     # the drop-in keeps a plan per calling thread, so the threads' graphs overlap on the GPU
     T = max(1, args.api_threads)
+    # every image makes ~45 short library calls that release the GIL; with CPython's default 5 ms switch interval a thread
+    # coming back from such a call can wait that long for the GIL while another one runs bytecode -- a server that drives
+    # the model from several threads lowers the interval (the caller's setting, restored below)
+    import sys as _sys
+    old_switch = _sys.getswitchinterval()
+    _sys.setswitchinterval(1e-4)
     per = [(args.steps + T - 1 - k) // T for k in range(T)]
     errs = []
 
@@ -534,6 +540,7 @@ def run_b200_arm(args, rank, local_rank, world):
     for t in ths:
         t.join()
     t_thr = time.perf_counter() - t0
+    _sys.setswitchinterval(old_switch)
     if errs:
         raise RuntimeError("reference-API worker failed: %s" % errs[0])
     api_threads = world * args.steps / shard.max_over_ranks(t_thr, device="cuda")
@@ -626,7 +633,7 @@ def run_b200_arm(args, rank, local_rank, world):
                    "one_image_in_flight": {"images_per_s_this_rank": args.steps / (ms_single / 1e3),
                                            "ms_per_image": ms_single / args.steps},
                    "seeds_one_image_in_flight": seed_rates,
-                   "cuda_graph": True, "programmatic_dependent_launch": os.environ.get("FRCNN_PDL", "1") != "0",
+                   "cuda_graph": True, "programmatic_dependent_launch": os.environ.get("FRCNN_PDL", "0") == "1",
                    "launches_per_image": plan.n_launches,
                    "frac_of_conv_roofline_burst": (value / world) * CONV_STACK_GFLOP / 1e3 / peak_burst},
         "clocks": clocks,
@@ -864,13 +871,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=3, help="independent images in flight per GPU (streams/graphs)")
+    ap.add_argument("--in-flight", type=int, default=4, help="independent images in flight per GPU (streams/graphs)")
     ap.add_argument("--grad-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="train_rpn workload: dtype of the all-reduced gradient bucket (BASELINE config #5 says bf16)")
     ap.add_argument("--no-overlap", action="store_true", help="train_rpn workload: one all-reduce after backward instead of bucket overlap")
     ap.add_argument("--smem-reserve-kb", type=int, default=0,
                     help="shared memory per SM the conv kernels leave to other streams' small kernels (tuning experiment)")
-    ap.add_argument("--api-threads", type=int, default=4, help="caller threads of the reference-interface e2e leg")
+    ap.add_argument("--api-threads", type=int, default=6, help="caller threads of the reference-interface e2e leg")
     ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")
     args = ap.parse_args()

@@ -15,10 +15,11 @@
 //   is exactly the conv's zero padding -- no im2col buffer, no halo handling in the kernel.
 //   The box lands in smem as 128 rows x 128 B, i.e. the canonical K-major SWIZZLE_128B UMMA tile.
 //
-// Kernel structure: persistent, one CTA per SM, 6 warps:
+// Kernel structure: persistent, one CTA per SM, 10 warps:
 //   warp 0    : TMA producer (one elected lane)         smem ring, full/empty mbarriers
 //   warp 1    : TMEM allocator + MMA issuer (one lane)  ring of accumulators in TMEM
-//   warps 2-5 : epilogue (TMEM lane group = warp % 4)   overlaps the next tile's main loop
+//   warps 2-9 : epilogue, two groups of four (TMEM lane group = warp % 4; group g takes the 32-column chunks g, g+2, ...);
+//               overlaps the next tile's main loop
 //
 // "bf16x3" mode (lo planes present): per k-block the stage holds A_hi, A_lo, B_hi, B_lo and the
 // issuer runs A_hi*B_hi into the main accumulator and A_lo*B_hi + A_hi*B_lo into a separate
@@ -64,7 +65,7 @@ struct ConvParams {
     long part_stride;
 };
 
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;          // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two groups of four)
 constexpr int kTileM = 128;
 constexpr int kStagePlane = kTileM * 64;          // one staging plane: 128 rows x 32 bf16
 constexpr int kStagingBytes = 2 * 2 * kStagePlane;   // 2 buffers x (hi, lo)
@@ -188,7 +189,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4 * CG);      // every epilogue warp of the pair arrives on the leader
+            ptx::mbar_init(&tempty_bar[i], 8 * CG);      // every epilogue warp of the pair arrives on the leader
         }
         for (int i = 0; i < AS; ++i) {
             ptx::mbar_init(&afull_bar[i], 1);
@@ -357,13 +358,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
     } else {
         // ================================ epilogue ================================
+        // Eight epilogue warps in two groups of four: a group covers all 128 accumulator rows (TMEM lane group = warp % 4) and
+        // takes every other 32-column chunk (group g: columns g*32, g*32 + 64, ...), with its own staging buffer, named barrier
+        // and bulk-store issuer.  With one warp per scheduler the epilogue issued an instruction every 5.5 cycles (ncu on
+        // conv1_1: no eligible warp 72 % of the time, profiles/r02_ncu_full_conv1_1_c8_details.txt): the N = 64 layers and the last
+        // tile of every launch are bound by it.
         const int lg = warp & 3;                 // TMEM lane group this warp may access
+        const int grp = (warp - 2) >> 2;         // epilogue group 0 / 1
         const int row = lg * 32 + lane;          // accumulator row == pixel within the tile
         const int m_valid = p.m_valid ? *p.m_valid : 0x7fffffff;
-        const bool issuer = (warp == 2 && lane == 0);     // the one thread that owns the bulk-store groups
+        const bool issuer = (warp == 2 + 4 * grp && lane == 0);     // the group's thread that owns its bulk-store groups
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t chunk_i = 0;                    // running chunk counter -> staging buffer parity
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
             const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
             const int nt = t2 % p.n_tiles;
@@ -378,31 +384,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
+            // TMEM -> registers, one 32-column chunk ahead: the loads of chunk c+1 (main and correction accumulator) are issued
+            // as soon as chunk c has been copied out of the landing registers, so their latency hides behind chunk c's bias /
+            // ReLU / split / staging work instead of standing at the head of every chunk (the N = 64 layers are epilogue-bound)
+            uint32_t rm[32], rc[32];
+            const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.acc_cols);
+            if (n0 + grp * 32 < p.n_cover && grp * 32 < BN) {
+                ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(grp * 32), rm);
+                if (p.x3) ptx::tmem_ld_32x32b_x32(tbase + (uint32_t)(grp * 32) + BN, rc);
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = grp * 32; c0 < BN; c0 += 64) {
                 if (n0 + c0 >= p.n_cover) break;   // warp-uniform: nothing is stored past the covered columns
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.acc_cols + c0);
-                ptx::tmem_ld_32x32b_x32(taddr, r);
+                const uint32_t taddr = tbase + (uint32_t)c0;
                 ptx::tmem_ld_wait();
                 const int n = n0 + c0;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rm[j]);
                 if (p.x3) {
                     // The tensor-core accumulator truncates on every add; keeping the ~2^-8-sized
                     // correction products in their own accumulator and adding them here with one
                     // round-to-nearest fp32 add keeps that bias at the single-pass level.
-                    ptx::tmem_ld_32x32b_x32(taddr + BN, r);
-                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rc[j]);
                 }
                 for (int a = 1; a < p.nacc; ++a) {            // rotated main accumulators of a long-K GEMM
                     ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)((a + (p.x3 ? 1 : 0)) * BN), r);
                     ptx::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                if (c0 + 64 < BN && n0 + c0 + 64 < p.n_cover) {      // this group's next chunk: its loads go out now
+                    ptx::tmem_ld_32x32b_x32(taddr + 64, rm);
+                    if (p.x3) ptx::tmem_ld_32x32b_x32(taddr + 64 + BN, rc);
                 }
                 if (p.bias != nullptr) {                    // split-K partial sums carry no bias (the reduction adds it once)
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -463,10 +479,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         // pooled tile is (TH/2) x (TW/2): row-major index of this thread's window
                         srow = ((row / p.TW) >> 1) * (p.TW >> 1) + ((row % p.TW) >> 1);
                     }
-                    uint8_t* sb = staging + (chunk_i & 1u) * (2 * kStagePlane);
-                    // the bulk store that last read this staging buffer (2 chunks ago) must be done reading
-                    if (issuer) ptx::bulk_wait_group_read<1>();
-                    ptx::named_bar_sync(1, 128);
+                    uint8_t* sb = staging + grp * (2 * kStagePlane);       // the group's own staging buffer
+                    // the group's previous bulk store must be done READING the buffer (it had this chunk's TMEM loads, bias,
+                    // ReLU and split to finish in)
+                    if (issuer) ptx::bulk_wait_group_read<0>();
+                    ptx::named_bar_sync(1 + grp, 128);
                     if (writer) {
                         const int sw = (srow >> 1) & 3;        // SWIZZLE_64B: 16-B chunk index ^= address bits [7:8]
                         uint8_t* rowp = sb + srow * 64;
@@ -491,14 +508,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         }
                     }
                     ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
-                    ptx::named_bar_sync(1, 128);
+                    ptx::named_bar_sync(1 + grp, 128);
                     if (issuer) {
                         const int ow = p.pool ? (w0 >> 1) : w0, oh = p.pool ? (h0 >> 1) : h0;
                         ptx::tma_store_3d(&tm_y_hi, sb, n, ow, oh);
                         if (p.store_lo) ptx::tma_store_3d(&tm_y_lo, sb + kStagePlane, n, ow, oh);
                         ptx::bulk_commit_group();
                     }
-                    ++chunk_i;
                 }
             }
             ptx::tc_fence_before();

@@ -235,6 +235,16 @@ static int nms_host_impl(const float* dets_host, int n, int dim, double thresh, 
     if (!dets_host || !keep_out_host) { set_error("nms host: NULL argument"); return FRCNN_ERR_ARG; }
     static thread_local HostNmsCtx ctx;
     const bool large = n > kSmallMax;
+    // device_id < 0: the calling thread's CURRENT device (cpu_nms has no device argument: a process that owns GPU 3 must
+    // not be moved to GPU 0 by its per-class NMS).  An explicit id (`_nms`, gpu_nms.pyx:16) is honoured and the caller's
+    // current device restored afterwards.
+    int prev_dev = 0;
+    FRCNN_CUDA_OK(cudaGetDevice(&prev_dev));
+    if (device_id < 0) device_id = prev_dev;
+    struct Restore {
+        int dev, prev;
+        ~Restore() { if (dev != prev) cudaSetDevice(prev); }
+    } restore{device_id, prev_dev};
     int rc = ctx_prepare(ctx, device_id, n, large);
     if (rc != FRCNN_OK) return rc;
     if (!large) {

@@ -29,46 +29,76 @@ __global__ void __launch_bounds__(kRedThreads) linear_reduce_kernel(const float*
     __shared__ float tile[kRedC][kRedR + 1];
     grid_dep_wait();
     const int c0 = blockIdx.x * kRedC, r0 = blockIdx.y * kRedR;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const int R = m_valid ? min(*m_valid, R_cap) : R_cap;
-    // load phase: a warp reads 32 consecutive RoI columns of one channel row (128 B), 8 rows per pass
+    // load phase: thread = (channel row, 4 consecutive RoI columns): one 16-byte load per split (ld % 32 == 0 keeps every row
+    // 128-byte aligned), all splits' loads of a thread independent; summed in split order (deterministic)
+    {
+        const int cl = threadIdx.x >> 3, rq = (threadIdx.x & 7) * 4;
 #pragma unroll
-    for (int j = 0; j < kRedC / 8; ++j) {
-        const int c = c0 + ty + 8 * j, r = r0 + tx;
-        float v = 0.0f;
-        if (c < Cout && r < R) {
-            const float* src = parts + (long)c * ld + r;
-            int s = 0;
-            for (; s + 8 <= S; s += 8) {                     // 8 independent loads in flight, then the adds in order
-                float t[8];
+        for (int j = 0; j < kRedC / 32; ++j) {
+            const int c = c0 + cl + 32 * j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < Cout) {
+                const float* src = parts + (long)c * ld + r0 + rq;
+                int s = 0;
+                for (; s + 4 <= S; s += 4) {
+                    float4 t[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = src[(long)(s + u) * part_stride];
+                    for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(src + (long)(s + u) * part_stride);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v = __fadd_rn(v, t[u]);
+                    for (int u = 0; u < 4; ++u) {
+                        v.x = __fadd_rn(v.x, t[u].x); v.y = __fadd_rn(v.y, t[u].y);
+                        v.z = __fadd_rn(v.z, t[u].z); v.w = __fadd_rn(v.w, t[u].w);
+                    }
+                }
+                for (; s < S; ++s) {
+                    const float4 t = *reinterpret_cast<const float4*>(src + (long)s * part_stride);
+                    v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w);
+                }
+                const float b = bias[c];
+                v.x = __fadd_rn(v.x, b); v.y = __fadd_rn(v.y, b); v.z = __fadd_rn(v.z, b); v.w = __fadd_rn(v.w, b);
+                if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             }
-            for (; s < S; ++s) v = __fadd_rn(v, src[(long)s * part_stride]);       // fixed order: deterministic
-            v = __fadd_rn(v, bias[c]);
-            if (relu) v = fmaxf(v, 0.0f);
+            const int r = r0 + rq;                       // rows past the RoI count are zero
+            float* t = &tile[cl + 32 * j][rq];
+            t[0] = r + 0 < R ? v.x : 0.f;
+            t[1] = r + 1 < R ? v.y : 0.f;
+            t[2] = r + 2 < R ? v.z : 0.f;
+            t[3] = r + 3 < R ? v.w : 0.f;
         }
-        tile[ty + 8 * j][tx] = v;
     }
     __syncthreads();
-    // store phase: a warp writes 2 x 32 consecutive channels of one RoI row
+    // store phase: thread = (RoI row, 2 adjacent channels): a warp writes 64 consecutive channels (128 B of bf16) of one row
+    {
+        const int cp = (threadIdx.x & 31) * 2, rl = threadIdx.x >> 5;
+        const int c = c0 + cp;
 #pragma unroll
-    for (int j = 0; j < kRedR / 8; ++j) {
-        const int r = r0 + ty + 8 * j;
-        if (r >= R_cap) continue;
-#pragma unroll
-        for (int h = 0; h < kRedC / 32; ++h) {
-            const int cl = tx + 32 * h, c = c0 + cl;
-            const float v = tile[cl][ty + 8 * j];
+        for (int k = 0; k < kRedR / 8; ++k) {
+            const int r = r0 + rl + 8 * k;
+            if (r >= R_cap) continue;
+            const float v0 = tile[cp][rl + 8 * k], v1 = tile[cp + 1][rl + 8 * k];
             if (y_hi != nullptr && c < Cout) {
-                __nv_bfloat16 hi, lo;
-                split_bf16(v, hi, lo);
-                y_hi[(long)r * Cout + c] = hi;
-                if (y_lo != nullptr) y_lo[(long)r * Cout + c] = lo;
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v0, h0, l0);
+                split_bf16(v1, h1, l1);
+                if ((Cout & 1) == 0) {                      // even row pitch: 4-byte aligned pairs
+                    __nv_bfloat162 hh, ll;
+                    hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
+                    *reinterpret_cast<__nv_bfloat162*>(y_hi + (long)r * Cout + c) = hh;
+                    if (y_lo != nullptr) *reinterpret_cast<__nv_bfloat162*>(y_lo + (long)r * Cout + c) = ll;
+                } else {
+                    y_hi[(long)r * Cout + c] = h0;
+                    if (y_lo != nullptr) y_lo[(long)r * Cout + c] = l0;
+                    if (c + 1 < Cout) {
+                        y_hi[(long)r * Cout + c + 1] = h1;
+                        if (y_lo != nullptr) y_lo[(long)r * Cout + c + 1] = l1;
+                    }
+                }
             }
-            if (y_f32 != nullptr && c < ld_f32) y_f32[(long)r * ld_f32 + c] = v;         // columns [Cout, ld_f32) are zero
+            if (y_f32 != nullptr) {
+                if (c < ld_f32) y_f32[(long)r * ld_f32 + c] = v0;               // columns [Cout, ld_f32) are zero
+                if (c + 1 < ld_f32) y_f32[(long)r * ld_f32 + c + 1] = v1;
+            }
         }
     }
 }

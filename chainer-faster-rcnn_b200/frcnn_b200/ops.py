@@ -348,7 +348,7 @@ def stream_synchronize(stream):
 
 def set_programmatic_launch(on=-1):
     """Programmatic dependent launch of the forward-path kernels for the calling thread: 1 on, 0 off, -1 = the
-    FRCNN_PDL environment default (on).  Read at launch time, i.e. baked into a CUDA graph at capture."""
+    FRCNN_PDL environment default (off).  Read at launch time, i.e. baked into a CUDA graph at capture."""
     _lib.load().frcnn_set_programmatic_launch(int(on))
 
 
@@ -489,7 +489,7 @@ def nms(dets, thresh, mode=_lib.NMS_GE_DOUBLE, max_keep=0):
 _nms_tls = None
 
 
-def cpu_nms_host(dets_np, thresh, device_id=0):
+def cpu_nms_host(dets_np, thresh, device_id=-1):
     """Host-array entry (frcnn_cpu_nms_host): numpy f32 [n,5] in, list[int] out -- the drop-in
     behind models.cpu_nms.cpu_nms (the arithmetic runs on the GPU).  Called 20 times per image by forward.py's loop, so
     the wrapper itself is kept lean: a per-thread output buffer, raw addresses instead of ctypes casts."""

@@ -51,7 +51,10 @@ void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, i
 
 /* Host-pointer greedy NMS with models/cpu_nms.pyx:18-69 semantics (internal descending sort with
  * ties -> lower index first, +1 pixel convention, (double)iou >= thresh).  dets_host [n,5].
- * Returns the number kept (>= 0) or a negative status.  Blocking. */
+ * Returns the number kept (>= 0) or a negative status.  Blocking.  device_id < 0: the calling thread's current device
+ * (cpu_nms has no device argument); an explicit id is used and the caller's current device restored.  n <= 2048 runs as ONE
+ * kernel on mapped pinned memory held per calling thread (no allocation, no cudaMemcpy, no stream synchronise per call);
+ * n <= 16384 through the chip-wide pipeline of frcnn_nms. */
 int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id);
 
 /* ---------------------------------------------------------------------------------------------
@@ -130,8 +133,8 @@ int frcnn_upload_pageable(void* dst_device, const void* src_host, void* staging_
 /* Host memcpy (pageable -> pinned staging) on a small pool of sleeping worker threads; dst and src must not overlap. */
 int frcnn_host_copy(void* dst, const void* src, size_t bytes);
 
-/* Programmatic dependent launch for the forward-path kernels (per calling thread; default on, or the FRCNN_PDL
- * environment variable "0"/"1"): a kernel's CTAs may become resident and run their prologue while the previous kernel of
+/* Programmatic dependent launch for the forward-path kernels (per calling thread; default OFF -- it measured no gain on the
+ * replayed graph, DESIGN.md 4 -- or the FRCNN_PDL environment variable "0"/"1"): a kernel's CTAs may become resident and run their prologue while the previous kernel of
  * the stream drains; every such kernel waits (griddepcontrol.wait) before it touches global memory.  on < 0 restores the
  * environment default.  Read when a launch is enqueued, i.e. fixed inside a captured graph. */
 void frcnn_set_programmatic_launch(int on);

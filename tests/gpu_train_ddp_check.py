@@ -27,6 +27,7 @@ def main():
     gts = [torch.tensor([[20 + 30 * r, 30, 150 + 30 * r, 170, 3], [100, 20 + 10 * r, 330, 240, 7]], dtype=torch.float32).cuda()
            for r in range(world)]
     tr = RpnTrainer(params, H, W, anchors, subsample="none")
+    tr.set_grad_exchange("fp32", overlap=False)       # the exact reference point: ONE all-reduce after backward
     tr.forward(imgs[rank], gts[rank])
     tr.backward()
     g_own = tr.g_flat.clone()
@@ -40,6 +41,7 @@ def main():
     ok = same
     if rank == 0:
         ref = RpnTrainer(params, H, W, anchors, subsample="none")
+        ref.set_grad_exchange("fp32", overlap=False)      # rank 0 alone: backward must not start a collective
         total = torch.zeros_like(g_own)
         for r in range(world):
             ref.forward(imgs[r], gts[r])
@@ -72,9 +74,9 @@ def main():
         print("bf16 bucket: ranks identical:", same_b, "| max |dv| / max |v| = %.2e (bound 2^-7)" % (num / max(den, 1e-30)),
               "| exposed exchange %.3f ms" % exposed, flush=True)
     ok = ok and same_b and close
-    # ---- fp32 exchange with the overlap on must reproduce the un-overlapped bucket exactly
+    # ---- fp32 exchange with the two overlapped buckets must reproduce the single all-reduce exactly
     to = RpnTrainer(params, H, W, anchors, subsample="none")
-    to.set_grad_exchange("fp32", overlap=False)
+    to.set_grad_exchange("fp32", overlap=True)
     to.forward(imgs[rank], gts[rank])
     to.backward()
     to.update()

@@ -376,4 +376,4 @@ def test_train_rpn_gradient_allreduce_two_ranks_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29547", os.path.join(ROOT, "tests", "gpu_train_ddp_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and "DDP_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-8000:]
