@@ -27,6 +27,11 @@ import sys
 import threading
 import time
 
+# More hardware work queues than the default 8: the B200 arm keeps 4 lane streams, a copy stream and, in the reference-interface
+# leg, a graph stream + a host-NMS stream per caller thread; with 8 queues unrelated streams alias onto one queue and a 30 us NMS
+# kernel can sit behind another thread's 1.4 ms graph (must be set before the CUDA context exists).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (os.path.join(ROOT, "chainer-faster-rcnn_b200"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
@@ -511,6 +516,7 @@ def run_b200_arm(args, rank, local_rank, world):
     _sys.setswitchinterval(1e-4)
     per = [(args.steps + T - 1 - k) // T for k in range(T)]
     errs = []
+    thread_secs = [0.0] * T
 
     def worker(k, n_local, sync):
         try:
@@ -520,8 +526,10 @@ def run_b200_arm(args, rank, local_rank, world):
             for i in range(2):
                 reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)     # per-thread plan + graph
             sync.wait()
+            tw = time.perf_counter()
             for i in range(n_local):
                 reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)
+            thread_secs[k] = time.perf_counter() - tw
         except Exception as exc:          # noqa: BLE001
             errs.append(repr(exc))
             try:
@@ -646,7 +654,7 @@ def run_b200_arm(args, rank, local_rank, world):
                         "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads" % T,
                 "reference_api_one_thread": {"value": api_serial, "unit": "images/s", "ms_per_image": 1e3 / (api_serial / world),
                                              "model_call_only_ms": api_model_only_ms, "last": list(r_api), "phases": api_phases},
-                "reference_api_threads": T,
+                "reference_api_threads": T, "reference_api_thread_seconds": [round(v, 4) for v in thread_secs],
                 "stream_runner_raw_uint8": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
                                             "d2h_bytes_per_step": runner8.d2h_bytes,
                                             "note": "the build's own streaming API (engine.StreamRunner): pinned RAW uint8 375x625 "

@@ -52,6 +52,7 @@ struct ConvParams {
     int nacc, acc_chunk;
     int ld_f32, n_cover;
     int store_bf16, store_lo;            // bf16 outputs go through the staged TMA store
+    int stage64;                         // 1: both epilogue groups fill ONE staging tile of 128-byte rows (64 channels) per 64-column block
     float* y_f32;
     const float* bias;
     const int* m_valid;
@@ -479,40 +480,73 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         // pooled tile is (TH/2) x (TW/2): row-major index of this thread's window
                         srow = ((row / p.TW) >> 1) * (p.TW >> 1) + ((row % p.TW) >> 1);
                     }
-                    uint8_t* sb = staging + grp * (2 * kStagePlane);       // the group's own staging buffer
-                    // the group's previous bulk store must be done READING the buffer (it had this chunk's TMEM loads, bias,
+                    // stage64 (Cout % 64 == 0): the two groups' 32-channel chunks are the two halves of ONE staging tile with
+                    // 128-byte rows (SWIZZLE_128B) and leave in one bulk store per plane: half as many (twice as long) rows for
+                    // the TMA unit -- the N = 64 layers are bound by the rate at which it retires store rows.  Otherwise each
+                    // group owns a staging tile of 64-byte rows (SWIZZLE_64B) and issues its own stores.
+                    const bool s64 = p.stage64 != 0;
+                    uint8_t* sb = s64 ? staging : staging + grp * (2 * kStagePlane);
+                    const int bar_id = s64 ? 3 : 1 + grp, bar_n = s64 ? 256 : 128;
+                    const bool my_store = s64 ? (warp == 2 && lane == 0) : issuer;
+                    // the previous bulk store out of this buffer must be done READING it (it had this chunk's TMEM loads, bias,
                     // ReLU and split to finish in)
-                    if (issuer) ptx::bulk_wait_group_read<0>();
-                    ptx::named_bar_sync(1 + grp, 128);
+                    if (my_store) ptx::bulk_wait_group_read<0>();
+                    ptx::named_bar_sync(bar_id, bar_n);
                     if (writer) {
-                        const int sw = (srow >> 1) & 3;        // SWIZZLE_64B: 16-B chunk index ^= address bits [7:8]
-                        uint8_t* rowp = sb + srow * 64;
+                        if (s64) {
+                            const int sw = srow & 7;               // SWIZZLE_128B: 16-B chunk index ^= address bits [7:9]
+                            uint8_t* rowp = sb + srow * 128;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float ra[8];
-                            uint4 hv;
-                            hv.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1], ra[0], ra[1]);
-                            hv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3], ra[2], ra[3]);
-                            hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
-                            hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
-                            *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = hv;
-                            if (p.store_lo) {
-                                float d0, d1;
-                                uint4 lv;
-                                lv.x = pack_bf16x2(ra[0], ra[1], d0, d1);
-                                lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
-                                lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
-                                lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
-                                *reinterpret_cast<uint4*>(rowp + kStagePlane + ((q ^ sw) << 4)) = lv;
+                            for (int q = 0; q < 4; ++q) {
+                                float ra[8];
+                                uint4 hv;
+                                hv.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1], ra[0], ra[1]);
+                                hv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3], ra[2], ra[3]);
+                                hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
+                                hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
+                                const int c16 = (grp * 4 + q) ^ sw;
+                                *reinterpret_cast<uint4*>(rowp + (c16 << 4)) = hv;
+                                if (p.store_lo) {
+                                    float d0, d1;
+                                    uint4 lv;
+                                    lv.x = pack_bf16x2(ra[0], ra[1], d0, d1);
+                                    lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
+                                    lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
+                                    lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
+                                    *reinterpret_cast<uint4*>(rowp + 2 * kStagePlane + (c16 << 4)) = lv;
+                                }
+                            }
+                        } else {
+                            const int sw = (srow >> 1) & 3;        // SWIZZLE_64B: 16-B chunk index ^= address bits [7:8]
+                            uint8_t* rowp = sb + srow * 64;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float ra[8];
+                                uint4 hv;
+                                hv.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1], ra[0], ra[1]);
+                                hv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3], ra[2], ra[3]);
+                                hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
+                                hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
+                                *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = hv;
+                                if (p.store_lo) {
+                                    float d0, d1;
+                                    uint4 lv;
+                                    lv.x = pack_bf16x2(ra[0], ra[1], d0, d1);
+                                    lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
+                                    lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
+                                    lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
+                                    *reinterpret_cast<uint4*>(rowp + kStagePlane + ((q ^ sw) << 4)) = lv;
+                                }
                             }
                         }
                     }
                     ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
-                    ptx::named_bar_sync(1 + grp, 128);
-                    if (issuer) {
+                    ptx::named_bar_sync(bar_id, bar_n);
+                    if (my_store) {
                         const int ow = p.pool ? (w0 >> 1) : w0, oh = p.pool ? (h0 >> 1) : h0;
-                        ptx::tma_store_3d(&tm_y_hi, sb, n, ow, oh);
-                        if (p.store_lo) ptx::tma_store_3d(&tm_y_lo, sb + kStagePlane, n, ow, oh);
+                        const int nn = s64 ? n - grp * 32 : n;      // first channel of the stored block
+                        ptx::tma_store_3d(&tm_y_hi, sb, nn, ow, oh);
+                        if (p.store_lo) ptx::tma_store_3d(&tm_y_lo, sb + (s64 ? 2 * kStagePlane : kStagePlane), nn, ow, oh);
                         ptx::bulk_commit_group();
                     }
                 }
@@ -856,6 +890,7 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     p.n_cover = cdiv(cout_cover, 32) * 32;
     p.store_bf16 = y_hi != nullptr;
     p.store_lo = y_lo != nullptr;
+    p.stage64 = (y_hi != nullptr && y_f32 == nullptr && Cout % 64 == 0) ? 1 : 0;
     p.y_f32 = y_f32;
     p.bias = bias;
     p.m_valid = m_valid;
@@ -881,9 +916,10 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     if (y_hi) {
         const int Ho = p.pool ? (H + 1) / 2 : H, Wo = p.pool ? (W + 1) / 2 : W;
         const int bw = p.pool ? TW / 2 : TW, bh = p.pool ? TH / 2 : TH;
-        if ((rc = make_tmap_3d(&tm[4], y_hi, Cout, Wo, Ho, 32, bw, bh)) != FRCNN_OK) return rc;
+        const int sc = p.stage64 ? 64 : 32;             // channels per store row: 128-byte (SWIZZLE_128B) or 64-byte rows
+        if ((rc = make_tmap_3d(&tm[4], y_hi, Cout, Wo, Ho, sc, bw, bh)) != FRCNN_OK) return rc;
         if (y_lo) {
-            if ((rc = make_tmap_3d(&tm[5], y_lo, Cout, Wo, Ho, 32, bw, bh)) != FRCNN_OK) return rc;
+            if ((rc = make_tmap_3d(&tm[5], y_lo, Cout, Wo, Ho, sc, bw, bh)) != FRCNN_OK) return rc;
         } else {
             tm[5] = tm[4];
         }

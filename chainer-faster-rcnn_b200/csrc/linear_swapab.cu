@@ -134,7 +134,7 @@ static LinearPlan plan_linear(int R_cap, int K, int Cout) {
     const double red_cost = (double)cdiv(Cout, 128) * 128 * lp.ld * 8.0 / 5e6 / 0.75;       // one slab written + read, in k-block times
     double best_cost = 0;
     lp.splits = 1;
-    for (int s = 1; s <= 64 && s * 2 <= (kb > 1 ? kb : 2); ++s) {
+    for (int s = 1; s <= 16 && s * 2 <= (kb > 1 ? kb : 2); ++s) {       // <= 16 slabs: the reduction reads them one after another
         const int per = cdiv(kb, s);
         if (cdiv(kb, per) != s) continue;                   // not an effective split count
         const double cost = (double)cdiv(base * s, slots) * per + red_cost * s;
