@@ -178,12 +178,10 @@ struct HostNmsCtx {
     size_t ws_bytes = 0;
     int ticket = 0;
     size_t smem_attr = 48 * 1024;   // largest dynamic shared-memory size set on nms_small_kernel by this thread so far
-    ~HostNmsCtx() {                 // thread exit: best effort (the CUDA context may already be gone)
-        if (h_in) cudaFreeHost(h_in);
-        if (h_out) cudaFreeHost(h_out);
-        if (d_ws) cudaFree(d_ws);
-        if (stream) cudaStreamDestroy(stream);
-    }
+    // No destructor on purpose: cudaFreeHost / cudaFree at THREAD EXIT synchronise the whole device and hold the context lock
+    // for milliseconds, stalling every other caller thread that is still running (measured: two of six threads took 3x as
+    // long, profiles/r02_api_threads_diag_before_plan_pool.txt).  A thread's ~50 KB of pinned staging and its stream stay
+    // allocated until the process exits.
 };
 
 static int ctx_prepare(HostNmsCtx& c, int device_id, int n, bool large) {

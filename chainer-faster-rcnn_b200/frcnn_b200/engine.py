@@ -456,6 +456,20 @@ class StreamRunner(object):
 
 
 
+class _PlanLease(object):
+    """Thread-local handle of a checked-out ForwardPlan: returns the plan to its engine's pool when the owning thread's
+    thread-local storage is torn down."""
+
+    def __init__(self, engine, key, plan):
+        self.engine, self.key, self.plan = engine, key, plan
+
+    def __del__(self):
+        try:
+            self.engine._return_plan(self.key, self.plan)
+        except Exception:          # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class Engine(object):
     """Weights + per-shape plans.  `engine(x)` -> (prob [R,21], boxes [R,84]) device tensors, R synced."""
     supports_hwc_input = True          # the VGG16 plan's first kernel takes source strides (ForwardPlan(hwc_input=True))
@@ -479,26 +493,32 @@ class Engine(object):
 
     def thread_plan(self, H, W, **overrides):
         """A ForwardPlan private to the calling thread (buffers, graph, stream over the shared weights): several host
-        threads may call the model concurrently, one image each, and their graphs overlap on the GPU."""
+        threads may call the model concurrently, one image each, and their graphs overlap on the GPU.  Plans live in a pool
+        per (shape, options): a thread checks one out on its first call and a finalizer on its thread-local state hands it
+        back when the thread ends, so the next thread reuses the captured graph and the pinned staging -- nothing is freed
+        at thread exit (cudaFree / cudaFreeHost there would stall every other caller)."""
         kw = dict(self.plan_kwargs)
         kw.update(overrides)
         key = (H, W, tuple(sorted(kw.items())))
-        cache = self._tls.__dict__.setdefault("plans", {})
-        p = cache.get(key)
-        if p is None:
+        held = self._tls.__dict__.setdefault("plans", {})
+        lease = held.get(key)
+        if lease is None:
             with self._lock:
-                base = self.plan(H, W, **overrides)
-                owner = getattr(base, "_owner_thread", None)
-                import threading
-                me = threading.get_ident()
-                if owner is None or owner == me:
-                    base._owner_thread = me
-                    p = base
-                else:
-                    p = base.clone()
-                    p._owner_thread = me
-            cache[key] = p
-        return p
+                pool = self.__dict__.setdefault("_plan_pool", {}).setdefault(key, [])
+                p = pool.pop() if pool else None
+                if p is None:
+                    base = self.plan(H, W, **overrides)
+                    if not getattr(base, "_leased", False):
+                        p = base
+                    else:
+                        p = base.clone()
+                p._leased = True
+            lease = held[key] = _PlanLease(self, key, p)
+        return lease.plan
+
+    def _return_plan(self, key, plan):
+        with self._lock:
+            self.__dict__.setdefault("_plan_pool", {}).setdefault(key, []).append(plan)
 
     def call_host(self, x_np, img_info=None, **overrides):
         """Host-array call: x_np float32 (3,H,W) numpy -> dict of numpy results (ForwardPlan.forward_host).  A C-contiguous
