@@ -508,6 +508,14 @@ def run_b200_arm(args, rank, local_rank, world):
     # T caller threads, each running the same serial per-image code on its own images (a thread-per-request server):
     # the drop-in keeps a plan per calling thread, so the threads' graphs overlap on the GPU
     T = max(1, args.api_threads)
+    # every caller thread (and every rank's main thread) spins on a core while it waits for the GPU: stay inside the
+    # container's CPU quota (the GPU boxes: cpu.max = 16 CPUs) when several ranks share it
+    try:
+        q = cg0["cpu_max"].split() if cg0["cpu_max"] else []
+        cpus = int(q[0]) // int(q[1]) if len(q) == 2 and q[0] != "max" else (os.cpu_count() or 8)
+    except (ValueError, ZeroDivisionError):
+        cpus = os.cpu_count() or 8
+    T = max(2, min(T, cpus // world - 1)) if world > 1 else T
     # every image makes ~45 short library calls that release the GIL; with CPython's default 5 ms switch interval a thread
     # coming back from such a call can wait that long for the GIL while another one runs bytecode -- a server that drives
     # the model from several threads lowers the interval (the caller's setting, restored below)
@@ -887,7 +895,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="train_rpn workload: one all-reduce after backward instead of bucket overlap")
     ap.add_argument("--smem-reserve-kb", type=int, default=0,
                     help="shared memory per SM the conv kernels leave to other streams' small kernels (tuning experiment)")
-    ap.add_argument("--api-threads", type=int, default=6, help="caller threads of the reference-interface e2e leg")
+    ap.add_argument("--api-threads", type=int, default=8, help="caller threads of the reference-interface e2e leg")
     ap.add_argument("--workload", default="forward", choices=["forward", "train_rpn", "train_rcnn", "resnet101"],
                     help="forward = the headline metric (default); train_rpn / resnet101 = secondary workloads (configs #5 / #4)")
     args = ap.parse_args()

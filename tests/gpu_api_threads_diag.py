@@ -51,8 +51,10 @@ def run(T, with_nms):
     return (N // T) * T / max(secs), (N // T) * T / tot, secs
 
 
-for with_nms in (False, True):
-    for T in (1, 2, 3, 4, 6):
+T_LIST = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 2, 3, 4, 6]
+NMS_LIST = [bool(int(v)) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [False, True]
+for with_nms in NMS_LIST:
+    for T in T_LIST:
         for rep in range(3):
             ips, ips_wall, secs = run(T, with_nms)
             print("nms=%d T=%d rep %d: %.1f img/s over the threads' loops (%.1f incl. thread start/stop)  thread seconds %s" %

@@ -38,5 +38,20 @@ rp = orc.make_resnet_params(50, seed=1)
 re_ = ResNetEngine(rp, 50, precision="bf16x3", anchors=anchors, use_graph=False, post_n=50)
 p2, b2, _ = re_(torch.from_numpy(orc.make_image(96, 131, seed=2)[0]).cuda())
 print("resnet", p2.shape)
+# round 2 additions: the host-array front end (pinned chunked upload, one result block), the host NMS paths
+# (one-kernel zero-copy path and the chip-wide pipeline), frcnn_linear with ragged shapes
+from frcnn_b200 import ops  # noqa: E402
+res, _ = eng.call_host(orc.make_image(H, W, seed=3)[0])
+print("host call", res["count"], res["prob"].shape)
+for n in (1, 65, 300, 2049):
+    d = np.random.default_rng(n).uniform(0, 200, size=(n, 5)).astype(np.float32)
+    d[:, 2:4] += d[:, 0:2]
+    print("cpu_nms_host", n, len(ops.cpu_nms_host(d, 0.5)))
+xa = torch.randn((1, 77, 192), device="cuda")
+hi = xa.to(torch.bfloat16)
+act = ops.Act(hi, (xa - hi.float()).to(torch.bfloat16))
+wh, wl = ops.pack_conv_weights(torch.randn((96, 192), device="cuda") * 0.05)
+y, y32 = ops.linear(act, wh, wl, ops.pad_bias(torch.zeros(96, device="cuda"), 96), True, ld_f32=96)
+print("linear", y32.shape)
 torch.cuda.synchronize()
 print("SANITIZER_TARGET_DONE")
