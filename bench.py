@@ -522,7 +522,8 @@ def run_b200_arm(args, rank, local_rank, world):
     import sys as _sys
     old_switch = _sys.getswitchinterval()
     _sys.setswitchinterval(1e-4)
-    per = [(args.steps + T - 1 - k) // T for k in range(T)]
+    n_thr = max(args.steps, 6 * T)           # at least 6 images per caller thread, whatever --steps says (reported: e2e.images_timed)
+    per = [(n_thr + T - 1 - k) // T for k in range(T)]
     errs = []
     thread_secs = [0.0] * T
 
@@ -664,7 +665,7 @@ def run_b200_arm(args, rank, local_rank, world):
                         "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads" % T,
                 "reference_api_one_thread": {"value": api_serial, "unit": "images/s", "ms_per_image": 1e3 / (api_serial / world),
                                              "model_call_only_ms": api_model_only_ms, "last": list(r_api), "phases": api_phases},
-                "reference_api_threads": T, "reference_api_wall_incl_thread_start_stop_s": round(t_thr, 4), "reference_api_thread_seconds": [round(v, 4) for v in thread_secs],
+                "reference_api_threads": T, "images_timed": int(sum(per)), "reference_api_wall_incl_thread_start_stop_s": round(t_thr, 4), "reference_api_thread_seconds": [round(v, 4) for v in thread_secs],
                 "stream_runner_raw_uint8": {"value": e2e8_val, "unit": "images/s", "h2d_bytes_per_step": runner8.h2d_bytes,
                                             "d2h_bytes_per_step": runner8.d2h_bytes,
                                             "note": "the build's own streaming API (engine.StreamRunner): pinned RAW uint8 375x625 "

@@ -730,6 +730,29 @@ def test_faster_rcnn_class_rcnn_training_branch(dropin_installed):
         tr.keep.numel(), int(tr.prop.count.item())))
     # (that a step lowers the loss on a fixed kept set is asserted in test_rcnn_train_step_layerwise_and_end_to_end; here the
     #  proposals themselves move with the trunk, so the two losses are not comparable)
+    # ---- the learnt weights flow back into the Link params: checkpoint / param_dict / inference see them
+    w_fc7_dev = tr.weights("fc7/W").cpu().numpy()
+    named = dict(model.namedparams())                         # namedparams() syncs from the trainer first
+    assert np.array_equal(named["/fc7/W"].data, w_fc7_dev) and not np.array_equal(w_fc7_dev, w0.cpu().numpy())
+    fc6_dev = tr.export_params()["fc6/W"]                     # back in the reference's (c, h, w) column order
+    assert np.array_equal(named["/fc6/W"].data, fc6_dev)
+    assert model.rcnn_trainer is tr and model._rcnn_trainer_key[1] == model.version_key()     # the trainer is kept, not rebuilt
+    # ---- a new image shape: the new trainer starts from the CURRENT weights and inherits the momentum
+    v_old = tr.v_flat.clone()
+    H2, W2 = 200, 264
+    np.random.seed(4)
+    gt2 = np.array([[[20, 30, 150, 170, 3], [100, 20, 250, 190, 7]]], f32)
+    model(Variable(orc.make_image(H2, W2, seed=6)), Variable(np.array([[H2, W2]], np.int32)), Variable(gt2))
+    tr2 = model.rcnn_trainer
+    assert tr2 is not tr and torch.equal(tr2.v_flat, v_old)
+    assert np.array_equal(tr2.weights("fc7/W").cpu().numpy(), w_fc7_dev)
+    # ---- a change made on a SUB-link is seen by the caches further up (version keys cover descendants)
+    k0 = model.version_key()
+    model.trunk.conv1_1.b.data = model.trunk.conv1_1.b.data + f32(0.5)          # assignment bumps the owning link
+    assert model.version_key() != k0
+    k1 = model.version_key()
+    model.RPN._params_changed()
+    assert model.version_key() != k1
 
 
 def test_single_pass_bf16_mode_of_the_training_and_resnet_paths():
