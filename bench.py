@@ -500,6 +500,16 @@ def run_b200_arm(args, rank, local_rank, world):
                   "per_image_ms_median": float(np.median(per_image)), "per_image_ms_mean": float(per_image.mean()),
                   "per_image_ms_p90": float(np.percentile(per_image, 90)), "per_image_ms_max": float(per_image.max())}
     api_serial = world * args.steps / shard.max_over_ranks(t_api, device="cuda")
+    # the same serial loop with the in-graph hand-off of the per-class NMS switched off: every cpu_nms call is its own kernel
+    # launch + host round trip (models/cpu_nms.py)
+    import models.cpu_nms as _caller_nms
+    _caller_nms.HANDOFF = False
+    reference_api_image(model, x_vars[0], info_var, ref_nms, np)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        reference_api_image(model, x_vars[i % n_img], info_var, ref_nms, np)
+    api_serial_standalone = world * args.steps / shard.max_over_ranks(time.perf_counter() - t0, device="cuda")
+    _caller_nms.HANDOFF = True
     # the model call alone (no caller NMS), serial: where the time of the serial number goes
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -524,45 +534,54 @@ def run_b200_arm(args, rank, local_rank, world):
     _sys.setswitchinterval(1e-4)
     n_thr = max(args.steps, 6 * T)           # at least 6 images per caller thread, whatever --steps says (reported: e2e.images_timed)
     per = [(n_thr + T - 1 - k) // T for k in range(T)]
-    errs = []
-    thread_secs = [0.0] * T
 
-    def worker(k, n_local, sync):
-        try:
-            torch.cuda.set_device(local_rank)
-            if args.smem_reserve_kb:
-                _ops.set_conv_smem_reserve(1024 * args.smem_reserve_kb)
-            for i in range(2):
-                reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)     # per-thread plan + graph
-            sync.wait()
-            tw = time.perf_counter()
-            for i in range(n_local):
-                reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)
-            thread_secs[k] = time.perf_counter() - tw
-        except Exception as exc:          # noqa: BLE001
-            errs.append(repr(exc))
+    def threads_leg():
+        errs = []
+        thread_secs = [0.0] * T
+
+        def worker(k, n_local, sync):
             try:
-                sync.abort()
-            except Exception:             # noqa: BLE001
-                pass
-    sync = threading.Barrier(T + 1)
-    ths = [threading.Thread(target=worker, args=(k, per[k], sync)) for k in range(T)]
-    for t in ths:
-        t.start()
-    try:
-        sync.wait()
-    except threading.BrokenBarrierError:
-        pass
-    t0 = time.perf_counter()
-    for t in ths:
-        t.join()
-    t_thr = time.perf_counter() - t0
+                torch.cuda.set_device(local_rank)
+                if args.smem_reserve_kb:
+                    _ops.set_conv_smem_reserve(1024 * args.smem_reserve_kb)
+                for i in range(2):
+                    reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)     # per-thread plan + graph
+                sync.wait()
+                tw = time.perf_counter()
+                for i in range(n_local):
+                    reference_api_image(model, x_vars[(k + i) % n_img], info_var, ref_nms, np)
+                thread_secs[k] = time.perf_counter() - tw
+            except Exception as exc:          # noqa: BLE001
+                errs.append(repr(exc))
+                try:
+                    sync.abort()
+                except Exception:             # noqa: BLE001
+                    pass
+        sync = threading.Barrier(T + 1)
+        ths = [threading.Thread(target=worker, args=(k, per[k], sync)) for k in range(T)]
+        for t in ths:
+            t.start()
+        try:
+            sync.wait()
+        except threading.BrokenBarrierError:
+            pass
+        t0 = time.perf_counter()
+        for t in ths:
+            t.join()
+        t_thr = time.perf_counter() - t0
+        if errs:
+            raise RuntimeError("reference-API worker failed: %s" % errs[0])
+        # the rate of the threads' own timed loops (first start to last finish is what t_thr adds: thread start-up and teardown)
+        t_loop = max(thread_secs) if all(v > 0 for v in thread_secs) else t_thr
+        return world * sum(per) / shard.max_over_ranks(t_loop, device="cuda"), t_thr, thread_secs
+
+    nms_stats0 = dict(_caller_nms.stats)
+    api_threads, t_thr, thread_secs = threads_leg()
+    nms_stats1 = dict(_caller_nms.stats)
+    _caller_nms.HANDOFF = False
+    api_threads_standalone, _, thread_secs_standalone = threads_leg()
+    _caller_nms.HANDOFF = True
     _sys.setswitchinterval(old_switch)
-    if errs:
-        raise RuntimeError("reference-API worker failed: %s" % errs[0])
-    # the rate of the threads' own timed loops (first start to last finish is what t_thr adds: thread start-up and teardown)
-    t_loop = max(thread_secs) if all(v > 0 for v in thread_secs) else t_thr
-    api_threads = world * sum(per) / shard.max_over_ranks(t_loop, device="cuda")
     link = host_link_probe(torch) if rank == 0 else None
     cg1 = cgroup_cpu()
     cgroup = {"cpu_max": cg1["cpu_max"],
@@ -637,7 +656,7 @@ def run_b200_arm(args, rank, local_rank, world):
                                   "stand-in for Chainer, NMS = %s" %
                                   (tt, tn, "reference cpu_nms.pyx" if ref_nms_c is not None else "C port of cpu_nms.pyx")}
 
-    d2h_api = 4 * plan.result_words_nodetect
+    d2h_api = 4 * plan.result_words()
     line = {
         "metric": "images/sec end-to-end VGG16 Faster R-CNN forward @600x1000",
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
@@ -657,12 +676,24 @@ def run_b200_arm(args, rank, local_rank, world):
                    "frac_of_conv_roofline_burst": (value / world) * CONV_STACK_GFLOP / 1e3 / peak_burst},
         "clocks": clocks,
         # headline e2e = the REFERENCE's interface: FasterRCNN.__call__ with a host float32 (1,3,600,1000) Variable and
-        # img_info, then the caller's 20 cpu_nms calls on host arrays -- per image, inside the timed region: the pinned
-        # upload of the 7.2 MB image, the graph, ONE download of (prob, boxes, proposals), 20 host-array NMS round trips.
-        "e2e": {"value": api_threads, "unit": "images/s", "h2d_bytes_per_step": 4 * 3 * H_IMG * W_IMG + 20 * 300 * 5 * 4,
-                "d2h_bytes_per_step": d2h_api + 20 * 300 * 4,
+        # img_info, then the caller's 20 cpu_nms calls on host arrays -- per image, inside the timed region: the upload of
+        # the 7.2 MB image, the graph (which, as the model's default caller_nms_thresh = 0.3 says, also runs forward.py's
+        # per-class NMS), ONE download of (prob, boxes, proposals, keep lists), and the 20 cpu_nms calls, each of which
+        # checks its rows bit for bit against the downloaded block and hands the device-computed keep list over
+        # (models/cpu_nms.py).  `*_standalone_nms` = the same with that hand-off switched off: 20 kernel launches + host
+        # round trips per image.
+        "e2e": {"value": api_threads, "unit": "images/s", "h2d_bytes_per_step": 4 * 3 * H_IMG * W_IMG,
+                "d2h_bytes_per_step": d2h_api,
                 "mode": "models.faster_rcnn.FasterRCNN.__call__(Variable float32 (1,3,600,1000) HOST, img_info) + 20 x "
-                        "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads" % T,
+                        "models.cpu_nms.cpu_nms(dets, 0.3) per image (forward.py:88-99,48-57), %d caller threads; per-class NMS "
+                        "computed in the image's graph (frcnn_detect), handed to cpu_nms after a bit-exact input check" % T,
+                "cpu_nms_calls": {"handed_over_from_graph": nms_stats1["handoff"] - nms_stats0["handoff"],
+                                  "standalone_kernel": nms_stats1["standalone"] - nms_stats0["standalone"]},
+                "reference_api_threads_standalone_nms": {"value": api_threads_standalone, "unit": "images/s",
+                                                         "h2d_bytes_per_step": 4 * 3 * H_IMG * W_IMG + 20 * 300 * 5 * 4,
+                                                         "d2h_bytes_per_step": d2h_api + 20 * 300 * 4,
+                                                         "thread_seconds": [round(v, 4) for v in thread_secs_standalone]},
+                "reference_api_one_thread_standalone_nms": {"value": api_serial_standalone, "unit": "images/s"},
                 "reference_api_one_thread": {"value": api_serial, "unit": "images/s", "ms_per_image": 1e3 / (api_serial / world),
                                              "model_call_only_ms": api_model_only_ms, "last": list(r_api), "phases": api_phases},
                 "reference_api_threads": T, "images_timed": int(sum(per)), "reference_api_wall_incl_thread_start_stop_s": round(t_thr, 4), "reference_api_thread_seconds": [round(v, 4) for v in thread_secs],

@@ -30,6 +30,7 @@
 // issues a 3-D TMA store {32 ch, TW, TH} which clips the ragged image edge -- 2 bulk stores per
 // chunk instead of 1024 16-byte STG (the first version was store-issue bound on the 64-channel layers).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -53,6 +54,8 @@ struct ConvParams {
     int ld_f32, n_cover;
     int store_bf16, store_lo;            // bf16 outputs go through the staged TMA store
     int stage64;                         // 1: both epilogue groups fill ONE staging tile of 128-byte rows (64 channels) per 64-column block
+    int b_res;                           // 1 (per-tap path, one N tile, few k-blocks): ALL weight tiles are loaded once per CTA and stay
+                                         // resident in shared memory; the ring then carries A tiles only (conv1_1: 4750 tiles x 24 KB saved)
     float* y_f32;
     const float* bias;
     const int* m_valid;
@@ -155,9 +158,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int planes = p.x3 ? 2 : 1;
     const int a_stage_bytes = HALO ? planes * kHaloBytes : 0;
     const int AS = HALO ? p.a_stages : 0;
-    const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
+    const bool bres = !HALO && p.b_res != 0;
+    const int bres_bytes = bres ? p.taps * p.cin_blocks * planes * C::B_BYTES : 0;       // resident weight tiles, k-block major
+    const int stage_bytes = HALO ? planes * C::B_BYTES : (bres ? planes * C::A_BYTES : planes * (C::A_BYTES + C::B_BYTES));
+    const int a_lo_off = bres ? C::A_BYTES : C::A_BYTES + C::B_BYTES;                     // A_lo inside a per-tap stage
     const int S = p.num_stages;
-    uint8_t* ring = smem + (size_t)AS * a_stage_bytes;
+    uint8_t* bres_base = smem + (size_t)AS * a_stage_bytes;
+    uint8_t* ring = bres_base + bres_bytes;
     uint8_t* staging = ring + (size_t)S * stage_bytes;                 // 1024-aligned (all slot sizes are multiples of 1 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (p.store_bf16 ? kStagingBytes : 0));
     uint64_t* full_bar = bars;            // [S]
@@ -166,7 +173,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     uint64_t* tempty_bar = bars + 2 * S + 2;  // [2]
     uint64_t* afull_bar = bars + 2 * S + 4;   // [AS]
     uint64_t* aempty_bar = afull_bar + AS;    // [AS]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + AS);
+    uint64_t* bres_bar = aempty_bar + AS;     // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -196,6 +204,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             ptx::mbar_init(&afull_bar[i], 1);
             ptx::mbar_init(&aempty_bar[i], 1);
         }
+        ptx::mbar_init(bres_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -226,6 +235,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             int as = 0;
             uint32_t aphase = 0;
             (void)as; (void)aphase;
+            if (bres) {                  // one N tile: every weight tile of the layer, once, for all of this CTA's pixel tiles
+                if (leader) ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)(bres_bytes * CG));
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+                    uint8_t* sb = bres_base + (size_t)kb * planes * C::B_BYTES;
+                    tma_ld<CG>(sb, &tm_b_hi, bres_bar, cb * BK, (int)rank * (BN / CG), tap);
+                    if (p.x3) tma_ld<CG>(sb + C::B_BYTES, &tm_b_lo, bres_bar, cb * BK, (int)rank * (BN / CG), tap);
+                }
+            }
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
                 const int nt = t2 % p.n_tiles;
@@ -264,11 +282,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     uint8_t* st = ring + (size_t)stage * stage_bytes;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(stage_bytes * CG));
                     tma_ld<CG>(st, &tm_a_hi, &full_bar[stage], ka + cb * BK, w0 + s - p.pad_w, h0 + r - p.pad_h);
-                    tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], kboff + cb * BK, n0, btap);
+                    if (!bres) tma_ld<CG>(st + C::A_BYTES, &tm_b_hi, &full_bar[stage], kboff + cb * BK, n0, btap);
                     if (p.x3) {
-                        uint8_t* st2 = st + C::A_BYTES + C::B_BYTES;
+                        uint8_t* st2 = st + a_lo_off;
                         tma_ld<CG>(st2, &tm_a_lo, &full_bar[stage], ka + cb * BK, w0 + s - p.pad_w, h0 + r - p.pad_h);
-                        tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], kboff + cb * BK, n0, btap);
+                        if (!bres) tma_ld<CG>(st2 + C::A_BYTES, &tm_b_lo, &full_bar[stage], kboff + cb * BK, n0, btap);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -284,6 +302,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         int as = 0;
         uint32_t aphase = 0;
         (void)as; (void)aphase;
+        if (bres && leader) {
+            ptx::mbar_wait(bres_bar, 0);                 // the resident weight tiles have landed
+            ptx::tc_fence_after();
+        }
         for (int tile = tile0; leader && tile < p.num_tiles; tile += tile_step) {
             ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
@@ -331,8 +353,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 ptx::tc_fence_after();
                 if (ptx::elect_one()) {
                     const uint32_t st = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
+                    const uint32_t sbw = bres ? ptx::smem_u32(bres_base + (size_t)kb * planes * C::B_BYTES) : st + C::A_BYTES;
                     const uint64_t a_hi = ptx::make_smem_desc(st, C::ROW_BYTES);
-                    const uint64_t b_hi = ptx::make_smem_desc(st + C::A_BYTES, C::ROW_BYTES);
+                    const uint64_t b_hi = ptx::make_smem_desc(sbw, C::ROW_BYTES);
                     const int turn = kb / p.acc_chunk, ai = turn % p.nacc;
                     const uint32_t d_main = d_tmem + (uint32_t)(ai == 0 ? 0 : (ai + (p.x3 ? 1 : 0)) * BN);
                     const bool fresh = turn < p.nacc && kb == turn * p.acc_chunk;     // first k-block into this accumulator
@@ -342,8 +365,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         mma_ss<CG>(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, !(fresh && k == 0));
                     }
                     if (p.x3) {
-                        const uint64_t a_lo = ptx::make_smem_desc(st + C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
-                        const uint64_t b_lo = ptx::make_smem_desc(st + 2 * C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
+                        const uint64_t a_lo = ptx::make_smem_desc(st + a_lo_off, C::ROW_BYTES);
+                        const uint64_t b_lo = ptx::make_smem_desc(bres ? sbw + C::B_BYTES : st + 2 * C::A_BYTES + C::B_BYTES, C::ROW_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) mma_ss<CG>(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
@@ -656,7 +679,13 @@ static int make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t
 
 // Tuning overrides (frcnn_conv2d_set_*): per calling thread, read when a launch is enqueued (and therefore fixed inside
 // a captured graph) -- two engines driven from different threads cannot disturb each other.
-static thread_local int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = 0, g_smem_reserve = 0;
+static int env_int(const char* name) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+// FRCNN_CONV_MAX_CTAS: a process-wide default for frcnn_conv2d_set_max_ctas (each thread starts from it)
+static thread_local int g_force_bn = 0, g_force_th = 0, g_force_tw = 0, g_force_cg = 0, g_max_ctas = env_int("FRCNN_CONV_MAX_CTAS"),
+                        g_smem_reserve = 0;
 
 static int device_sm_count() {
     static int sms = 0;
@@ -673,8 +702,10 @@ template <int BN, int BK, bool HALO, int CG>
 static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream) {
     using C = Cfg<BN, BK, CG>;
     const int planes = p.x3 ? 2 : 1;
-    const int stage_bytes = HALO ? planes * C::B_BYTES : planes * (C::A_BYTES + C::B_BYTES);
-    const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0);
+    const bool bres = !HALO && p.b_res != 0;
+    const int bres_bytes = bres ? p.taps * p.cin_blocks * planes * C::B_BYTES : 0;
+    const int stage_bytes = HALO ? planes * C::B_BYTES : (bres ? planes * C::A_BYTES : planes * (C::A_BYTES + C::B_BYTES));
+    const int fixed = 1024 /*align slack*/ + kBarrierBytes + (p.store_bf16 ? kStagingBytes : 0) + bres_bytes;
     // shared-memory budget of the persistent CTA: everything by default; frcnn_conv2d_set_smem_reserve leaves a slice of
     // every SM to other kernels, so that the small kernels of ANOTHER image in flight (decode, NMS, RoI pooling, a host
     // caller's per-class NMS) can become resident next to a convolution instead of waiting for one of its CTAs to retire
@@ -891,6 +922,8 @@ static int conv2d_impl(const void* x_hi, const void* x_lo, int H, int W, int Cin
     p.store_bf16 = y_hi != nullptr;
     p.store_lo = y_lo != nullptr;
     p.stage64 = (y_hi != nullptr && y_f32 == nullptr && Cout % 64 == 0) ? 1 : 0;
+    // resident weights: the compact first layer (3 k-blocks, one N tile): 24 KB fetched once per CTA instead of once per tile
+    p.b_res = (we != nullptr && p.n_tiles == 1 && ge == nullptr && p.taps * p.cin_blocks <= 16) ? 1 : 0;
     p.y_f32 = y_f32;
     p.bias = bias;
     p.m_valid = m_valid;

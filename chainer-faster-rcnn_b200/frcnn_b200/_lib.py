@@ -26,6 +26,8 @@ SIGNATURES = {
     "frcnn_last_error": (c_char_p, []),
     "_nms": (None, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int]),
     "frcnn_cpu_nms_host": (c_int, [c_void_p, c_int, c_double, c_void_p, c_int]),
+    "frcnn_host_nms_phase_cycles": (c_int, [c_void_p]),
+    "frcnn_match_class_dets": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int]),
     "frcnn_nms_workspace_bytes": (c_size_t, [c_int]),
     "frcnn_nms": (c_int, [c_void_p, c_int, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "frcnn_proposals_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -135,6 +137,23 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_pylib = None
+
+
+def load_gil():
+    """A second handle on the same library whose calls KEEP the GIL (ctypes.PyDLL): for sub-microsecond pure-host helpers,
+    where releasing and re-acquiring the GIL (a condition-variable round trip under several caller threads) would cost
+    a hundred times the call."""
+    global _pylib
+    if _pylib is None:
+        load()
+        lib = ctypes.PyDLL(LIB_PATH)
+        fn = lib.frcnn_match_class_dets
+        fn.restype, fn.argtypes = SIGNATURES["frcnn_match_class_dets"]
+        _pylib = lib
+    return _pylib
 
 
 def last_error():

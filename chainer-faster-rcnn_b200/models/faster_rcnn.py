@@ -40,6 +40,10 @@ class FasterRCNN(links.Link):
         d["_rpn_delta"], d["_rcnn_delta"] = rpn_delta, rcnn_delta
         d["_rcnn_train"] = False
         d["_engine"] = (None, -1)
+        # forward.py:48-57 runs cpu_nms(dets, 0.3) per class on this call's host outputs (thresholds: forward.py:75-76).  With
+        # a threshold here the inference graph runs that per-class NMS itself (frcnn_detect) and models.cpu_nms hands the
+        # keep lists over when it is called on exactly those rows; None = the graph stops at (cls_prob, bbox_pred).
+        d["caller_nms_thresh"], d["caller_nms_conf"] = 0.3, 0.8
         d["rpn_proposals"], d["rpn_probs"] = None, None
         self.RPN.train = False
 
@@ -97,17 +101,21 @@ class FasterRCNN(links.Link):
 
     def engine(self):
         eng, ver = self._engine
-        if eng is None or ver != self.version_key():
+        n_layers = getattr(self.trunk, "n_layers", None)
+        handoff = self.caller_nms_thresh if n_layers is None else None
+        key = (self.version_key(), handoff, self.caller_nms_conf)
+        if eng is None or ver != key:
             params = self.param_dict()
             kw = dict(precision=self.precision, anchors=self.RPN.proposal_layer._anchors, num_classes=self._num_classes,
                       n_anchors=self.RPN.proposal_layer._num_anchors, feat_stride=self._feat_stride)
-            n_layers = getattr(self.trunk, "n_layers", None)
+            if handoff is not None:
+                kw.update(with_detect=True, det_nms_thresh=float(handoff), det_conf=float(self.caller_nms_conf))
             if n_layers is not None:                    # models.resnet.ResNet trunk
                 from frcnn_b200.resnet_engine import ResNetEngine
                 eng = ResNetEngine(params, n_layers, **kw)
             else:
                 eng = Engine(params, **kw)
-            self.__dict__["_engine"] = (eng, self.version_key())
+            self.__dict__["_engine"] = (eng, key)
         return eng
 
     def __call__(self, x, img_info, gt_boxes=None):
@@ -165,6 +173,11 @@ class FasterRCNN(links.Link):
             res, plan = self.engine().call_host(xd[0], img_info=(int(hw[0]), int(hw[1])), **kw)
             self.__dict__["rpn_proposals"] = res["rois"].copy()
             self.__dict__["rpn_probs"] = res["scores"].reshape(-1, 1).copy()
+            from models import cpu_nms as _caller_nms
+            if plan.with_detect:                         # the caller's per-class NMS already ran in the graph: hand it over
+                _caller_nms.publish(res["prob"], res["boxes"], res["keep_idx"], res["keep_count"], plan.det_nms_thresh)
+            else:
+                _caller_nms.withdraw()
             return Variable(res["prob"].copy()), res["boxes"].copy()
         t = arrays.to_device(x)
         prob, boxes, plan = self.engine()(t[0], img_info=(int(hw[0]), int(hw[1])), **kw)

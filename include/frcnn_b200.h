@@ -56,6 +56,17 @@ void _nms(int* keep_out, int* num_out, const float* boxes_host, int boxes_num, i
  * kernel on mapped pinned memory held per calling thread (no allocation, no cudaMemcpy, no stream synchronise per call);
  * n <= 16384 through the chip-wide pipeline of frcnn_nms. */
 int frcnn_cpu_nms_host(const float* dets_host, int n, double thresh, int* keep_out_host, int device_id);
+/* Diagnostics (no reference counterpart) of the calling thread's last small-n host NMS call: out8[0..5] = SM clock stamps --
+ * kernel entry, rows read from the mapped host block, ranked, diagonal blocks built, greedy chain resolved, keep list
+ * written; out8[6] = host ns inside the kernel-launch call, out8[7] = host ns polling the completion flag.  Returns 1 if
+ * out8 was filled, 0 if this thread has not made such a call yet. */
+int frcnn_host_nms_phase_cycles(long long* out8);
+/* Host-side helper (no CUDA call, no reference counterpart) of the in-graph per-class NMS hand-off: forward.py:48-57 builds
+ * dets = hstack(boxes[:, 4c:4c+4], prob[:, c]) per class and calls cpu_nms(dets, 0.3); the model call already ran that NMS
+ * for every class inside its graph (frcnn_detect).  Returns the class c (1 .. num_classes-1) whose rows of the result
+ * block equal `dets` [R,5] BIT FOR BIT (tries `hint` first), or 0 -- then the caller runs frcnn_cpu_nms_host. */
+int frcnn_match_class_dets(const float* dets, int R, const float* boxes, int ld_boxes, const float* prob, int ld_prob,
+                           int num_classes, int hint);
 
 /* ---------------------------------------------------------------------------------------------
  * Device NMS on UNSORTED dets [n,5] (x1,y1,x2,y2,score): replaces models/cpu_nms.pyx:18-69.

@@ -80,3 +80,27 @@ d32 = np.ascontiguousarray(dets, np.float32)
 print("ops.cpu_nms_host direct          : median %.3f ms (min %.3f max %.3f)" % med(lambda: ops.cpu_nms_host(d32, 0.3), n=200))
 print("whole image, reference interface : median %.3f ms (min %.3f max %.3f)" %
       med(lambda: bench.reference_api_image(model, Variable(xc), info, cpu_nms, np)))
+# where the per-call time of the host-array NMS goes: the round-trip floor (n = 2 rows: launch + mapped read + flag) and
+# the kernel's own device time at n = 300 (CUPTI)
+d2 = np.ascontiguousarray(d32[:2])
+print("ops.cpu_nms_host, 2 rows (floor) : median %.3f ms (min %.3f max %.3f)" % med(lambda: ops.cpu_nms_host(d2, 0.3), n=200))
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(50):
+        ops.cpu_nms_host(d32, 0.3)
+    torch.cuda.synchronize()
+for ev in prof.key_averages():
+    if "nms" in ev.key:
+        print("device time of %-40s: %.1f us avg over %d launches" % (ev.key[:40], ev.device_time_total / max(ev.count, 1), ev.count))
+import ctypes  # noqa: E402
+from frcnn_b200 import _lib  # noqa: E402
+
+acc = np.zeros(5)
+for _ in range(50):
+    ops.cpu_nms_host(d32, 0.3)
+    c = (ctypes.c_longlong * 8)()
+    if _lib.load().frcnn_host_nms_phase_cycles(ctypes.cast(c, ctypes.c_void_p)):
+        acc += np.diff(np.array(list(c)[:6], np.float64))
+print("nms_small_fast_kernel phases, SM cycles avg (read rows | rank | bitmask | chain | write-out): " +
+      " | ".join("%.0f" % v for v in acc / 50))

@@ -256,6 +256,63 @@ def test_reference_api_host_arrays_equal_device_path_and_threads(model, params):
             assert keep == orc.cpu_nms(dets, 0.3)
 
 
+def test_caller_nms_handoff_equals_standalone_and_falls_back(model):
+    """forward.py:48-57 calls cpu_nms(hstack(bbox_pred[:, 4c:4c+4], cls_score[:, c]), 0.3) per class after model(x, img_info).
+    A model with caller_nms_thresh (default 0.3) runs that NMS inside the image's graph and models.cpu_nms hands the keep
+    list over when it is called on exactly those rows: the result must equal the standalone kernel and the oracle for every
+    class, and every deviation of the input (other rows, other threshold, mutated arrays, hand-off disabled) must take
+    the standalone path and still be right."""
+    from chainer import Variable
+    import models.cpu_nms as cn
+    H, W = 150, 201
+    info = Variable(np.array([[H, W]], np.int32))
+    assert model.caller_nms_thresh == 0.3
+    cls, box = model(Variable(orc.make_image(H, W, seed=71)), info)
+    prob = cls.data
+    R = prob.shape[0]
+    assert R > 20
+
+    def dets_of(c):
+        return np.hstack((box[:, 4 * c:4 * c + 4], prob[:, c][:, np.newaxis]))
+    s0 = dict(cn.stats)
+    handed = [cn.cpu_nms(dets_of(c), 0.3) for c in range(1, 21)]
+    assert cn.stats["handoff"] - s0["handoff"] == 20 and cn.stats["standalone"] == s0["standalone"]
+    cn.HANDOFF = False
+    try:
+        alone = [cn.cpu_nms(dets_of(c), 0.3) for c in range(1, 21)]
+    finally:
+        cn.HANDOFF = True
+    assert cn.stats["standalone"] - s0["standalone"] == 20
+    for c in range(1, 21):
+        assert handed[c - 1] == alone[c - 1] == orc.cpu_nms(dets_of(c), 0.3), c
+    assert any(len(k) < R for k in handed)                    # the case suppresses something
+    # out of order and repeated classes are found by content, not by position
+    for c in (20, 3, 3, 11):
+        assert cn.cpu_nms(dets_of(c), 0.3) == alone[c - 1]
+    assert cn.stats["handoff"] - s0["handoff"] == 24
+    s1 = dict(cn.stats)
+    # one changed score, another threshold, fewer rows, a float64-made copy: none of them is the graph's input
+    d = dets_of(5)
+    d[R // 2, 4] = np.nextafter(d[R // 2, 4], np.float32(2))
+    assert cn.cpu_nms(d, 0.3) == orc.cpu_nms(d, 0.3)
+    assert cn.cpu_nms(dets_of(5), 0.5) == orc.cpu_nms(dets_of(5), 0.5)
+    assert cn.cpu_nms(dets_of(5)[:R // 2], 0.3) == orc.cpu_nms(dets_of(5)[:R // 2], 0.3)
+    # the caller scales the returned boxes in place (the model's own copy is not touched by that) and runs NMS on them
+    box *= np.float32(0.5)
+    assert cn.cpu_nms(dets_of(5), 0.3) == orc.cpu_nms(dets_of(5), 0.3)
+    assert cn.stats["handoff"] == s1["handoff"] and cn.stats["standalone"] - s1["standalone"] == 4
+    # switched off on the model: the graph stops at (cls_prob, bbox_pred); same outputs, standalone NMS
+    model.caller_nms_thresh = None
+    try:
+        cls2, box2 = model(Variable(orc.make_image(H, W, seed=71)), info)
+        assert np.array_equal(cls2.data, prob) and np.array_equal(box2 * np.float32(0.5), box)
+        d = np.hstack((box2[:, 4:8], cls2.data[:, 1][:, np.newaxis]))
+        assert cn.cpu_nms(d, 0.3) == alone[0]
+        assert cn.stats["handoff"] == s1["handoff"]
+    finally:
+        model.caller_nms_thresh = 0.3
+
+
 def test_cpu_nms_host_small_and_large_paths_and_threads():
     """models.cpu_nms.cpu_nms on host arrays: n <= 2048 runs as ONE kernel on mapped pinned memory, larger n through the
     chip-wide pipeline; both must equal the oracle (= the reference's cpu_nms.pyx on the golden cases), repeatedly (the
