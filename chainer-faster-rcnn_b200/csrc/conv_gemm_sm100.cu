@@ -39,11 +39,34 @@
 
 namespace frcnn {
 
+// Division by a launch-constant divisor without the ~25-instruction software division the compiler emits for `x / p.field`
+// (every role recomputes the tile coordinates once per tile: five divisions were a fifth of the epilogue's instructions on
+// the 64-channel layers).  Granlund-Montgomery round-up multiplier: exact for every 32-bit unsigned x and d >= 1.
+struct FastDiv {
+    uint32_t m, s1, s2, d;
+};
+__device__ __forceinline__ int fd_div(int x, const FastDiv& f) {
+    const uint32_t q = __umulhi(f.m, (uint32_t)x);
+    return (int)(((((uint32_t)x - q) >> f.s1) + q) >> f.s2);
+}
+static inline FastDiv make_fastdiv(int d_) {
+    FastDiv f;
+    const uint32_t d = d_ > 0 ? (uint32_t)d_ : 1u;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                       // l = ceil(log2 d)
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l - f.s1;
+    f.d = d;
+    return f;
+}
+
 struct ConvParams {
     int H, W, Cout;
     int taps, ksize, cin_blocks;
     int kw, pad_h, pad_w;                // tap -> (r, s) = (tap / kw, tap % kw); A box origin (w0 + s - pad_w, h0 + r - pad_h)
     int TH, TW, tiles_h, tiles_w, n_tiles, num_tiles;
+    FastDiv fd_tiles_w, fd_n_tiles, fd_tiles_per_part;   // set by finish_params() once the three divisors are final
     int num_stages, a_stages, x3, relu, pool;
     int acc_bufs, acc_cols, tmem_cols;   // TMEM ring: acc_bufs buffers of acc_cols columns (x3: main | correction)
     // long-K GEMMs (fc6: K = 25,088 .. 100,352): the tensor core's fp32 accumulator truncates on every add, an error that
@@ -245,11 +268,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 }
             }
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-                const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
-                const int nt = t2 % p.n_tiles;
-                const int mt = (t2 / p.n_tiles) * CG + (int)rank;      // an out-of-range tile of an odd pair loads zeros, stores nothing
-                const int h0 = (mt / p.tiles_w) * p.TH;
-                const int w0 = (mt % p.tiles_w) * p.TW;
+                const int part = fd_div(tile, p.fd_tiles_per_part), t2 = tile - part * p.tiles_per_part;
+                const int mq = fd_div(t2, p.fd_n_tiles), nt = t2 - mq * p.n_tiles;
+                const int mt = mq * CG + (int)rank;      // an out-of-range tile of an odd pair loads zeros, stores nothing
+                const int th_i = fd_div(mt, p.fd_tiles_w);
+                const int h0 = th_i * p.TH;
+                const int w0 = (mt - th_i * p.tiles_w) * p.TW;
                 const int n0 = nt * BN + (int)rank * (BN / CG);        // this CTA's half of the weight tile
                 if constexpr (HALO) {
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
@@ -347,7 +371,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 if (++acc == p.acc_bufs) { acc = 0; acc_phase ^= 1; }
                 continue;
             }
-            const int nkb = part_kblocks(p, tile / p.tiles_per_part, num_kb);
+            const int nkb = part_kblocks(p, fd_div(tile, p.fd_tiles_per_part), num_kb);
             for (int kb = 0; kb < nkb; ++kb) {
                 ptx::mbar_wait(&full_bar[stage], phase);
                 ptx::tc_fence_after();
@@ -390,17 +414,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int lg = warp & 3;                 // TMEM lane group this warp may access
         const int grp = (warp - 2) >> 2;         // epilogue group 0 / 1
         const int row = lg * 32 + lane;          // accumulator row == pixel within the tile
+        const int row_h = row / p.TW, row_w = row - row_h * p.TW;     // its position inside the TH x TW patch (once per kernel)
         const int m_valid = p.m_valid ? *p.m_valid : 0x7fffffff;
         const bool issuer = (warp == 2 + 4 * grp && lane == 0);     // the group's thread that owns its bulk-store groups
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-            const int part = tile / p.tiles_per_part, t2 = tile - part * p.tiles_per_part;
-            const int nt = t2 % p.n_tiles;
-            const int mt = (t2 / p.n_tiles) * CG + (int)rank;
-            const int h0 = (mt / p.tiles_w) * p.TH, w0 = (mt % p.tiles_w) * p.TW;
-            const int h = h0 + row / p.TW;
-            const int w = w0 + row % p.TW;
+            const int part = fd_div(tile, p.fd_tiles_per_part), t2 = tile - part * p.tiles_per_part;
+            const int mq = fd_div(t2, p.fd_n_tiles), nt = t2 - mq * p.n_tiles;
+            const int mt = mq * CG + (int)rank;
+            const int th_i = fd_div(mt, p.fd_tiles_w);
+            const int h0 = th_i * p.TH, w0 = (mt - th_i * p.tiles_w) * p.TW;
+            const int h = h0 + row_h;
+            const int w = w0 + row_w;
             const int n0 = nt * BN;
             const bool in_img = (h < p.H) && (w < p.W);
             const long pix = (long)h * p.W + w;
@@ -501,7 +527,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         }
                         writer = (lane & (1 | tw_mask)) == 0;
                         // pooled tile is (TH/2) x (TW/2): row-major index of this thread's window
-                        srow = ((row / p.TW) >> 1) * (p.TW >> 1) + ((row % p.TW) >> 1);
+                        srow = (row_h >> 1) * (p.TW >> 1) + (row_w >> 1);
                     }
                     // stage64 (Cout % 64 == 0): the two groups' 32-channel chunks are the two halves of ONE staging tile with
                     // 128-byte rows (SWIZZLE_128B) and leave in one bulk store per plane: half as many (twice as long) rows for
@@ -518,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     if (writer) {
                         if (s64) {
                             const int sw = srow & 7;               // SWIZZLE_128B: 16-B chunk index ^= address bits [7:9]
-                            uint8_t* rowp = sb + srow * 128;
+                            const uint32_t rowp = ptx::smem_u32(sb) + (uint32_t)(srow * 128);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 float ra[8];
@@ -528,7 +554,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                                 hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
                                 hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
                                 const int c16 = (grp * 4 + q) ^ sw;
-                                *reinterpret_cast<uint4*>(rowp + (c16 << 4)) = hv;
+                                ptx::st_shared_v4(rowp + (uint32_t)(c16 << 4), hv);
                                 if (p.store_lo) {
                                     float d0, d1;
                                     uint4 lv;
@@ -536,12 +562,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                                     lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
                                     lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
                                     lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
-                                    *reinterpret_cast<uint4*>(rowp + 2 * kStagePlane + (c16 << 4)) = lv;
+                                    ptx::st_shared_v4(rowp + (uint32_t)(2 * kStagePlane + (c16 << 4)), lv);
                                 }
                             }
                         } else {
                             const int sw = (srow >> 1) & 3;        // SWIZZLE_64B: 16-B chunk index ^= address bits [7:8]
-                            uint8_t* rowp = sb + srow * 64;
+                            const uint32_t rowp = ptx::smem_u32(sb) + (uint32_t)(srow * 64);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 float ra[8];
@@ -550,7 +576,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                                 hv.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3], ra[2], ra[3]);
                                 hv.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5], ra[4], ra[5]);
                                 hv.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7], ra[6], ra[7]);
-                                *reinterpret_cast<uint4*>(rowp + ((q ^ sw) << 4)) = hv;
+                                ptx::st_shared_v4(rowp + (uint32_t)((q ^ sw) << 4), hv);
                                 if (p.store_lo) {
                                     float d0, d1;
                                     uint4 lv;
@@ -558,7 +584,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                                     lv.y = pack_bf16x2(ra[2], ra[3], d0, d1);
                                     lv.z = pack_bf16x2(ra[4], ra[5], d0, d1);
                                     lv.w = pack_bf16x2(ra[6], ra[7], d0, d1);
-                                    *reinterpret_cast<uint4*>(rowp + kStagePlane + ((q ^ sw) << 4)) = lv;
+                                    ptx::st_shared_v4(rowp + (uint32_t)(kStagePlane + ((q ^ sw) << 4)), lv);
                                 }
                             }
                         }
@@ -701,6 +727,9 @@ static int device_sm_count() {
 template <int BN, int BK, bool HALO, int CG>
 static int launch_conv(const CUtensorMap* tm, ConvParams p, cudaStream_t stream) {
     using C = Cfg<BN, BK, CG>;
+    p.fd_tiles_w = make_fastdiv(p.tiles_w);
+    p.fd_n_tiles = make_fastdiv(p.n_tiles);
+    p.fd_tiles_per_part = make_fastdiv(p.tiles_per_part);
     const int planes = p.x3 ? 2 : 1;
     const bool bres = !HALO && p.b_res != 0;
     const int bres_bytes = bres ? p.taps * p.cin_blocks * planes * C::B_BYTES : 0;

@@ -390,66 +390,74 @@ struct ScanArgs {
 __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
     grid_dep_wait();
     extern __shared__ unsigned long long removed[];   // [col_blocks]
-    __shared__ int s_keep[64];
+    __shared__ unsigned long long tile[256][4];       // the current super-block's rows x its own four 64-column words
+    __shared__ int s_keep[256];
     __shared__ int s_nk, s_total;
     __shared__ int s_keep_all[2048];                  // positions of the first 2048 survivors (for the gather)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n_ptr ? min(*a.n_ptr, a.n_cap) : a.n_cap;
     const int nb = (n + 63) / 64;
+    const int nsb = (nb + 3) / 4;
     const int limit = a.max_keep > 0 ? a.max_keep : 0x7fffffff;
     for (int w = tid; w < a.col_blocks; w += blockDim.x) removed[w] = 0ull;
     if (tid == 0) s_total = 0;
-    // The diagonal words (the bits inside a row's own 64-block) of the block being resolved are held by warp 0 in
-    // registers -- lane holds rows `lane` and `lane + 32` -- and the NEXT block's are requested before the current block
-    // is resolved, so their L2 latency hides behind the resolve + fold of the current one.  (The first version copied all
-    // n diagonal words to shared memory up front: 6000 scattered loads = 9 us before the first block could start.)
-    unsigned long long nd0 = 0ull, nd1 = 0ull;
-    if (warp == 0 && nb > 0) {
-        const int rows0 = min(64, n);
-        if (lane < rows0) nd0 = a.mask[(long)lane * a.col_blocks];
-        if (lane + 32 < rows0) nd1 = a.mask[(long)(lane + 32) * a.col_blocks];
-    }
+    // The greedy chain is serial in the 64-row blocks, and every step that has to wait for L2 (the kept rows' mask words for
+    // the blocks ahead) costs ~0.7 us: with one such step per block the scan took 75 us on 94 blocks.  Here FOUR blocks form
+    // a super-block: its 256 x 256-bit corner of the mask (8 KB) is staged in shared memory -- requested one super-block
+    // ahead, so that latency is off the chain -- and warp 0 resolves all four blocks from shared memory alone; only the fold
+    // of the super-block's kept rows into the words beyond it goes to L2, once per 256 rows.
+    unsigned long long pf[4];
+    auto request = [&](int sb) {                      // thread t: row sb*256 + t, words 4sb .. 4sb+3
+        const long row = (long)sb * 256 + tid;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int w = 4 * sb + j;
+            pf[j] = (row < n && w < nb) ? a.mask[row * a.col_blocks + w] : 0ull;
+        }
+    };
+    if (nsb > 0) request(0);
     __syncthreads();
 
-    for (int blk = 0; blk < nb; ++blk) {
+    for (int sb = 0; sb < nsb; ++sb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[tid][j] = pf[j];
+        __syncthreads();
+        if (sb + 1 < nsb) request(sb + 1);            // in flight while this super-block is resolved and folded
         if (warp == 0) {
-            const int rows = min(64, n - blk * 64);
-            const unsigned long long d0 = nd0, d1 = nd1;
-            if (blk + 1 < nb) {                          // prefetch the next block's diagonal words
-                const int rn = min(64, n - (blk + 1) * 64);
-                nd0 = lane < rn ? a.mask[(long)((blk + 1) * 64 + lane) * a.col_blocks + blk + 1] : 0ull;
-                nd1 = lane + 32 < rn ? a.mask[(long)((blk + 1) * 64 + lane + 32) * a.col_blocks + blk + 1] : 0ull;
-            }
-            unsigned long long cand = ~removed[blk];
-            if (rows < 64) cand &= (1ull << rows) - 1ull;
             int total = s_total, nk = 0;
-            while (cand != 0ull && total < limit) {
-                const int i = __ffsll((long long)cand) - 1;
-                if (lane == 0) {
-                    s_keep[nk] = i;
-                    const int pos = blk * 64 + i;
-                    if (a.keep_out) a.keep_out[total] = a.index_map ? a.index_map[pos] : pos;
-                    if (total < 2048) s_keep_all[total] = pos;
+            for (int j = 0; j < 4 && 4 * sb + j < nb && total < limit; ++j) {
+                const int blk = 4 * sb + j;
+                const int rows = min(64, n - blk * 64);
+                unsigned long long cand = ~removed[blk];
+                if (rows < 64) cand &= (1ull << rows) - 1ull;
+                while (cand != 0ull && total < limit) {
+                    const int i = __ffsll((long long)cand) - 1;
+                    const int lr = 64 * j + i;                      // row inside the super-block
+                    if (lane == 0) {
+                        s_keep[nk] = lr;
+                        const int pos = blk * 64 + i;
+                        if (a.keep_out) a.keep_out[total] = a.index_map ? a.index_map[pos] : pos;
+                        if (total < 2048) s_keep_all[total] = pos;
+                    }
+                    ++nk;
+                    ++total;
+                    cand &= ~tile[lr][j];
+                    cand &= ~(1ull << i);
+                    if (lane > j && lane < 4 && 4 * sb + lane < nb) removed[4 * sb + lane] |= tile[lr][lane];    // later blocks of this super-block
                 }
-                ++nk;
-                ++total;
-                const unsigned long long di = (i < 32) ? __shfl_sync(0xffffffffu, d0, i) : __shfl_sync(0xffffffffu, d1, i - 32);
-                cand &= ~di;
-                cand &= ~(1ull << i);
+                __syncwarp();                    // lanes 1..3's words are read by every lane in the next round
             }
-            __syncwarp();                    // every lane has read s_total (above) before lane 0 overwrites it
             if (lane == 0) { s_nk = nk; s_total = total; }
         }
         __syncthreads();
         const int nk = s_nk;
         if (s_total >= limit) break;
-        // Fold the kept rows of this block into `removed` for the blocks still ahead: nk x (nb - blk - 1) mask words, spread
-        // over ALL threads (item = (kept row, word)), 8 independent loads in flight per thread, OR-ed into shared memory
-        // with atomics.  (The first version gave each of the <= 93 words to one thread, which then chained up to 16 L2 round
-        // trips per block: 11 us of the 12 us a block cost.)
-        const int W = nb - blk - 1;
-        const int items = nk * W;
-        const unsigned long long* base = a.mask + (long)(blk * 64) * a.col_blocks + blk + 1;
+        // Fold the kept rows of this super-block into `removed` for the blocks beyond it: nk x W mask words, spread over ALL
+        // threads (item = (kept row, word)), 8 independent loads in flight per thread, OR-ed into shared memory with atomics.
+        const int w0 = 4 * (sb + 1);
+        const int W = nb - w0;
+        const int items = W > 0 ? nk * W : 0;
+        const unsigned long long* base = a.mask + (long)(sb * 256) * a.col_blocks + w0;
         for (int it0 = tid; it0 < items; it0 += 8 * 256) {
             unsigned long long m[8];
             int wv[8];
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(256, 1) nms_scan_kernel(const ScanArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (m[u] != 0ull) atomicOr(&removed[blk + 1 + wv[u]], m[u]);
+                if (m[u] != 0ull) atomicOr(&removed[w0 + wv[u]], m[u]);
         }
         __syncthreads();
     }
