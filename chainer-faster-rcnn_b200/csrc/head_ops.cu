@@ -400,7 +400,8 @@ __global__ void head_decode_kernel(const float* scores, const float* deltas, int
 // cpu_nms arithmetic), and ONE warp walks the rows in rank order keeping `removed` in registers (lane w owns word w, a
 // second pass for R > 2048/... never needed: R <= 2048 = 32 words) -- the greedy chain costs a shuffle + a few ALU ops per
 // row instead of a block-wide barrier per kept box (the first version: 85 us for 300 rows; this one: ~12 us).
-constexpr int kDetThreads = 256;
+constexpr int kDetThreads = 256;                      // detect_barrier_kernel
+constexpr int kDetMaskThreads = 1024;                 // detect_kernel: 20 CTAs on 148 SMs -- the rank and mask phases scale with the CTA
 constexpr int kDetMaxR = 2048;
 
 __device__ __forceinline__ float det_iou(const float4 a, const float4 b) {
@@ -413,7 +414,7 @@ __device__ __forceinline__ float det_iou(const float4 a, const float4 b) {
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
-__global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, const float* boxes, const int* count,
+__global__ void __launch_bounds__(kDetMaskThreads) detect_kernel(const float* prob, const float* boxes, const int* count,
                                                              int R_cap, int NC, double thr, float conf,
                                                              int* keep_idx, int* keep_count, int* conf_count) {
     grid_dep_wait();
@@ -424,10 +425,21 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, 
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(sbox + R_cap);   // [R_cap][words]: row i = who i suppresses
     float* sc = reinterpret_cast<float*>(mask + (size_t)R_cap * words);               // [R_cap] scores by roi
     int* order = reinterpret_cast<int*>(sc + R_cap);                 // [R_cap] roi index by rank
+    __shared__ int s_nge;                                            // rows with score >= conf: ranks [0, s_nge) after the sort
     const int cls = blockIdx.x + 1, tid = threadIdx.x;
-    for (int r = tid; r < R; r += kDetThreads) sc[r] = prob[(long)r * NC + cls];
+    if (tid == 0) s_nge = 0;
     __syncthreads();
-    for (int r = tid; r < R; r += kDetThreads) {
+    {
+        int nge = 0;
+        for (int r = tid; r < R; r += kDetMaskThreads) {
+            const float s = prob[(long)r * NC + cls];
+            sc[r] = s;
+            nge += s >= conf;
+        }
+        if (nge) atomicAdd(&s_nge, nge);
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += kDetMaskThreads) {
         const float s = sc[r];
         int rank = 0;
         for (int q = 0; q < R; ++q) {
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, 
     const float thr_f = (float)thr;
     const float thr_lo = thr_f * (1.0f - 1e-5f), thr_hi = thr_f * (1.0f + 1e-5f);
     const bool fast_ok = thr_f > 1e-3f;
-    for (int it = tid; it < R * nw; it += kDetThreads) {
+    for (int it = tid; it < R * nw; it += kDetMaskThreads) {
         const int w = it / R, i = it - w * R;
         unsigned long long bits = 0ull;
         if (w >= (i >> 6)) {
@@ -475,15 +487,33 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const float* prob, 
     __syncthreads();
     if (tid < 32) {
         const int lane = tid;
+        const int n_ge = s_nge;
         unsigned long long removed = 0ull;                // lane w: suppression state of ranks [64w, 64w+64)
         int nk = 0, nconf = 0;
-        for (int i = 0; i < R; ++i) {
-            const unsigned long long word = __shfl_sync(0xffffffffu, removed, i >> 6);
-            if ((word >> (i & 63)) & 1ull) continue;      // warp-uniform
-            if (lane == 0) keep_idx[(long)(cls - 1) * R_cap + nk] = order[i];
-            ++nk;
-            if (sc[order[i]] >= conf) nconf = nk;
-            if (lane < nw) removed |= mask[(size_t)i * words + lane];
+        // The loop-carried chain is removed -> shuffle -> bit test -> OR.  The row's mask word and its RoI index do not depend on
+        // it: they are loaded four rows ahead, so that no shared-memory latency sits on the chain (it did: a load issued after
+        // the test stalls the in-order warp at its first use, ~2x the chain itself).  "score >= conf" of the kept row is a rank
+        // comparison: the rows are sorted by descending score, so the rows with score >= conf are exactly ranks [0, n_ge).
+        for (int i0 = 0; i0 < R; i0 += 4) {
+            unsigned long long m[4];
+            int o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                m[k] = (i < R && lane < nw) ? mask[(size_t)i * words + lane] : 0ull;
+                o[k] = i < R ? order[i] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                if (i >= R) break;                        // warp-uniform
+                const unsigned long long word = __shfl_sync(0xffffffffu, removed, i >> 6);
+                if ((word >> (i & 63)) & 1ull) continue;  // warp-uniform
+                if (lane == 0) keep_idx[(long)(cls - 1) * R_cap + nk] = o[k];
+                ++nk;
+                if (i < n_ge) nconf = nk;
+                removed |= m[k];
+            }
         }
         for (int k = nk + lane; k < R_cap; k += 32) keep_idx[(long)(cls - 1) * R_cap + k] = -1;
         if (lane == 0) {
@@ -777,7 +807,7 @@ extern "C" int frcnn_detect(const float* prob, const float* boxes, const int* co
         return FRCNN_OK;
     }
     FRCNN_CUDA_OK(cudaFuncSetAttribute(detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FRCNN_CUDA_OK(launch_pdl(detect_kernel, dim3(num_classes - 1), dim3(kDetThreads), smem, (cudaStream_t)stream, prob, boxes,
+    FRCNN_CUDA_OK(launch_pdl(detect_kernel, dim3(num_classes - 1), dim3(kDetMaskThreads), smem, (cudaStream_t)stream, prob, boxes,
                              count, R_cap, num_classes, nms_thresh, conf, keep_idx, keep_count, conf_count));
     return FRCNN_OK;
 }

@@ -339,13 +339,19 @@ def test_maxpool_ceil(ops, precision):
     assert got.shape == (64, 19, 32) and np.array_equal(got, want)
 
 
+# (C, H, W): 64 = half a 128-channel slice of the window-staged kernel, 192 = one and a half, 512 = the headline trunk,
+# W = 100 > 96 = the per-bin gather kernel that wide feature maps keep; "neg" = features that are NOT clipped at zero
+# (an all-negative window must give its negative maximum, an empty bin 0)
+@pytest.mark.parametrize("shape", [(64, 38, 63, "relu"), (192, 21, 33, "neg"), (512, 38, 63, "relu"), (64, 30, 100, "neg")])
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
-def test_roi_pool_exact(ops, precision):
+def test_roi_pool_exact(ops, precision, shape):
     rng = np.random.default_rng(5)
-    C, H, W, R_cap, R = 64, 38, 63, 300, 257
-    feat = np.maximum(rng.standard_normal((C, H, W)), 0).astype(f32)
+    C, H, W, kind = shape
+    R_cap, R = 300, 257
+    feat = rng.standard_normal((C, H, W)).astype(f32)
+    feat = np.maximum(feat, 0) if kind == "relu" else feat - 1.0
     q = _quant16 if precision == "bf16x3" else _bf16
-    xy = rng.uniform(-20, 980, size=(R_cap, 2))
+    xy = rng.uniform(-20, [16 * W - 28, 16 * H - 28], size=(R_cap, 2))
     wh = rng.uniform(1, 500, size=(R_cap, 2))
     rois = np.hstack([xy, xy + wh]).astype(f32)
     rois[:6] = [[0, 0, 999, 599], [8, 8, 8, 8], [24, 40, 24, 40], [990, 590, 999, 599], [0, 0, 15, 15], [-30, -30, 5, 5]]
