@@ -421,10 +421,11 @@ __global__ void __launch_bounds__(kDetMaskThreads) detect_kernel(const float* pr
     extern __shared__ __align__(16) unsigned char dsm[];
     const int R = count ? min(*count, R_cap) : R_cap;
     const int words = (R_cap + 63) >> 6;                             // uint64 words per mask row
-    float4* sbox = reinterpret_cast<float4*>(dsm);                   // [R_cap] boxes by rank
-    unsigned long long* mask = reinterpret_cast<unsigned long long*>(sbox + R_cap);   // [R_cap][words]: row i = who i suppresses
+    float4* sbox = reinterpret_cast<float4*>(dsm);                   // [64*words] boxes by rank (entries >= R are never used: masked)
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(sbox + 64 * words);   // [R_cap][words]: row i = who i suppresses
     float* sc = reinterpret_cast<float*>(mask + (size_t)R_cap * words);               // [R_cap] scores by roi
     int* order = reinterpret_cast<int*>(sc + R_cap);                 // [R_cap] roi index by rank
+    float* sarea = reinterpret_cast<float*>(order + R_cap);          // [64*words] box areas by rank
     __shared__ int s_nge;                                            // rows with score >= conf: ranks [0, s_nge) after the sort
     const int cls = blockIdx.x + 1, tid = threadIdx.x;
     if (tid == 0) s_nge = 0;
@@ -447,14 +448,18 @@ __global__ void __launch_bounds__(kDetMaskThreads) detect_kernel(const float* pr
             rank += (t > s) || (t == s && q < r);
         }
         order[rank] = r;
-        sbox[rank] = reinterpret_cast<const float4*>(boxes)[(long)r * NC + cls];
+        const float4 b = reinterpret_cast<const float4*>(boxes)[(long)r * NC + cls];
+        sbox[rank] = b;
+        sarea[rank] = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
     }
     __syncthreads();
     // mask rows: item = (word w, row i) with w >= i/64 (upper triangle), i fastest: the lanes of a warp work on consecutive
     // rows i against the SAME 64 columns, so sbox[j] is a broadcast read and sbox[i] a conflict-free one (with w fastest the
-    // lanes read 5 different boxes 1 KB apart = the same banks: measured 4x slower).  The decision "iou >= thr" is taken
-    // with products wherever that is provably the same decision as the reference's divide + double compare
-    // (models/cpu_nms.pyx:64-65); only within 1e-5 of the threshold the exact sequence runs (as in nms_mask_kernel).
+    // lanes read 5 different boxes 1 KB apart = the same banks: measured 4x slower).  The 64-pair loop is straight-line code
+    // (as in nms_mask_kernel): the decision "iou >= thr" is taken with products wherever that is provably the same decision
+    // as the reference's divide + double compare (models/cpu_nms.pyx:64-65); the pairs the products cannot decide (within
+    // 1e-5 of the threshold, a non-positive union) are recorded in a second word and take the exact sequence after the loop.
+    // Columns past R hold whatever the shared memory held: their bits are masked off, never used.
     const int nw = (R + 63) >> 6;
     const float thr_f = (float)thr;
     const float thr_lo = thr_f * (1.0f - 1e-5f), thr_hi = thr_f * (1.0f + 1e-5f);
@@ -464,22 +469,32 @@ __global__ void __launch_bounds__(kDetMaskThreads) detect_kernel(const float* pr
         unsigned long long bits = 0ull;
         if (w >= (i >> 6)) {
             const float4 a = sbox[i];
-            const float area_a = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
-            const int j0 = w << 6, j1 = min(R, j0 + 64);
-            for (int j = max(j0, i + 1); j < j1; ++j) {
-                const float4 b = sbox[j];
+            const float area_a = sarea[i];
+            const int j0 = w << 6;
+            uint32_t sup_w[2] = {0u, 0u}, und_w[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float4 b = sbox[j0 + j];
                 const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
                 const float ww = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
                 const float hh = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
                 const float inter = __fmul_rn(ww, hh);
-                if (fast_ok && inter == 0.0f) continue;
-                const float area_b = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
-                const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
-                bool sup;
-                if (fast_ok && uni > 0.0f && inter > thr_hi * uni) sup = true;
-                else if (fast_ok && uni > 0.0f && inter < thr_lo * uni) sup = false;
-                else sup = (double)__fdiv_rn(inter, uni) >= thr;
-                if (sup) bits |= 1ull << (j - j0);
+                const float uni = __fsub_rn(__fadd_rn(area_a, sarea[j0 + j]), inter);
+                const bool pos = uni > 0.0f;
+                const bool yes = pos && inter > thr_hi * uni, no = pos && inter < thr_lo * uni;
+                sup_w[j >> 5] |= (uint32_t)yes << (j & 31);
+                und_w[j >> 5] |= (uint32_t)!(yes || no) << (j & 31);
+            }
+            const int lo = max(i + 1 - j0, 0), hi = min(R - j0, 64);              // live columns [lo, hi) of this word
+            unsigned long long live = hi < 64 ? (1ull << hi) - 1ull : ~0ull;
+            live = lo < 64 ? (live >> lo) << lo : 0ull;
+            bits = ((unsigned long long)sup_w[0] | ((unsigned long long)sup_w[1] << 32)) & live;
+            unsigned long long und = fast_ok ? ((unsigned long long)und_w[0] | ((unsigned long long)und_w[1] << 32)) & live : live;
+            while (und != 0ull) {                                                 // rare: the reference's exact sequence
+                const int j = __ffsll((long long)und) - 1;
+                und &= und - 1ull;
+                const bool sup = (double)det_iou(a, sbox[j0 + j]) >= thr;
+                bits = sup ? (bits | (1ull << j)) : (bits & ~(1ull << j));
             }
         }
         mask[(size_t)i * words + w] = bits;
@@ -798,7 +813,7 @@ extern "C" int frcnn_detect(const float* prob, const float* boxes, const int* co
     FRCNN_REQUIRE(prob && boxes && keep_idx && keep_count && conf_count && num_classes > 1, "frcnn_detect: bad arguments");
     FRCNN_REQUIRE(R_cap > 0 && R_cap <= kDetMaxR, "frcnn_detect: R_cap must be in [1,%d] (got %d)", kDetMaxR, R_cap);
     const size_t words = (size_t)(R_cap + 63) / 64;
-    size_t smem = (size_t)R_cap * (sizeof(float) + sizeof(int) + sizeof(float4) + 8 * words) + 16;
+    size_t smem = (size_t)R_cap * (sizeof(float) + sizeof(int) + 8 * words) + 64 * words * (sizeof(float4) + sizeof(float)) + 16;
     if (smem > 200 * 1024) {
         smem = (size_t)R_cap * (sizeof(float) + sizeof(int) + sizeof(float4) + 1) + 16;
         FRCNN_CUDA_OK(cudaFuncSetAttribute(detect_barrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
