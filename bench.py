@@ -200,6 +200,25 @@ def run_reference_arm(args, rank):
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
+def hbm_fractions(tj, table, peak_hbm):
+    """Per-kernel HBM fractions: DRAM bytes of each launch from the ncu pass of this binary
+    (profiles/r02_conv_stack_dram.json) over the launch's LIVE CUDA-event time where bench.py times it (the GEMM launches:
+    same order as `table`), else over its duration under ncu (cold caches, serialised)."""
+    out = {}
+    gl = tj.get("gemm_launches") or []
+    if len(gl) == len(table):
+        for name, idx in (("conv1_1", 0), ("conv1_2", 1), ("fc6", len(table) - 3), ("fc7", len(table) - 2)):
+            mb, ms = gl[idx]["dram_mb"], table[idx][1]
+            out[name] = {"dram_mb_ncu": mb, "ms_live": round(ms, 4), "gbs": round(mb / ms, 1),
+                         "frac_of_hbm_peak": round(mb / ms / peak_hbm, 3)}
+    for name, key in (("pack_image_c8", "frcnn::pack_image_c8_kernel"), ("roi_pool", "frcnn::roi_pool_kernel")):
+        e = (tj.get("per_kernel") or {}).get(key)
+        if e:
+            out[name] = {"dram_mb_ncu": e["dram_mb"], "us_under_ncu": e["us"], "gbs": round(e["dram_mb"] / e["us"] * 1e3, 1),
+                         "frac_of_hbm_peak": round(e["dram_mb"] / e["us"] * 1e3 / peak_hbm, 3)}
+    return out
+
+
 def conv_layer_table(plan, torch, reps=3, spin=True):
     """Per-launch device time of the tensor-core kernel over one forward: eager re-run with CUDA events around each
     frcnn_conv2d / frcnn_linear call (same stream, same buffers).  Returns [(name, ms, gflop)].  (frcnn_linear = the
@@ -608,12 +627,13 @@ def run_b200_arm(args, rank, local_rank, world):
     conv_ms = sum(r[1] for r in conv_rows)
     all_ms = sum(r[1] for r in table)
     exec_mult = 3.0 if args.precision == "bf16x3" else 1.0
-    traffic, traffic_src = None, None
+    traffic, traffic_src, hbm_frac = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r02_conv_stack_dram.json")
     if args.precision == "bf16x3" and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj["conv_stack_dram_bytes_per_step"], tj["source"]
+        hbm_frac = hbm_fractions(tj, table, peak_hbm)
     achieved = CONV_STACK_GFLOP / conv_ms          # GFLOP/ms == TFLOP/s (algorithmic flops)
     sus_ips = n_sus / (ms_sus / 1e3)               # per rank set: all ranks ran n_sus images in ms_sus
     roofline = {
@@ -637,6 +657,7 @@ def run_b200_arm(args, rank, local_rank, world):
         # once, weights (17.1 M params, hi+lo) read once: 1.02 GB
         "algorithmic_bytes_per_step": 1.02e9 if args.precision == "bf16x3" else 0.51e9,
         "hbm_peak_gbs": peak_hbm,
+        "hbm_fractions": hbm_frac,   # per-kernel DRAM GB/s over the HBM peak for the kernels that move the most bytes
         "layers": [{"shape": n, "ms": round(m, 4), "tflops_algorithmic": round(g / m, 1)} for n, m, g in table],
     }
 

@@ -51,11 +51,15 @@ def main():
         e["launches"] += 1
         e["us"] += r["gpu__time_duration.sum"]
         e["dram_mb"] += (r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"]) / 1e6
+    gemms = [{"kernel": r["name"].split("(")[0].replace("void frcnn::", ""), "us_under_ncu": round(r["gpu__time_duration.sum"], 1),
+              "dram_mb": round((r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"]) / 1e6, 1)}
+             for r in img if "conv_gemm_kernel" in r["name"]]
     res = {
         "conv_stack_dram_bytes_per_step": dram,
         "conv_stack_launches": len(conv),
         "conv_stack_time_share_under_ncu": t_conv / t_all,
         "launches_per_image": len(img),
+        "gemm_launches": gemms,        # in launch order = the order of bench.py's `layers` table
         "per_kernel": {k: {"launches": v["launches"], "us": round(v["us"], 1), "dram_mb": round(v["dram_mb"], 1)} for k, v in per_kernel.items()},
         "source": "profiles/r02_launches_dram_forward.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                   "--clock-control none python tests/gpu_ncu_target.py forward; second forward; binary of git %s)" % git,
