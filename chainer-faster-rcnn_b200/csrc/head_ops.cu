@@ -399,7 +399,7 @@ __global__ void head_decode_kernel(const float* scores, const float* deltas, int
 // a bitmask: every thread fills rows of the R x R/64 "i suppresses j" matrix in shared memory (upper triangle, exact
 // cpu_nms arithmetic), and ONE warp walks the rows in rank order keeping `removed` in registers (lane w owns word w, a
 // second pass for R > 2048/... never needed: R <= 2048 = 32 words) -- the greedy chain costs a shuffle + a few ALU ops per
-// row instead of a block-wide barrier per kept box (the first version: 85 us for 300 rows; this one: ~12 us).
+// row instead of a block-wide barrier per kept box (the first version: 85 us for 300 rows x 20 classes; this one: 40 us).
 constexpr int kDetThreads = 256;                      // detect_barrier_kernel
 constexpr int kDetMaskThreads = 1024;                 // detect_kernel: 20 CTAs on 148 SMs -- the rank and mask phases scale with the CTA
 constexpr int kDetMaxR = 2048;
