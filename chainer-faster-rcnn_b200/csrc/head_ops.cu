@@ -293,8 +293,32 @@ __global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl,
 // version recomputed the rounding / divide / floor / ceil chain in every (bin, 8-channel) thread); then the threads walk
 // (pw, 8 channels) items: consecutive threads = consecutive channel groups of one bin, so a warp reads whole 512-byte pixel rows
 // of the feature map (L2-resident: 4.9 MB) and writes whole output rows.
-constexpr int kRoiThreads = 256, kRoiMaxBins = 32;
-__global__ void __launch_bounds__(kRoiThreads) roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl, int H, int W, int C,
+//
+// The maximum is taken on the PACKED bf16 pairs, not on converted floats.  A feature value is v = hi + lo with hi = RN_bf16(v)
+// and |lo| <= ulp(hi)/2 (split_bf16), and rounding is monotone, so v_a > v_b  <=>  hi_a > hi_b, or hi_a == hi_b and lo_a > lo_b:
+// the maximum of v over a window is the lexicographic maximum of (hi, lo).  Pass 1 folds the hi plane with max.bf16x2 (one
+// instruction per two channels and pixel); pass 2 re-reads the window (L1 hits) and folds lo over the pixels whose hi equals
+// that maximum (set.eq.u32.bf16x2 -> mask, one LOP3 select, max.bf16x2).  The result IS one input pixel's (hi, lo) pair, so it
+// is stored as it is -- the same bits the float formulation produced (max of the floats, then split_bf16 of it: the split of
+// hi + lo gives hi and lo back) at ~30 instead of ~45 instructions per loaded pixel and 8-channel group, and without the
+// 8 float -> bf16 pair conversions per output item: a third fewer instructions issued (less energy on a power-capped part).
+// The kernel's TIME did not move with it (25 -> 26 us): ncu shows no saturated unit (issue slots 57 %, L1 42 %, L2 22 % of
+// peak) -- the time is the dependent chain  bounds -> barrier -> window loads (L2 round trips) -> stores  of 2100 small CTAs
+// (profiles/r02_roi_pool_window_experiment_negative.txt, profiles/r02_ncu_full_roi_pool_details.txt).
+constexpr int kRoiMaxThreads = 256, kRoiMaxBins = 32;   // the CTA size is chosen per launch so that the row's items split into EQUAL rounds
+
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {       // 0xFFFF per half where a == b (as values)
+    uint32_t d;
+    asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+constexpr uint32_t kBf2NegInf = 0xFF80FF80u;
+__global__ void __launch_bounds__(kRoiMaxThreads) roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl, int H, int W, int C,
                                                                const float* rois, const int* count, int R_cap, int PH, int PW,
                                                                float scale, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32) {
     grid_dep_wait();
@@ -324,30 +348,57 @@ __global__ void __launch_bounds__(kRoiThreads) roi_pool_kernel(const __nv_bfloat
         }
         __syncthreads();
         const int items = PW * C8;
-        for (int it = threadIdx.x; it < items; it += kRoiThreads) {
+        for (int it = threadIdx.x; it < items; it += (int)blockDim.x) {
             const int c8 = it % C8, pw = it / C8;
-            F8 m;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m.v[j] = 0.0f;
+            uint4 mh = make_uint4(0u, 0u, 0u, 0u), ml = make_uint4(0u, 0u, 0u, 0u);       // empty bin / row past the count -> 0
             if (valid) {
                 const int hs = s_h[0], he = s_h[1], ws = s_ws[pw], we = s_we[pw];
                 if (he > hs && we > ws) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) m.v[j] = -1e37f;
-                    for (int y = hs; y < he; ++y)
-                        for (int x = ws; x < we; ++x) {
-                            const F8 v = load8(fh, fl, ((long)y * W + x) * C + 8 * c8);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) m.v[j] = v.v[j] > m.v[j] ? v.v[j] : m.v[j];
+                    mh = make_uint4(kBf2NegInf, kBf2NegInf, kBf2NegInf, kBf2NegInf);
+                    for (int y = hs; y < he; ++y) {
+                        const uint4* row = reinterpret_cast<const uint4*>(fh + ((long)y * W + ws) * C + 8 * c8);
+                        for (int x = 0; x < we - ws; ++x) {
+                            const uint4 h = __ldg(row + (long)x * C8);
+                            mh.x = bf2_max(mh.x, h.x);
+                            mh.y = bf2_max(mh.y, h.y);
+                            mh.z = bf2_max(mh.z, h.z);
+                            mh.w = bf2_max(mh.w, h.w);
                         }
+                    }
+                    if (fl) {
+                        ml = make_uint4(kBf2NegInf, kBf2NegInf, kBf2NegInf, kBf2NegInf);
+                        for (int y = hs; y < he; ++y) {
+                            const long o = ((long)y * W + ws) * C + 8 * c8;
+                            const uint4* rh = reinterpret_cast<const uint4*>(fh + o);
+                            const uint4* rl = reinterpret_cast<const uint4*>(fl + o);
+                            for (int x = 0; x < we - ws; ++x) {
+                                const uint4 h = __ldg(rh + (long)x * C8), l = __ldg(rl + (long)x * C8);
+                                uint32_t e;
+                                e = bf2_eq_mask(h.x, mh.x); ml.x = bf2_max(ml.x, (l.x & e) | (kBf2NegInf & ~e));
+                                e = bf2_eq_mask(h.y, mh.y); ml.y = bf2_max(ml.y, (l.y & e) | (kBf2NegInf & ~e));
+                                e = bf2_eq_mask(h.z, mh.z); ml.z = bf2_max(ml.z, (l.z & e) | (kBf2NegInf & ~e));
+                                e = bf2_eq_mask(h.w, mh.w); ml.w = bf2_max(ml.w, (l.w & e) | (kBf2NegInf & ~e));
+                            }
+                        }
+                    }
                 }
             }
             const long off = (((long)r * PH + ph) * PW + pw) * C + 8 * c8;
-            if (oh) store8(oh, ol, off, m);
+            if (oh) {
+                *reinterpret_cast<uint4*>(oh + off) = mh;
+                if (ol) *reinterpret_cast<uint4*>(ol + off) = ml;
+            }
             if (of32) {
+                const uint32_t hw[4] = {mh.x, mh.y, mh.z, mh.w}, lw[4] = {ml.x, ml.y, ml.z, ml.w};
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                        // hi + lo is exact (<= 24 significant bits), as in load8
+                    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                }
                 float4* d = reinterpret_cast<float4*>(of32 + off);
-                d[0] = make_float4(m.v[0], m.v[1], m.v[2], m.v[3]);
-                d[1] = make_float4(m.v[4], m.v[5], m.v[6], m.v[7]);
+                d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                d[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
         __syncthreads();
@@ -739,7 +790,11 @@ extern "C" int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, i
     FRCNN_REQUIRE(!out_lo || out_hi, "frcnn_roi_pool: out_lo without out_hi");
     FRCNN_REQUIRE(outw < kRoiMaxBins, "frcnn_roi_pool: outw must be < %d", kRoiMaxBins);
     const long blocks = (long)R_cap * outh;
-    FRCNN_CUDA_OK(launch_pdl(roi_pool_kernel, dim3((unsigned)(blocks < 148l * 32 ? blocks : 148l * 32)), dim3(kRoiThreads), 0, (cudaStream_t)stream,
+    // CTA size: the row's outw * C/8 items in equal rounds (7 x 64 items: 2 rounds of 224 threads; with 256 threads the second
+    // round ran three-quarters full and the idle warps waited at the row's barrier -- ncu: barrier = the second stall reason)
+    const int items = outw * (C / 8), rounds = (items + kRoiMaxThreads - 1) / kRoiMaxThreads;
+    const int threads = min(kRoiMaxThreads, (((items + rounds - 1) / rounds + 31) / 32) * 32);
+    FRCNN_CUDA_OK(launch_pdl(roi_pool_kernel, dim3((unsigned)(blocks < 148l * 32 ? blocks : 148l * 32)), dim3(threads), 0, (cudaStream_t)stream,
                              (const __nv_bfloat16*)feat_hi, (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw,
                              scale, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32));
     return FRCNN_OK;
