@@ -7,12 +7,19 @@
 Workload (config #2): synthetic 600x1000 image (uniform(0,255) - BGR means), random-init weights
 (heads N(0,0.01), He-normal trunk), test-mode ProposalLayer (6000 -> NMS 0.7 -> 300), 21 classes.
 One step = one image through the whole graph (trunk, RPN, ProposalLayer, RoI pool, fc6/fc7, heads,
-softmax/decode/clip) on each GPU; images shard one per GPU with no collective ("scaling": "weak").
+softmax/decode/clip and the caller's per-class NMS of forward.py:48-57) on each GPU; images shard one per GPU with
+no collective ("scaling": "weak").
 
-Prints ONE JSON line (rank 0).  `value`   : device-timed (CUDA events) images/s, inputs resident in HBM.
-                                `e2e`     : same metric through the public call with a pinned HOST image copied
-                                            H2D and the result copied D2H inside the timed region, every step.
-                                `roofline`: the conv/GEMM tensor-core kernel, timed live per launch.
+Prints ONE JSON line (rank 0).  `value`   : device-timed (CUDA events) images/s, inputs resident in HBM, 4 images in
+                                            flight per GPU (`detail.one_image_in_flight` = the batch-1 latency view).
+                                `e2e`     : the same metric through the REFERENCE's interface, per image inside the timed
+                                            region: models.faster_rcnn.FasterRCNN.__call__ on a HOST float32
+                                            (1,3,600,1000) array (7.2 MB H2D) + the caller's 20 models.cpu_nms.cpu_nms
+                                            calls on host arrays, 8 caller threads; the one-thread number, the
+                                            standalone-NMS numbers and the build's streaming API are reported beside it.
+                                `roofline`: the conv/GEMM tensor-core kernel, timed live per launch (frac vs the burst
+                                            peak), a >= 200-image sustained run (vs the sustained peak), DRAM traffic and
+                                            per-kernel HBM fractions from the committed ncu pass of this binary.
                                 `cpu_baseline`: the CPU oracle pipeline on this box's host cores (rank 0, N=1).
 `--impl reference` times the reference-equivalent CPU pipeline instead (torch-CPU fp32 dense ops standing in for
 Chainer-NumPy -- Chainer is not installable offline -- plus the reference's own compiled cpu_nms.pyx when
