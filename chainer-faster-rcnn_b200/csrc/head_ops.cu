@@ -288,24 +288,20 @@ __global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl,
 }
 
 // ------------------------------------------------------------------------------------------ RoI max pooling
-// One CTA per (RoI, output row ph).  Caffe / Chainer-v1 GPU semantics (see the oracle's orc_roi_pool): round() half away from
-// zero, float32 bin sizes, empty bin -> 0.  The row's h-range and the PW w-ranges are computed ONCE per CTA (the first
-// version recomputed the rounding / divide / floor / ceil chain in every (bin, 8-channel) thread); then the threads walk
-// (pw, 8 channels) items: consecutive threads = consecutive channel groups of one bin, so a warp reads whole 512-byte pixel rows
-// of the feature map (L2-resident: 4.9 MB) and writes whole output rows.
+// Caffe / Chainer-v1 GPU semantics (see the oracle's orc_roi_pool): round() half away from zero, float32 bin sizes, empty
+// bin -> 0.  The bounds of the PH row bands and the PW column bins are computed ONCE per RoI.
 //
 // The maximum is taken on the PACKED bf16 pairs, not on converted floats.  A feature value is v = hi + lo with hi = RN_bf16(v)
 // and |lo| <= ulp(hi)/2 (split_bf16), and rounding is monotone, so v_a > v_b  <=>  hi_a > hi_b, or hi_a == hi_b and lo_a > lo_b:
-// the maximum of v over a window is the lexicographic maximum of (hi, lo).  Pass 1 folds the hi plane with max.bf16x2 (one
-// instruction per two channels and pixel); pass 2 re-reads the window (L1 hits) and folds lo over the pixels whose hi equals
-// that maximum (set.eq.u32.bf16x2 -> mask, one LOP3 select, max.bf16x2).  The result IS one input pixel's (hi, lo) pair, so it
-// is stored as it is -- the same bits the float formulation produced (max of the floats, then split_bf16 of it: the split of
-// hi + lo gives hi and lo back) at ~30 instead of ~45 instructions per loaded pixel and 8-channel group, and without the
-// 8 float -> bf16 pair conversions per output item: a third fewer instructions issued (less energy on a power-capped part).
-// The kernel's TIME did not move with it (25 -> 26 us): ncu shows no saturated unit (issue slots 57 %, L1 42 %, L2 22 % of
-// peak) -- the time is the dependent chain  bounds -> barrier -> window loads (L2 round trips) -> stores  of 2100 small CTAs
-// (profiles/r02_roi_pool_window_experiment_negative.txt, profiles/r02_ncu_full_roi_pool_details.txt).
-constexpr int kRoiMaxThreads = 256, kRoiMaxBins = 32;   // the CTA size is chosen per launch so that the row's items split into EQUAL rounds
+// the maximum of v over a window is the lexicographic maximum of (hi, lo) (max.bf16x2 / set.{gt,eq}.u32.bf16x2 on two
+// channels per instruction).  The result IS one input pixel's (hi, lo) pair, so it is stored as it is -- the same bits the
+// float formulation produced (max of the floats, then split_bf16 of it: the split of hi + lo gives hi and lo back), without
+// the unpack / add per loaded pixel and the 8 float -> bf16 pair conversions per output item.
+//
+// History of this kernel, all variants bit-exact and measured on the same workload (profiles/r02_roi_pool_window_experiment_negative.txt):
+// per-bin gather, float compares 25 us; the same on packed pairs 26 us (a third fewer instructions, same time: ncu shows no
+// saturated unit, a latency chain); bands staged in shared memory with a barrier pair per output row 44 us; this one 21 us.
+constexpr int kRoiMaxBins = 32;
 
 __device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -318,87 +314,147 @@ __device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {       
     return d;
 }
 constexpr uint32_t kBf2NegInf = 0xFF80FF80u;
-__global__ void __launch_bounds__(kRoiMaxThreads) roi_pool_kernel(const __nv_bfloat16* fh, const __nv_bfloat16* fl, int H, int W, int C,
-                                                               const float* rois, const int* count, int R_cap, int PH, int PW,
-                                                               float scale, __nv_bfloat16* oh, __nv_bfloat16* ol, float* of32) {
+
+// Bin-column walker: one CTA per (RoI, channel slice), one thread per (output column pw, 8 channels) -- NO shared-memory
+// staging and no barrier inside the RoI.  The thread walks the window's rows top to bottom ONCE: per row it folds the pixels
+// of its bin's columns [ws, we) into a row value, per output row ph it folds the band's row values, and because band ph+1
+// starts at he[ph] or he[ph]-1 (floor / ceil of the SAME product, see the bounds) the only row two bands can share is the
+// last one folded -- it is kept in registers, so every window row is loaded exactly once per bin column (82 MB of distinct
+// window pixels at the headline workload where a thread per BIN requests 185 MB and re-derives every bin from scratch).  All folds are the lexicographic maximum of the packed (hi, lo) pairs (see above), streaming: h' = max(h, b.h),
+// l' = b.h > h ? b.l : (b.h == h ? max(l, b.l) : l).  Rows are taken two at a time so that a tall RoI's chain of L2 round
+// trips is halved.  All RoIs are resident at once (300 CTAs of 448 threads): the kernel time is the tallest RoI's chain.
+struct Pair8 { uint4 h, l; };
+
+__device__ __forceinline__ void lex_fold(uint32_t& h, uint32_t& l, uint32_t bh, uint32_t bl) {
+    uint32_t gt, eq;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(bh), "r"(h));
+    eq = bf2_eq_mask(bh, h);
+    const uint32_t lm = bf2_max(l, bl);
+    const uint32_t t = (lm & eq) | (l & ~eq);
+    l = (bl & gt) | (t & ~gt);
+    h = bf2_max(h, bh);
+}
+template <bool LO>
+__device__ __forceinline__ void lex_fold8(Pair8& a, const uint4 bh, const uint4 bl) {
+    if (LO) {
+        lex_fold(a.h.x, a.l.x, bh.x, bl.x);
+        lex_fold(a.h.y, a.l.y, bh.y, bl.y);
+        lex_fold(a.h.z, a.l.z, bh.z, bl.z);
+        lex_fold(a.h.w, a.l.w, bh.w, bl.w);
+    } else {
+        a.h.x = bf2_max(a.h.x, bh.x);
+        a.h.y = bf2_max(a.h.y, bh.y);
+        a.h.z = bf2_max(a.h.z, bh.z);
+        a.h.w = bf2_max(a.h.w, bh.w);
+    }
+}
+__device__ __forceinline__ Pair8 pair8_neg_inf() {
+    Pair8 p;
+    p.h = make_uint4(kBf2NegInf, kBf2NegInf, kBf2NegInf, kBf2NegInf);
+    p.l = p.h;
+    return p;
+}
+
+constexpr int kRoiColMaxThreads = 448;        // 7 output columns x 64 channel groups; two CTAs of 72 registers per SM
+template <bool LO>
+__global__ void __launch_bounds__(kRoiColMaxThreads, 2) roi_pool_col_kernel(const __nv_bfloat16* __restrict__ fh, const __nv_bfloat16* __restrict__ fl,
+                                                                         int H, int W, int C, const float* __restrict__ rois,
+                                                                         const int* __restrict__ count, int R_cap, int PH, int PW, float scale,
+                                                                         __nv_bfloat16* __restrict__ oh, __nv_bfloat16* __restrict__ ol,
+                                                                         float* __restrict__ of32, int c8_per_cta, int slices) {
     grid_dep_wait();
-    __shared__ int s_ws[kRoiMaxBins], s_we[kRoiMaxBins], s_h[2];
+    __shared__ int s_ws[kRoiMaxBins], s_we[kRoiMaxBins], s_hs[kRoiMaxBins], s_he[kRoiMaxBins];
     const int C8 = C / 8;
     const int R = count ? min(*count, R_cap) : R_cap;
-    for (int blk = blockIdx.x; blk < R_cap * PH; blk += gridDim.x) {
-        const int r = blk / PH, ph = blk - r * PH;
-        const bool valid = r < R;
-        if (valid && (int)threadIdx.x <= PW) {
+    const int tid = threadIdx.x;
+    const int pw = tid / c8_per_cta, c8l = tid - pw * c8_per_cta;
+    for (int blk = blockIdx.x; blk < R_cap * slices; blk += gridDim.x) {
+        const int r = blk / slices, c8 = (blk - r * slices) * c8_per_cta + c8l;
+        const bool valid = r < R;                            // CTA-uniform
+        if (valid && tid < max(PH, PW)) {                    // the rounding chain of the oracle (orc_roi_pool)
             const float4 roi = reinterpret_cast<const float4*>(rois)[r];
             const int sw = (int)roundf(__fmul_rn(roi.x, scale)), sh = (int)roundf(__fmul_rn(roi.y, scale));
             const int ew = (int)roundf(__fmul_rn(roi.z, scale)), eh = (int)roundf(__fmul_rn(roi.w, scale));
             const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
-            if ((int)threadIdx.x == PW) {
+            if (tid < PH) {
                 const float bh = __fdiv_rn((float)rh, (float)PH);
-                const int hs = (int)floorf(__fmul_rn((float)ph, bh)) + sh, he = (int)ceilf(__fmul_rn((float)(ph + 1), bh)) + sh;
-                s_h[0] = min(max(hs, 0), H);
-                s_h[1] = min(max(he, 0), H);
-            } else {
-                const int pw = threadIdx.x;
+                const int hs = (int)floorf(__fmul_rn((float)tid, bh)) + sh, he = (int)ceilf(__fmul_rn((float)(tid + 1), bh)) + sh;
+                s_hs[tid] = min(max(hs, 0), H);
+                s_he[tid] = min(max(he, 0), H);
+            }
+            if (tid < PW) {
                 const float bw = __fdiv_rn((float)rw, (float)PW);
-                const int ws = (int)floorf(__fmul_rn((float)pw, bw)) + sw, we = (int)ceilf(__fmul_rn((float)(pw + 1), bw)) + sw;
-                s_ws[pw] = min(max(ws, 0), W);
-                s_we[pw] = min(max(we, 0), W);
+                const int ws = (int)floorf(__fmul_rn((float)tid, bw)) + sw, we = (int)ceilf(__fmul_rn((float)(tid + 1), bw)) + sw;
+                s_ws[tid] = min(max(ws, 0), W);
+                s_we[tid] = min(max(we, 0), W);
             }
         }
         __syncthreads();
-        const int items = PW * C8;
-        for (int it = threadIdx.x; it < items; it += (int)blockDim.x) {
-            const int c8 = it % C8, pw = it / C8;
-            uint4 mh = make_uint4(0u, 0u, 0u, 0u), ml = make_uint4(0u, 0u, 0u, 0u);       // empty bin / row past the count -> 0
-            if (valid) {
-                const int hs = s_h[0], he = s_h[1], ws = s_ws[pw], we = s_we[pw];
-                if (he > hs && we > ws) {
-                    mh = make_uint4(kBf2NegInf, kBf2NegInf, kBf2NegInf, kBf2NegInf);
-                    for (int y = hs; y < he; ++y) {
-                        const uint4* row = reinterpret_cast<const uint4*>(fh + ((long)y * W + ws) * C + 8 * c8);
-                        for (int x = 0; x < we - ws; ++x) {
-                            const uint4 h = __ldg(row + (long)x * C8);
-                            mh.x = bf2_max(mh.x, h.x);
-                            mh.y = bf2_max(mh.y, h.y);
-                            mh.z = bf2_max(mh.z, h.z);
-                            mh.w = bf2_max(mh.w, h.w);
-                        }
+        if (pw < PW && c8 < C8) {
+            const int ws = valid ? s_ws[pw] : 0, bwid = valid ? s_we[pw] - ws : 0;
+            int prev_y = -1;                                 // the last row folded, and its row value
+            Pair8 prev = pair8_neg_inf();
+            for (int ph = 0; ph < PH; ++ph) {
+                uint4 mh = make_uint4(0u, 0u, 0u, 0u), ml = mh;          // empty bin / row past the count -> 0
+                const int hs = valid ? s_hs[ph] : 0, he = valid ? s_he[ph] : 0;
+                if (he > hs && bwid > 0) {
+                    Pair8 acc = pair8_neg_inf();
+                    int y = hs;
+                    if (y == prev_y) {                       // the row this band shares with the previous one
+                        acc = prev;
+                        ++y;
                     }
-                    if (fl) {
-                        ml = make_uint4(kBf2NegInf, kBf2NegInf, kBf2NegInf, kBf2NegInf);
-                        for (int y = hs; y < he; ++y) {
-                            const long o = ((long)y * W + ws) * C + 8 * c8;
-                            const uint4* rh = reinterpret_cast<const uint4*>(fh + o);
-                            const uint4* rl = reinterpret_cast<const uint4*>(fl + o);
-                            for (int x = 0; x < we - ws; ++x) {
-                                const uint4 h = __ldg(rh + (long)x * C8), l = __ldg(rl + (long)x * C8);
-                                uint32_t e;
-                                e = bf2_eq_mask(h.x, mh.x); ml.x = bf2_max(ml.x, (l.x & e) | (kBf2NegInf & ~e));
-                                e = bf2_eq_mask(h.y, mh.y); ml.y = bf2_max(ml.y, (l.y & e) | (kBf2NegInf & ~e));
-                                e = bf2_eq_mask(h.z, mh.z); ml.z = bf2_max(ml.z, (l.z & e) | (kBf2NegInf & ~e));
-                                e = bf2_eq_mask(h.w, mh.w); ml.w = bf2_max(ml.w, (l.w & e) | (kBf2NegInf & ~e));
+                    for (; y < he; y += 2) {
+                        const bool two = y + 1 < he;         // warp-uniform
+                        Pair8 ra = pair8_neg_inf(), rb = ra;
+                        const long o = ((long)y * W + ws) * C + 8 * c8;
+                        const uint4* ph0 = reinterpret_cast<const uint4*>(fh + o);
+                        const uint4* pl0 = reinterpret_cast<const uint4*>(LO ? fl + o : fh + o);
+                        const long row = (long)W * C8;       // one image row in uint4 units
+                        if (two) {
+                            for (int x = 0; x < bwid; ++x) {
+                                const uint4 ha = __ldg(ph0 + (long)x * C8), hb = __ldg(ph0 + row + (long)x * C8);
+                                uint4 la = ha, lb = hb;
+                                if (LO) { la = __ldg(pl0 + (long)x * C8); lb = __ldg(pl0 + row + (long)x * C8); }
+                                lex_fold8<LO>(ra, ha, la);
+                                lex_fold8<LO>(rb, hb, lb);
                             }
+                            lex_fold8<LO>(acc, ra.h, ra.l);
+                            lex_fold8<LO>(acc, rb.h, rb.l);
+                            prev = rb;
+                            prev_y = y + 1;
+                        } else {
+                            for (int x = 0; x < bwid; ++x) {
+                                const uint4 ha = __ldg(ph0 + (long)x * C8);
+                                uint4 la = ha;
+                                if (LO) la = __ldg(pl0 + (long)x * C8);
+                                lex_fold8<LO>(ra, ha, la);
+                            }
+                            lex_fold8<LO>(acc, ra.h, ra.l);
+                            prev = ra;
+                            prev_y = y;
                         }
                     }
+                    mh = acc.h;
+                    if (LO) ml = acc.l;
                 }
-            }
-            const long off = (((long)r * PH + ph) * PW + pw) * C + 8 * c8;
-            if (oh) {
-                *reinterpret_cast<uint4*>(oh + off) = mh;
-                if (ol) *reinterpret_cast<uint4*>(ol + off) = ml;
-            }
-            if (of32) {
-                const uint32_t hw[4] = {mh.x, mh.y, mh.z, mh.w}, lw[4] = {ml.x, ml.y, ml.z, ml.w};
-                float v[8];
+                const long off = (((long)r * PH + ph) * PW + pw) * C + 8 * c8;
+                if (oh) {
+                    *reinterpret_cast<uint4*>(oh + off) = mh;
+                    if (ol) *reinterpret_cast<uint4*>(ol + off) = ml;
+                }
+                if (of32) {
+                    const uint32_t hw[4] = {mh.x, mh.y, mh.z, mh.w}, lw[4] = {ml.x, ml.y, ml.z, ml.w};
+                    float v[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {                        // hi + lo is exact (<= 24 significant bits), as in load8
-                    v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                    v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                    for (int j = 0; j < 4; ++j) {
+                        v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                        v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                    }
+                    float4* d = reinterpret_cast<float4*>(of32 + off);
+                    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    d[1] = make_float4(v[4], v[5], v[6], v[7]);
                 }
-                float4* d = reinterpret_cast<float4*>(of32 + off);
-                d[0] = make_float4(v[0], v[1], v[2], v[3]);
-                d[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
         __syncthreads();
@@ -788,15 +844,22 @@ extern "C" int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, i
                       outh > 0 && outw > 0,
                   "frcnn_roi_pool: bad arguments");
     FRCNN_REQUIRE(!out_lo || out_hi, "frcnn_roi_pool: out_lo without out_hi");
-    FRCNN_REQUIRE(outw < kRoiMaxBins, "frcnn_roi_pool: outw must be < %d", kRoiMaxBins);
-    const long blocks = (long)R_cap * outh;
-    // CTA size: the row's outw * C/8 items in equal rounds (7 x 64 items: 2 rounds of 224 threads; with 256 threads the second
-    // round ran three-quarters full and the idle warps waited at the row's barrier -- ncu: barrier = the second stall reason)
-    const int items = outw * (C / 8), rounds = (items + kRoiMaxThreads - 1) / kRoiMaxThreads;
-    const int threads = min(kRoiMaxThreads, (((items + rounds - 1) / rounds + 31) / 32) * 32);
-    FRCNN_CUDA_OK(launch_pdl(roi_pool_kernel, dim3((unsigned)(blocks < 148l * 32 ? blocks : 148l * 32)), dim3(threads), 0, (cudaStream_t)stream,
-                             (const __nv_bfloat16*)feat_hi, (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw,
-                             scale, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32));
+    FRCNN_REQUIRE(outw < kRoiMaxBins && outh < kRoiMaxBins, "frcnn_roi_pool: outh and outw must be < %d", kRoiMaxBins);
+    int c8_per_cta = 1;                                      // a power of two: the slice's channel groups are contiguous
+    while (2 * c8_per_cta <= C / 8 && 2 * c8_per_cta * outw <= kRoiColMaxThreads) c8_per_cta *= 2;
+    const int slices = (C / 8 + c8_per_cta - 1) / c8_per_cta;
+    const int threads = ((outw * c8_per_cta + 31) / 32) * 32;
+    const long ctas = (long)R_cap * slices;
+    const dim3 grid((unsigned)(ctas < 148l * 64 ? ctas : 148l * 64));
+    if (feat_lo) {
+        FRCNN_CUDA_OK(launch_pdl(roi_pool_col_kernel<true>, grid, dim3(threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)feat_hi,
+                                 (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw, scale, (__nv_bfloat16*)out_hi,
+                                 (__nv_bfloat16*)out_lo, out_f32, c8_per_cta, slices));
+    } else {
+        FRCNN_CUDA_OK(launch_pdl(roi_pool_col_kernel<false>, grid, dim3(threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)feat_hi,
+                                 (const __nv_bfloat16*)feat_lo, H, W, C, rois, count, R_cap, outh, outw, scale, (__nv_bfloat16*)out_hi,
+                                 (__nv_bfloat16*)out_lo, out_f32, c8_per_cta, slices));
+    }
     return FRCNN_OK;
 }
 

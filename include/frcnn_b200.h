@@ -211,7 +211,7 @@ int frcnn_maxpool2x2_ceil(const void* x_hi, const void* x_lo, int H, int W, int 
 /* F.roi_pooling_2d(feature_map, [0|rois], outh, outw, scale) (models/faster_rcnn.py:123-126), Caffe
  * semantics.  feat [H,W,C] bf16 hi(/lo); rois [R_cap,4] fp32; *count valid rows (NULL = R_cap).
  * out_hi/out_lo: [R_cap, outh*outw, C] bf16 (row = one RoI, K order (ph,pw,c)); rows >= count are 0.
- * out_f32 (optional): same layout in fp32. */
+ * out_f32 (optional): same layout in fp32.  outh, outw < 32; C a multiple of 8. */
 int frcnn_roi_pool(const void* feat_hi, const void* feat_lo, int H, int W, int C, const float* rois,
                    const int* count, int R_cap, int outh, int outw, float scale, void* out_hi, void* out_lo,
                    float* out_f32, void* stream);
