@@ -339,9 +339,10 @@ def test_maxpool_ceil(ops, precision):
     assert got.shape == (64, 19, 32) and np.array_equal(got, want)
 
 
-# (C, H, W): 64 = half a 128-channel slice of the window-staged kernel, 192 = one and a half, 512 = the headline trunk,
-# W = 100 > 96 = the per-bin gather kernel that wide feature maps keep; "neg" = features that are NOT clipped at zero
-# (an all-negative window must give its negative maximum, an empty bin 0)
+# (C, H, W): 64 = 8 channel groups per CTA, 192 = 24 groups (a slice of 16 + a partial one), 512 = the headline trunk (one CTA of
+# 7 x 64 threads per RoI), W = 100 = a map wider than the headline one; "neg" = features that are NOT clipped at zero: the
+# kernel takes the maximum on packed (hi, lo) bf16 pairs, which must order negative values and negative lo parts correctly
+# (an all-negative window gives its negative maximum, an empty bin 0)
 @pytest.mark.parametrize("shape", [(64, 38, 63, "relu"), (192, 21, 33, "neg"), (512, 38, 63, "relu"), (64, 30, 100, "neg")])
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
 def test_roi_pool_exact(ops, precision, shape):
