@@ -218,11 +218,13 @@ def hbm_fractions(tj, table, peak_hbm):
             mb, ms = gl[idx]["dram_mb"], table[idx][1]
             out[name] = {"dram_mb_ncu": mb, "ms_live": round(ms, 4), "gbs": round(mb / ms, 1),
                          "frac_of_hbm_peak": round(mb / ms / peak_hbm, 3)}
-    for name, key in (("pack_image_c8", "frcnn::pack_image_c8_kernel"), ("roi_pool", "frcnn::roi_pool_kernel")):
-        e = (tj.get("per_kernel") or {}).get(key)
-        if e:
-            out[name] = {"dram_mb_ncu": e["dram_mb"], "us_under_ncu": e["us"], "gbs": round(e["dram_mb"] / e["us"] * 1e3, 1),
-                         "frac_of_hbm_peak": round(e["dram_mb"] / e["us"] * 1e3 / peak_hbm, 3)}
+    for name, sub in (("pack_image_c8", "pack_image_c8_kernel"), ("roi_pool", "roi_pool")):
+        for key, e in (tj.get("per_kernel") or {}).items():
+            if sub in key:
+                out[name] = {"kernel": key.replace("void ", "").replace("frcnn::", ""), "dram_mb_ncu": e["dram_mb"], "us_under_ncu": e["us"],
+                             "gbs": round(e["dram_mb"] / e["us"] * 1e3, 1),
+                             "frac_of_hbm_peak": round(e["dram_mb"] / e["us"] * 1e3 / peak_hbm, 3)}
+                break
     return out
 
 
