@@ -294,9 +294,11 @@ __global__ void maxpool_kernel(const __nv_bfloat16* xh, const __nv_bfloat16* xl,
 // The maximum is taken on the PACKED bf16 pairs, not on converted floats.  A feature value is v = hi + lo with hi = RN_bf16(v)
 // and |lo| <= ulp(hi)/2 (split_bf16), and rounding is monotone, so v_a > v_b  <=>  hi_a > hi_b, or hi_a == hi_b and lo_a > lo_b:
 // the maximum of v over a window is the lexicographic maximum of (hi, lo) (max.bf16x2 / set.{gt,eq}.u32.bf16x2 on two
-// channels per instruction).  The result IS one input pixel's (hi, lo) pair, so it is stored as it is -- the same bits the
-// float formulation produced (max of the floats, then split_bf16 of it: the split of hi + lo gives hi and lo back), without
-// the unpack / add per loaded pixel and the 8 float -> bf16 pair conversions per output item.
+// channels per instruction).  The result IS one input pixel's (hi, lo) pair and is stored as it is: its VALUE hi + lo is
+// exactly what the float formulation produced (max of the floats), without the unpack / add per loaded pixel and the 8
+// float -> bf16 pair conversions per output item.  (The float formulation re-split the maximum; the re-split of hi + lo gives
+// the same pair back except when lo is exactly +-ulp(hi)/2 -- a rounding midpoint, 0.08 % of random values -- where it may
+// name the same value by its other neighbour: tests/test_host_cpu.py::test_packed_pair_maximum_is_the_maximum_of_the_values.)
 //
 // History of this kernel, all variants bit-exact and measured on the same workload (profiles/r02_roi_pool_window_experiment_negative.txt):
 // per-bin gather, float compares 25 us; the same on packed pairs 26 us (a third fewer instructions, same time: ncu shows no

@@ -157,3 +157,50 @@ def test_bench_traffic_record_is_reproducible_from_the_committed_ncu_launch_list
     import bench
     frac = bench.hbm_fractions(got, [("layer", 0.1, 1.0)] * len(got["gemm_launches"]), 6571.9)
     assert {"conv1_1", "fc6", "pack_image_c8", "roi_pool"} <= set(frac) and 0 < frac["fc6"]["frac_of_hbm_peak"] < 1
+
+
+def test_packed_pair_maximum_is_the_maximum_of_the_values():
+    """What roi_pool_col_kernel relies on (csrc/head_ops.cu, 'RoI max pooling'): an activation is stored as v = hi + lo with
+    hi = RN_bf16(v), lo = RN_bf16(v - hi), so |lo| <= ulp(hi)/2.  (1) hi + lo is exact in float32; (2) the order of the values is
+    the lexicographic order of (hi, lo) -- equal values may have two different pairs (lo = +-ulp/2 exactly: v is a rounding
+    midpoint, reachable from either neighbour), and only then; (3) the streaming fold the kernel uses (h' = max(h, b.h),
+    l' = b.h > h ? b.l : b.h == h ? max(l, b.l) : l) returns a pair whose VALUE is the maximum, for any visiting order."""
+    f32 = np.float32
+
+    def rn_bf16(x):
+        u = np.asarray(x, f32).view(np.uint32).astype(np.uint64)
+        return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32).view(f32)
+
+    def split(x):
+        hi = rn_bf16(x)
+        return hi, rn_bf16(np.asarray(x, f32) - hi)
+
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.standard_normal(200000).astype(f32) * f32(3), rng.uniform(-1e-3, 1e-3, 50000).astype(f32),
+                        (rng.integers(-4096, 4096, 50000) / 8).astype(f32),          # many ties in hi, exact midpoints
+                        np.array([0.0, -0.0, 257.0, 258.0, 255.0, -257.0, 1.0, 1.00390625, 0.99609375], f32)])
+    hi, lo = split(x)
+    v = hi + lo
+    assert np.array_equal(v.astype(np.float64), hi.astype(np.float64) + lo.astype(np.float64))            # (1) exact sum
+    ulp = np.ldexp(1.0, np.frexp(hi.astype(np.float64))[1] - 8)                                            # bf16: 8 significant bits
+    assert np.all(np.abs(lo.astype(np.float64))[hi != 0] <= ulp[hi != 0] / 2)
+    # a pair is not always the canonical split of its own value: when rounding lo lands on exactly half an ulp the value is a
+    # midpoint and its re-split may pick the other neighbour -- same value, other pair; rare
+    h2, l2 = split(v)
+    other = (h2 != hi) | (l2 != lo)
+    assert np.array_equal(h2 + l2, v) and 0 < other.sum() < 0.01 * len(x)
+    # (2) sorting by (hi, lo) sorts by value (non-strictly: the equal-valued twin pairs are neighbours)
+    order = np.lexsort((lo, hi))
+    assert np.all(np.diff(v[order].astype(np.float64)) >= 0)
+    # (3) the streaming fold over windows of random size and order, seeded with twin pairs where there are any
+    twins = np.nonzero(other)[0]
+    for k in range(300):
+        idx = rng.integers(0, len(x), size=rng.integers(1, 70))
+        if k % 3 == 0:
+            idx = np.concatenate([idx, twins[rng.integers(0, len(twins), 3)]])
+        h, l = f32(-np.inf), f32(-np.inf)
+        for i in idx:
+            bh, bl = hi[i], lo[i]
+            l = bl if bh > h else (max(l, bl) if bh == h else l)
+            h = max(h, bh)
+        assert f32(h) + f32(l) == v[idx].max()
